@@ -1,0 +1,380 @@
+// fft_core.cuh — register/shared-memory real FFT core for the acids_transforms hot path (sm_100a).
+//
+// One frame of N real samples is transformed as an M = N/2 point complex FFT of
+// z[n] = x[2n] + i x[2n+1] by T cooperating threads that each keep V = M/T complex values in
+// registers.  Passes are Stockham (self-sorting) radix-R steps: a pass reads its R inputs at the
+// fixed stride M/R and writes its outputs at stride Ns (the product of the earlier radices), so
+// after the last pass the spectrum is in natural order.  Between passes the values cross threads
+// through a swizzled shared-memory buffer private to the frame's thread group.
+//
+// The real<->half-complex "untangle" needs Z[k] together with Z[M-k].  In the pass that touches
+// the spectrum side (last pass forward, first pass inverse) butterfly j holds Z[j + q*M/R] and
+// butterfly M/R - j holds exactly the mirrored bins, so each thread takes butterflies in such
+// PAIRS and the untangle happens in registers: no extra exchange.  Butterflies 0 and M/(2R) are
+// their own mirrors; thread 0 takes both and re-routes its operands with selects.
+//
+// Everything that only depends on the thread's role (pass twiddles, untangle twiddles, analysis
+// window taps) is computed once per kernel and kept in registers across the frame loop.
+//
+// The per-thread phases are __host__ __device__ so tests/emu/emu_fft.cpp can run the very same
+// index arithmetic on the CPU (there is no GPU in the build container).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ACIDS_HD __host__ __device__ __forceinline__
+#define ACIDS_ALIGN8 __align__(8)
+#else
+#define ACIDS_HD inline
+#define ACIDS_ALIGN8 alignas(8)
+#endif
+
+namespace acids {
+
+struct ACIDS_ALIGN8 cf {
+    float x, y;
+};
+
+ACIDS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+ACIDS_HD cf operator+(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
+ACIDS_HD cf operator-(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+ACIDS_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+ACIDS_HD cf cconj(cf a) { return mk(a.x, -a.y); }
+ACIDS_HD cf mul_pi(cf a) { return mk(-a.y, a.x); }   // a * (+i)
+ACIDS_HD cf mul_mi(cf a) { return mk(a.y, -a.x); }   // a * (-i)
+ACIDS_HD cf csel(bool p, cf a, cf b) { return mk(p ? a.x : b.x, p ? a.y : b.y); }
+
+// a * e^{-+ 2 pi i Q / R}  (forward: minus).  Q, R compile-time, R | 32, 0 <= Q < R/2.
+template <int R, int Q, bool INV>
+ACIDS_HD cf mul_root(cf a) {
+    constexpr int t = Q * (32 / R);
+    if (t == 0) return a;
+    if (t == 8) return INV ? mul_pi(a) : mul_mi(a);
+    // literal constants so they fold into FFMA immediates
+    constexpr float c = (t == 1) ? 0.980785280f : (t == 2) ? 0.923879533f : (t == 3) ? 0.831469612f :
+                        (t == 4) ? 0.707106781f : (t == 5) ? 0.555570233f : (t == 6) ? 0.382683432f :
+                        (t == 7) ? 0.195090322f : (t == 9) ? -0.195090322f : (t == 10) ? -0.382683432f :
+                        (t == 11) ? -0.555570233f : (t == 12) ? -0.707106781f : (t == 13) ? -0.831469612f :
+                        (t == 14) ? -0.923879533f : -0.980785280f;
+    constexpr float s = (t == 1) ? 0.195090322f : (t == 2) ? 0.382683432f : (t == 3) ? 0.555570233f :
+                        (t == 4) ? 0.707106781f : (t == 5) ? 0.831469612f : (t == 6) ? 0.923879533f :
+                        (t == 7) ? 0.980785280f : (t == 9) ? 0.980785280f : (t == 10) ? 0.923879533f :
+                        (t == 11) ? 0.831469612f : (t == 12) ? 0.707106781f : (t == 13) ? 0.555570233f :
+                        (t == 14) ? 0.382683432f : 0.195090322f;
+    return INV ? mk(a.x * c - a.y * s, a.y * c + a.x * s) : mk(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+
+// In-place radix-R DFT of a[0..R), natural-order output.  b[q] = sum_r a[r] e^{-+2 pi i r q / R}.
+template <int R, bool INV>
+struct Dft;
+
+template <bool INV>
+struct Dft<1, INV> {
+    static ACIDS_HD void run(cf*) {}
+};
+
+template <bool INV>
+struct Dft<2, INV> {
+    static ACIDS_HD void run(cf* a) {
+        cf t = a[0];
+        a[0] = t + a[1];
+        a[1] = t - a[1];
+    }
+};
+
+template <bool INV>
+struct Dft<4, INV> {
+    static ACIDS_HD void run(cf* a) {
+        cf t0 = a[0] + a[2], t1 = a[0] - a[2], t2 = a[1] + a[3];
+        cf d = a[1] - a[3];
+        cf t3 = INV ? mul_pi(d) : mul_mi(d);
+        a[0] = t0 + t2;
+        a[2] = t0 - t2;
+        a[1] = t1 + t3;
+        a[3] = t1 - t3;
+    }
+};
+
+template <int R, int Q, bool INV>
+struct Combine {
+    static ACIDS_HD void run(cf* a, const cf* e, const cf* o) {
+        cf t = mul_root<R, Q, INV>(o[Q]);
+        a[Q] = e[Q] + t;
+        a[Q + R / 2] = e[Q] - t;
+        Combine<R, Q + 1, INV>::run(a, e, o);
+    }
+};
+template <int R, bool INV>
+struct Combine<R, R / 2, INV> {
+    static ACIDS_HD void run(cf*, const cf*, const cf*) {}
+};
+
+template <int R, bool INV>
+struct Dft {
+    static ACIDS_HD void run(cf* a) {
+        cf e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) {
+            e[i] = a[2 * i];
+            o[i] = a[2 * i + 1];
+        }
+        Dft<R / 2, INV>::run(e);
+        Dft<R / 2, INV>::run(o);
+        Combine<R, 0, INV>::run(a, e, o);
+    }
+};
+
+// (cos, sin)(2 pi num / den), accurate (computed once per kernel, not per frame)
+ACIDS_HD cf unit(int num, int den) {
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * (float)num / (float)den, &s, &c);
+#else
+    double a = 2.0 * 3.14159265358979323846 * (double)num / (double)den;
+    s = (float)sin(a);
+    c = (float)cos(a);
+#endif
+    return mk(c, s);
+}
+
+// Shared-memory index swizzle for the exchange that follows pass P (pad one slot every 2^PADLOG).
+template <int PADLOG>
+ACIDS_HD int swz(int i) {
+    return i + (i >> PADLOG);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plan: N real points, T threads per frame, up to 4 passes.  For the forward transform the LAST
+// pass is the paired one (needs an even butterfly count per thread); for the inverse the FIRST.
+// ---------------------------------------------------------------------------------------------
+template <int N_, int T_, int R0_, int R1_, int R2_ = 1, int R3_ = 1>
+struct Plan {
+    static constexpr int N = N_;
+    static constexpr int M = N_ / 2;
+    static constexpr int F = N_ / 2 + 1;
+    static constexpr int T = T_;
+    static constexpr int V = M / T_;
+    static constexpr int NP = (R3_ > 1) ? 4 : ((R2_ > 1) ? 3 : 2);
+    static constexpr int PADLOG = 4;
+    static constexpr int SMEM_CF = M + (M >> PADLOG) + 1;   // exchange buffer, complex slots
+    static_assert(R0_ * R1_ * R2_ * R3_ == M, "radices must multiply to N/2");
+    static_assert(M % T_ == 0, "T must divide N/2");
+    static constexpr int radix(int p) { return p == 0 ? R0_ : (p == 1 ? R1_ : (p == 2 ? R2_ : R3_)); }
+    static constexpr int ns(int p) {
+        int s = 1;
+        for (int i = 0; i < p; ++i) s *= radix(i);
+        return s;
+    }
+    static constexpr int nb(int p) { return M / radix(p); }          // butterflies in pass p
+    static constexpr int bpt(int p) { return nb(p) / T_; }           // butterflies per thread
+    // twiddle storage: pass p >= 1 keeps (R-1) factors per butterfly it owns
+    static constexpr int tw_count(int p) { return p == 0 ? 0 : bpt(p) * (radix(p) - 1); }
+    static constexpr int tw_off(int p) {
+        int s = 0;
+        for (int i = 0; i < p; ++i) s += tw_count(i);
+        return s;
+    }
+    static constexpr int TWN = tw_off(NP) > 0 ? tw_off(NP) : 1;
+};
+
+// Index helpers of the paired pass (radix R, nb = M/R butterflies, pair c of thread tid).
+template <class P, int PASS>
+struct Pairing {
+    static constexpr int R = P::radix(PASS);
+    static constexpr int NB = P::nb(PASS);
+    static constexpr int PC = P::bpt(PASS) / 2;   // pairs per thread
+    static_assert(P::bpt(PASS) % 2 == 0, "paired pass needs an even butterfly count per thread");
+    static ACIDS_HD int ja(int tid, int c) { return tid + P::T * c; }
+    static ACIDS_HD int jb(int tid, int c) {
+        int pi = tid + P::T * c;
+        return pi == 0 ? NB / 2 : NB - pi;
+    }
+    // bin index of untangle slot s of pair c: X[k1] and X[M - k1] come out of it
+    static ACIDS_HD int k1(int tid, int c, int s) {
+        int pi = tid + P::T * c;
+        if (pi != 0) return pi + s * NB;
+        return s < R / 2 ? s * NB : NB / 2 + (s - R / 2) * NB;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread state and phases.  INV = false: real -> half-complex; INV = true: the reverse.
+// v[] (V complex registers) is owned by the caller so that it can be shared with the epilogue.
+// ---------------------------------------------------------------------------------------------
+template <class P, bool INV>
+struct FrameFFT {
+    static constexpr int PAIRED = INV ? 0 : P::NP - 1;
+    using PR = Pairing<P, PAIRED>;
+    cf tw[P::TWN];        // pass twiddles (already conjugated for INV)
+    cf wk[P::V / 2];      // untangle twiddles e^{-2 pi i k1 / N} per (pair, slot); conj for INV
+    int tid;
+
+    template <int PASS>
+    ACIDS_HD void init_pass() {
+        constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = P::bpt(PASS);
+        if (PASS > 0) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                int j;
+                if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
+                else j = tid + P::T * b;
+                int k = j % NS;
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    cf u = unit((r * k) % (NS * R), NS * R);
+                    tw[P::tw_off(PASS) + b * (R - 1) + (r - 1)] = INV ? u : cconj(u);
+                }
+            }
+        }
+    }
+
+    ACIDS_HD void init(int tid_) {
+        tid = tid_;
+        init_pass<0>();
+        init_pass<1>();
+        if (P::NP > 2) init_pass<(P::NP > 2 ? 2 : 0)>();
+        if (P::NP > 3) init_pass<(P::NP > 3 ? 3 : 0)>();
+#pragma unroll
+        for (int c = 0; c < PR::PC; ++c)
+#pragma unroll
+            for (int s = 0; s < PR::R; ++s) {
+                cf u = unit(PR::k1(tid, c, s), P::N);
+                wk[c * PR::R + s] = INV ? u : cconj(u);
+            }
+    }
+
+    // element (complex index) that register v[b*R + r] of pass PASS holds BEFORE the butterfly
+    template <int PASS>
+    ACIDS_HD int in_index(int b, int r) const {
+        constexpr int NB = P::nb(PASS);
+        int j;
+        if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
+        else j = tid + P::T * b;
+        return j + r * NB;
+    }
+    // element that v[b*R + q] holds AFTER the butterfly of pass PASS
+    template <int PASS>
+    ACIDS_HD int out_index(int b, int q) const {
+        constexpr int R = P::radix(PASS), NS = P::ns(PASS);
+        int j;
+        if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
+        else j = tid + P::T * b;
+        int k = j % NS;
+        return (j - k) * R + k + q * NS;
+    }
+
+    template <int PASS>
+    ACIDS_HD void butterflies(cf* v) const {
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (PASS > 0) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], tw[P::tw_off(PASS) + b * (R - 1) + (r - 1)]);
+            }
+            Dft<R, INV>::run(v + b * R);
+        }
+    }
+
+    template <int PASS>
+    ACIDS_HD void store(const cf* v, cf* s) const {
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int q = 0; q < R; ++q) s[swz<P::PADLOG>(out_index<PASS>(b, q))] = v[b * R + q];
+    }
+
+    template <int PASS>
+    ACIDS_HD void load(cf* v, const cf* s) const {
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b * R + r] = s[swz<P::PADLOG>(in_index<PASS>(b, r))];
+    }
+
+    // ---- forward untangle (after the paired last pass): v holds Z, produce X -------------------
+    // o1[c*R+s] = X[k1(c,s)], o2[c*R+s] = X[M - k1(c,s)]; extra = X[M/2] (meaningful on tid 0 only).
+    // Z must be the FFT of z[n] = (x[2n] + i x[2n+1]) / 2: the caller folds the 1/2 of the
+    // even/odd split into the analysis window.  DC and Nyquist get an exact +0 imaginary part,
+    // like the reference's r2c transform (their phase is 0 or +pi, never -pi).
+    ACIDS_HD void untangle_fwd(const cf* v, cf* o1, cf* o2, cf& extra) const {
+        constexpr int R = PR::R;
+#pragma unroll
+        for (int c = 0; c < PR::PC; ++c) {
+            const cf* va = v + (2 * c) * R;
+            const cf* vb = v + (2 * c + 1) * R;
+            const bool sp = (tid + P::T * c) == 0;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                cf A = va[s], Bv = vb[R - 1 - s];
+                if (c == 0) {   // only pair 0 can be the self-mirrored one
+                    if (s == 0) Bv = csel(sp, va[0], Bv);
+                    else if (s < R / 2) Bv = csel(sp, va[R - s], Bv);
+                    else {
+                        A = csel(sp, vb[s - R / 2], A);
+                        Bv = csel(sp, vb[3 * R / 2 - 1 - s], Bv);
+                    }
+                }
+                cf E = mk(A.x + Bv.x, A.y - Bv.y);       // A + conj(B)
+                cf O = mk(A.y + Bv.y, Bv.x - A.x);       // -i (A - conj(B))
+                cf Pm = cmul(O, wk[c * R + s]);
+                cf x1 = E + Pm, x2 = cconj(E - Pm);
+                if (c == 0 && s == 0) {
+                    x1.y = sp ? 0.f : x1.y;
+                    x2.y = sp ? 0.f : x2.y;
+                }
+                o1[c * R + s] = x1;
+                o2[c * R + s] = x2;
+            }
+            if (c == 0) extra = mk(2.f * va[R / 2].x, -2.f * va[R / 2].y);
+        }
+    }
+
+    // ---- inverse pre-tangle (before the paired first pass): A = X[k1], Bx = X[M-k1] ------------
+    // in1/in2 laid out like o1/o2 above; extra = X[M/2].  Produces v = 2 Z (unnormalised).
+    ACIDS_HD void pretangle_inv(const cf* in1, const cf* in2, cf extra, cf* v) const {
+        constexpr int R = PR::R;
+#pragma unroll
+        for (int c = 0; c < PR::PC; ++c) {
+            cf za[R], zb[R];
+            const bool sp = (tid + P::T * c) == 0;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                cf A = in1[c * R + s], Bx = in2[c * R + s];
+                if (c == 0 && s == 0) {   // c2r ignores the imaginary parts of DC and Nyquist
+                    A.y = sp ? 0.f : A.y;
+                    Bx.y = sp ? 0.f : Bx.y;
+                }
+                cf E2 = mk(A.x + Bx.x, A.y - Bx.y);          // A + conj(Bx)
+                cf P2 = mk(A.x - Bx.x, A.y + Bx.y);          // A - conj(Bx)
+                cf O2 = cmul(P2, wk[c * R + s]);             // conj(W^k) P2
+                cf iO = mul_pi(O2);
+                za[s] = E2 + iO;
+                zb[s] = cconj(E2 - iO);
+            }
+            cf* va = v + (2 * c) * R;
+            cf* vb = v + (2 * c + 1) * R;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                cf ga = za[q], gb = zb[R - 1 - q];
+                if (c == 0) {
+                    cf sa, sb;
+                    if (q == 0) sa = za[0];
+                    else if (q < R / 2) sa = za[q];
+                    else if (q == R / 2) sa = mk(2.f * extra.x, -2.f * extra.y);
+                    else sa = zb[R - q];
+                    if (q < R / 2) sb = za[q + R / 2];
+                    else sb = zb[3 * R / 2 - 1 - q];
+                    ga = csel(sp, sa, ga);
+                    gb = csel(sp, sb, gb);
+                }
+                va[q] = ga;
+                vb[q] = gb;
+            }
+        }
+    }
+};
+
+}  // namespace acids

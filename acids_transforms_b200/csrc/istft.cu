@@ -1,0 +1,403 @@
+// istft.cu — inverse real FFT fused with synthesis-window overlap-add and envelope normalisation.
+// Rows A15, A16, A17 of SURVEY.md §8(a).
+//
+// Atomic-free segmented accumulation: a CTA owns a contiguous span of OUTPUT samples of one clip
+// (a chunk of frames [ta, tb)), transforms the frames that touch that span (ceil(n_fft/hop) - 1 halo
+// frames at the chunk start are recomputed rather than exchanged), parks each windowed frame in a
+// shared-memory ring slot, and after every round of G frames gathers the samples that have now seen
+// all of their contributing frames: y[n] = sum_t ring[t][n - t*hop] / sum_t g^2[n - t*hop], summed in
+// ascending t like torch.istft's col2im.  Nothing is scattered, no atomics, no global scratch.
+//
+// HBM traffic per frame: (n_fft/2+1)*8 B in, hop*4 B out.
+#include "common.cuh"
+#include "plans.cuh"
+
+namespace acids {
+
+struct InvParams {
+    const cf* X;
+    int64_t B;
+    int n_frames;
+    int hop;
+    const float* window;
+    float* out;
+    int64_t out_len;        // hop * (n_frames - 1) for the centred istft
+    int trim;               // n_fft / 2
+    int chunk_frames;
+    int chunks_per_clip;
+    int ovc;                // ceil(n_fft / hop)
+    int ring;               // G + ovc - 1 slots
+};
+
+// Spectrum row -> N windowed time samples, left in v[] in the natural order of the last pass.
+template <class P, int THREADS>
+__device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, const cf* __restrict__ row, bool valid,
+                                              cf* v, cf* s, int g) {
+    constexpr int M = P::M, T = P::T, V = P::V;
+    using PR = typename FrameFFT<P, true>::PR;
+    auto gsync = [&]() { group_sync<T, THREADS>(g); };
+    cf i1[V / 2], i2[V / 2], ex;
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < PR::PC; ++c)
+#pragma unroll
+            for (int q = 0; q < PR::R; ++q) {
+                const int k = PR::k1(fft.tid, c, q);
+                const float2 a = ldg_stream2(reinterpret_cast<const float2*>(row + k));
+                const float2 d = ldg_stream2(reinterpret_cast<const float2*>(row + (M - k)));
+                i1[c * PR::R + q] = mk(a.x, a.y);
+                i2[c * PR::R + q] = mk(d.x, d.y);
+            }
+        const float2 e = __ldg(reinterpret_cast<const float2*>(row + M / 2));
+        ex = mk(e.x, e.y);
+    } else {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) i1[i] = i2[i] = mk(0.f, 0.f);
+        ex = mk(0.f, 0.f);
+    }
+    fft.pretangle_inv(i1, i2, ex, v);
+    fft.template butterflies<0>(v);
+    gsync();
+    fft.template store<0>(v, s);
+    gsync();
+    fft.template load<1>(v, s);
+    fft.template butterflies<1>(v);
+    if constexpr (P::NP > 2) {
+        gsync();
+        fft.template store<1>(v, s);
+        gsync();
+        fft.template load<2>(v, s);
+        fft.template butterflies<2>(v);
+    }
+    if constexpr (P::NP > 3) {
+        gsync();
+        fft.template store<2>(v, s);
+        gsync();
+        fft.template load<3>(v, s);
+        fft.template butterflies<3>(v);
+    }
+}
+
+template <class P, int THREADS>
+__global__ void __launch_bounds__(THREADS) istft_ola_kernel(const InvParams p) {
+    constexpr int N = P::N, T = P::T, V = P::V, G = THREADS / T;
+    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP);
+    using FFT = FrameFFT<P, true>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / T, tid = threadIdx.x % T;
+    cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
+    float* ring = reinterpret_cast<float*>(reinterpret_cast<cf*>(smem_raw) + (size_t)G * P::SMEM_CF);
+    float* g2 = ring + (size_t)p.ring * N;
+
+    FFT fft;
+    fft.init(tid);
+    // synthesis window taps of this thread's output samples, with irfft's 1/N folded in
+    float2 win[V];
+#pragma unroll
+    for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+            const int n = fft.template out_index<LP>(b, q);
+            win[b * RL + q] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
+        }
+    for (int i = threadIdx.x; i < N; i += THREADS) {
+        const float w = __ldg(p.window + i);
+        g2[i] = w * w;
+    }
+
+    const int64_t clip = blockIdx.x / p.chunks_per_clip;
+    const int ch = blockIdx.x % p.chunks_per_clip;
+    const int ta = ch * p.chunk_frames;
+    const int tb = min(p.n_frames, ta + p.chunk_frames);
+    const int hop = p.hop;
+    // padded-sample span owned by this CTA
+    const int64_t own_lo = (int64_t)ta * hop;
+    const int64_t own_hi = (tb == p.n_frames) ? (int64_t)(p.n_frames - 1) * hop + N : (int64_t)tb * hop;
+    const int t_start = max(0, ta - (p.ovc - 1));
+    int64_t emitted = own_lo;
+    const cf* __restrict__ Xc = p.X + clip * (int64_t)p.n_frames * P::F;
+    float* __restrict__ outc = p.out + clip * p.out_len;
+    __syncthreads();
+
+    for (int tr = t_start; tr < tb; tr += G) {
+        const int t = tr + g;
+        const bool valid = t < tb;
+        cf v[V];
+        inverse_frame<P, THREADS>(fft, Xc + (int64_t)t * P::F, valid, v, s, g);
+        if (valid) {
+            float2* slot = reinterpret_cast<float2*>(ring + (size_t)(t % p.ring) * N);
+#pragma unroll
+            for (int b = 0; b < BL; ++b)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int n = fft.template out_index<LP>(b, q);
+                    slot[n] = make_float2(v[b * RL + q].x * win[b * RL + q].x, v[b * RL + q].y * win[b * RL + q].y);
+                }
+        }
+        __syncthreads();
+        // gather every sample that no later frame can touch
+        const int t_done = min(tr + G, tb) - 1;
+        const int64_t hi = (t_done == p.n_frames - 1) ? own_hi : min(own_hi, (int64_t)(t_done + 1) * hop);
+        for (int64_t np = emitted + threadIdx.x; np < hi; np += THREADS) {
+            const int64_t num = np - N + hop;
+            const int t_lo = num > 0 ? (int)(num / hop) : 0;
+            const int t_hi = min((int64_t)p.n_frames - 1, np / hop);
+            float acc = 0.f, env = 0.f;
+            for (int tt = t_lo; tt <= t_hi; ++tt) {
+                const int m = (int)(np - (int64_t)tt * hop);
+                acc += ring[(size_t)(tt % p.ring) * N + m];
+                env += g2[m];
+            }
+            const int64_t n = np - p.trim;
+            if (n >= 0 && n < p.out_len) stg_stream1(outc + n, acc / env);
+        }
+        if (hi > emitted) emitted = hi;
+        __syncthreads();
+    }
+}
+
+// ---- per-frame inverse without overlap-add: irfft(X) * window (RealtimeSTFT.invert) ------------
+struct InvFramesParams {
+    const cf* X;
+    int64_t rows;
+    const float* window;
+    float* out;
+};
+
+template <class P, int THREADS>
+__global__ void __launch_bounds__(THREADS) irfft_frames_kernel(const InvFramesParams p) {
+    constexpr int N = P::N, T = P::T, V = P::V, G = THREADS / T;
+    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP);
+    using FFT = FrameFFT<P, true>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / T, tid = threadIdx.x % T;
+    cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
+    FFT fft;
+    fft.init(tid);
+    float2 win[V];
+#pragma unroll
+    for (int b = 0; b < BL; ++b)
+#pragma unroll
+        for (int q = 0; q < RL; ++q) {
+            const int n = fft.template out_index<LP>(b, q);
+            win[b * RL + q] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
+        }
+    const int64_t units = (p.rows + G - 1) / G;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int64_t r = u * G + g;
+        const bool valid = r < p.rows;
+        cf v[V];
+        inverse_frame<P, THREADS>(fft, p.X + r * (int64_t)P::F, valid, v, s, g);
+        if (valid) {
+            float2* dst = reinterpret_cast<float2*>(p.out + r * (int64_t)N);
+#pragma unroll
+            for (int b = 0; b < BL; ++b)
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int n = fft.template out_index<LP>(b, q);
+                    stg_stream2(dst + n, v[b * RL + q].x * win[b * RL + q].x, v[b * RL + q].y * win[b * RL + q].y);
+                }
+        }
+        group_sync<T, THREADS>(g);   // next frame's store<0> must not overtake this frame's last reads
+    }
+}
+
+// ---- overlap-add from frames in global memory (fallback for huge n_fft, and the streaming OLA) ----
+struct OlaParams {
+    const float* frames;    // [B, n, N]
+    int64_t B;
+    int n;
+    int N, hop;
+    const float* window;    // g for the envelope, or nullptr (no envelope)
+    const float* carry_in;  // [B, keep] or nullptr
+    int64_t keep;           // carried tail length (streaming) or 0
+    float gain;             // divide by this when window == nullptr
+    int64_t trim;           // leading samples to drop
+    float* out;             // [B, out_len]
+    int64_t out_len;
+    float* carry_out;       // [B, keep] or nullptr
+};
+
+__global__ void ola_gather_kernel(const OlaParams p) {
+    const int64_t total = (int64_t)(p.n - 1) * p.hop + p.N;
+    const int64_t clip = blockIdx.y;
+    const float* __restrict__ fr = p.frames + clip * (int64_t)p.n * p.N;
+    for (int64_t np = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; np < total; np += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t num = np - p.N + p.hop;
+        const int t_lo = num > 0 ? (int)(num / p.hop) : 0;
+        const int t_hi = (int)min((int64_t)p.n - 1, np / p.hop);
+        float acc = (p.carry_in && np < p.keep) ? __ldg(p.carry_in + clip * p.keep + np) : 0.f;
+        float env = 0.f;
+        for (int tt = t_lo; tt <= t_hi; ++tt) {
+            const int m = (int)(np - (int64_t)tt * p.hop);
+            acc += __ldg(fr + (int64_t)tt * p.N + m);
+            if (p.window) {
+                const float w = __ldg(p.window + m);
+                env += w * w;
+            }
+        }
+        const int64_t n = np - p.trim;
+        if (n >= 0 && n < p.out_len) p.out[clip * p.out_len + n] = p.window ? acc / env : acc / p.gain;
+        else if (p.carry_out && n >= p.out_len && n - p.out_len < p.keep) p.carry_out[clip * p.keep + (n - p.out_len)] = acc;
+    }
+}
+
+template <class P>
+struct InvLaunch {
+    static constexpr int THREADS = P::T > 256 ? P::T : 256;
+    static constexpr int G = THREADS / P::T;
+    static size_t smem_ola(int ovc) {
+        return (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float);
+    }
+    static int ola(InvParams p, cudaStream_t st) {
+        auto kern = istft_ola_kernel<P, THREADS>;
+        const size_t smem = smem_ola(p.ovc);
+        static size_t reserved = 0;
+        if (smem > reserved) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                set_error("istft_ola: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+                return ACIDS_ECUDA;
+            }
+            reserved = smem;
+        }
+        p.ring = G + p.ovc - 1;
+        // chunking: enough CTAs for ~8 waves, chunks no shorter than 8 overlaps, multiples of G
+        int64_t want = 8LL * 2 * num_sms();
+        int cpc = (int)((want + p.B - 1) / (p.B > 0 ? p.B : 1));
+        int max_cpc = p.n_frames / (8 * p.ovc);
+        if (max_cpc < 1) max_cpc = 1;
+        if (cpc > max_cpc) cpc = max_cpc;
+        if (cpc < 1) cpc = 1;
+        int cf_ = (p.n_frames + cpc - 1) / cpc;
+        cf_ = ((cf_ + G - 1) / G) * G;
+        p.chunk_frames = cf_;
+        p.chunks_per_clip = (p.n_frames + cf_ - 1) / cf_;
+        const int64_t grid = p.B * p.chunks_per_clip;
+        if (grid == 0) return ACIDS_OK;
+        ACIDS_REQUIRE(grid < (1LL << 31), ACIDS_EINVAL, "istft_ola: grid too large");
+        kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
+        ACIDS_CHECK_LAUNCH("istft_ola");
+        return ACIDS_OK;
+    }
+    static int frames(const InvFramesParams& p, cudaStream_t st) {
+        auto kern = irfft_frames_kernel<P, THREADS>;
+        constexpr size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf);
+        static int ctas_per_sm = 0;
+        if (ctas_per_sm == 0) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                set_error("irfft_frames: cannot reserve shared memory");
+                return ACIDS_ECUDA;
+            }
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem);
+            ctas_per_sm = nb > 0 ? nb : 1;
+        }
+        const int64_t units = (p.rows + G - 1) / G;
+        if (units == 0) return ACIDS_OK;
+        int64_t grid = (int64_t)num_sms() * ctas_per_sm;
+        if (grid > units) grid = units;
+        kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
+        ACIDS_CHECK_LAUNCH("irfft_frames");
+        return ACIDS_OK;
+    }
+};
+
+static const size_t kMaxSmem = 227 * 1024;
+
+#define ACIDS_INV_SWITCH(n_fft, EXPR)                                          \
+    switch (n_fft) {                                                           \
+        case 32: { using PL = Inv32; EXPR; } break;                            \
+        case 64: { using PL = Inv64; EXPR; } break;                            \
+        case 128: { using PL = Inv128; EXPR; } break;                          \
+        case 256: { using PL = Inv256; EXPR; } break;                          \
+        case 512: { using PL = Inv512; EXPR; } break;                          \
+        case 1024: { using PL = Inv1024; EXPR; } break;                        \
+        case 2048: { using PL = Inv2048; EXPR; } break;                        \
+        case 4096: { using PL = Inv4096; EXPR; } break;                        \
+        case 8192: { using PL = Inv8192; EXPR; } break;                        \
+        case 16384: { using PL = Inv16384; EXPR; } break;                      \
+        default:                                                               \
+            set_error("n_fft=%d is not supported (power of two in [32, 16384])", n_fft); \
+            return ACIDS_ENOTSUP;                                              \
+    }
+
+static int fused_fits(int n_fft, int hop, bool& fits) {
+    const int ovc = (n_fft + hop - 1) / hop;
+    size_t need = 0;
+    ACIDS_INV_SWITCH(n_fft, need = InvLaunch<PL>::smem_ola(ovc));
+    fits = need <= kMaxSmem;
+    return ACIDS_OK;
+}
+
+static int launch_ola_gather(const OlaParams& p, cudaStream_t st) {
+    const int64_t total = (int64_t)(p.n - 1) * p.hop + p.N;
+    if (p.B == 0 || p.n == 0) return ACIDS_OK;
+    ACIDS_REQUIRE(p.B < 65536, ACIDS_EINVAL, "ola: more than 65535 clips per call");
+    int64_t gx = (total + 255) / 256;
+    if (gx > 4096) gx = 4096;
+    ola_gather_kernel<<<dim3((unsigned)gx, (unsigned)p.B), 256, 0, st>>>(p);
+    ACIDS_CHECK_LAUNCH("ola_gather");
+    return ACIDS_OK;
+}
+
+}  // namespace acids
+
+using namespace acids;
+
+extern "C" ACIDS_API int64_t acids_istft_workspace_bytes(int64_t B, int64_t n_frames, int n_fft, int hop) {
+    if (hop <= 0) return 0;
+    bool fits = true;
+    if (fused_fits(n_fft, hop, fits) != ACIDS_OK) return 0;
+    return fits ? 0 : B * n_frames * (int64_t)n_fft * (int64_t)sizeof(float);
+}
+
+extern "C" ACIDS_API int acids_irfft_frames(const float* X, int64_t rows, int n_fft, const float* window, float* out, void* stream) {
+    ACIDS_REQUIRE(X && window && out, ACIDS_EINVAL, "irfft_frames: NULL pointer");
+    ACIDS_REQUIRE(rows >= 0, ACIDS_EINVAL, "irfft_frames: negative row count");
+    InvFramesParams p{reinterpret_cast<const cf*>(X), rows, window, out};
+    ACIDS_INV_SWITCH(n_fft, return InvLaunch<PL>::frames(p, static_cast<cudaStream_t>(stream)));
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_istft_ola(const float* X, int64_t B, int64_t n_frames, int n_fft, int hop, const float* window,
+                               float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    ACIDS_REQUIRE(X && window && out, ACIDS_EINVAL, "istft_ola: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 30) && hop > 0 && hop <= n_fft, ACIDS_EINVAL,
+                  "istft_ola: bad sizes B=%lld frames=%lld hop=%d", (long long)B, (long long)n_frames, hop);
+    bool fits = true;
+    int rc = fused_fits(n_fft, hop, fits);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t out_len = (int64_t)hop * (n_frames - 1);
+    if (fits) {
+        InvParams p{};
+        p.X = reinterpret_cast<const cf*>(X); p.B = B; p.n_frames = (int)n_frames; p.hop = hop; p.window = window;
+        p.out = out; p.out_len = out_len; p.trim = n_fft / 2; p.ovc = (n_fft + hop - 1) / hop;
+        ACIDS_INV_SWITCH(n_fft, return InvLaunch<PL>::ola(p, st));
+        return ACIDS_OK;
+    }
+    // two-step fallback: frames to the caller's workspace, then a gather
+    const int64_t need = B * n_frames * (int64_t)n_fft * (int64_t)sizeof(float);
+    ACIDS_REQUIRE(workspace && workspace_bytes >= need, ACIDS_EWORKSPACE,
+                  "istft_ola: n_fft=%d hop=%d needs a %lld-byte workspace", n_fft, hop, (long long)need);
+    rc = acids_irfft_frames(X, B * n_frames, n_fft, window, static_cast<float*>(workspace), stream);
+    if (rc) return rc;
+    OlaParams q{};
+    q.frames = static_cast<const float*>(workspace); q.B = B; q.n = (int)n_frames; q.N = n_fft; q.hop = hop;
+    q.window = window; q.trim = n_fft / 2; q.out = out; q.out_len = out_len; q.gain = 1.f;
+    return launch_ola_gather(q, st);
+}
+
+extern "C" ACIDS_API int acids_ola_stream(const float* frames, int64_t B, int64_t n, int n_fft, int hop, int64_t keep,
+                                const float* carry_in, float gain, float* out, float* carry_out, void* stream) {
+    ACIDS_REQUIRE(frames && out, ACIDS_EINVAL, "ola_stream: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n >= 1 && hop > 0 && n_fft > 0 && keep >= 0, ACIDS_EINVAL, "ola_stream: bad sizes");
+    const int64_t total = (n - 1) * hop + n_fft;
+    ACIDS_REQUIRE(keep < total, ACIDS_EINVAL, "ola_stream: carry longer than the recomposed signal");
+    ACIDS_REQUIRE(gain != 0.f, ACIDS_EINVAL, "ola_stream: zero gain");
+    OlaParams q{};
+    q.frames = frames; q.B = B; q.n = (int)n; q.N = n_fft; q.hop = hop; q.window = nullptr;
+    q.carry_in = carry_in; q.keep = keep; q.gain = gain; q.trim = 0; q.out = out; q.out_len = total - keep;
+    q.carry_out = carry_out;
+    return launch_ola_gather(q, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,378 @@
+// spectral_repr.cu — representation kernels on an existing complex spectrum.
+// Rows A6, A8 (Magnitude forward / invert), A10-A13 (Phase, unwrap, IF forward / invert), A14 (polar
+// recombination) of SURVEY.md §8(a).  All HBM bound: one read of the input, one write of the output.
+#include "common.cuh"
+
+namespace acids {
+
+// ---------------------------------------------------------------------------------------------
+// Magnitude.forward on a spectrum: one warp per row; |X| staged in shared memory so that the banded
+// mel projection can read neighbouring bins.
+// ---------------------------------------------------------------------------------------------
+struct MagParams {
+    const float2* X;
+    int64_t rows;
+    int n_bins;
+    EpiParams ep;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    float* out;
+    int64_t out_row_stride;
+};
+
+__global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* val = smem + (size_t)warp * p.n_bins;
+    EpiParams ep = p.ep;
+    load_norm(p.offset_ptr, p.scale_ptr, ep.offset, ep.inv_scale);
+    const int64_t wpg = (int64_t)gridDim.x * 8;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < p.rows; r += wpg) {
+        const float2* __restrict__ row = p.X + r * p.n_bins;
+        __syncwarp();
+        for (int k = lane; k < p.n_bins; k += 32) {
+            const float2 a = ldg_stream2(row + k);
+            val[k] = sqrtf(a.x * a.x + a.y * a.y);
+        }
+        __syncwarp();
+        epilogue_row<32>(val, lane, ep, p.out + r * p.out_row_stride, 1, true);
+    }
+}
+
+// Magnitude.invert: m = contrast^-1(y * scale + offset) [zero padded] @ inverse band
+struct MagInvParams {
+    const float* y;
+    int64_t rows;
+    int n_in;
+    int64_t y_row_stride;
+    int pad_last;
+    const int32_t* meta;
+    const float* coef;
+    int n_out;
+    int contrast;
+    float eps;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    float* out;
+};
+
+__global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_val = p.n_in + p.pad_last;
+    float* val = smem + (size_t)warp * n_val;
+    const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
+    const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
+    const int64_t wpg = (int64_t)gridDim.x * 8;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < p.rows; r += wpg) {
+        const float* __restrict__ row = p.y + r * p.y_row_stride;
+        __syncwarp();
+        for (int k = lane; k < n_val; k += 32) {
+            // the zero pad is appended BEFORE the contrast inversion (spectral_repr.py:230-234)
+            const float a = k < p.n_in ? __ldg(row + k) * sc + off : 0.f;
+            val[k] = invert_contrast(a, p.contrast, p.eps);
+        }
+        __syncwarp();
+        float* __restrict__ out = p.out + r * (int64_t)p.n_out;
+        for (int m = lane; m < p.n_out; m += 32) {
+            float a;
+            if (p.meta) {
+                const int2 me = __ldg(reinterpret_cast<const int2*>(p.meta) + m);
+                const int start = me.x & 0xffff, cnt = me.x >> 16;
+                const float* c = p.coef + me.y;
+                a = 0.f;
+                for (int u = 0; u < cnt; ++u) a = fmaf(val[start + u], __ldg(c + u), a);
+            } else {
+                a = val[m];
+            }
+            stg_stream1(out + m, a);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase / unwrap / IF: one thread per (clip, bin) column walks the frames; the unwrap correction is a
+// sequential float32 running sum exactly like torch.cumsum along the frame axis (utils/misc.py:25).
+// ---------------------------------------------------------------------------------------------
+struct PhaseParams {
+    const float2* X;
+    int64_t B;
+    int n_frames, n_bins;
+    int mode, method, weighted;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    int drop_first;
+    float* out;
+    int64_t out_clip_stride, out_row_stride;
+};
+
+#define ACIDS_PI_F 3.14159265358979323846f
+#define ACIDS_2PI_F 6.28318530717958647692f
+
+__device__ __forceinline__ float unwrap_correction(float d) {
+    // utils/misc.py:19-24: ddmod = (d + pi) % 2pi - pi (python remainder); +pi when it lands on -pi going up
+    float r = fmodf(d + ACIDS_PI_F, ACIDS_2PI_F);
+    if (r < 0.f) r += ACIDS_2PI_F;
+    float dd = r - ACIDS_PI_F;
+    if (dd == -ACIDS_PI_F && d > 0.f) dd = ACIDS_PI_F;
+    return fabsf(d) < ACIDS_PI_F ? 0.f : dd - d;
+}
+
+__device__ __forceinline__ float if_weight(int t, int T) {
+    // spectral_repr.py:341-342
+    const float N = (float)T, n = (float)t;
+    const float a = (n - (N / 2.f - 1.f)) / (N / 2.f);
+    return (1.5f * N) / (N * N - 1.f) * (1.f - a * a);
+}
+
+__global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= p.B * p.n_bins) return;
+    const int64_t b = col / p.n_bins;
+    const int f = (int)(col - b * p.n_bins);
+    const float2* __restrict__ X = p.X + b * (int64_t)p.n_frames * p.n_bins + f;
+    const bool write = f >= p.drop_first;
+    float* __restrict__ out = p.out + b * p.out_clip_stride + (f - p.drop_first);
+    const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
+    const float inv = p.scale_ptr ? 1.0f / __ldg(p.scale_ptr) : 1.0f;
+    const int T = p.n_frames;
+    auto emit = [&](int t, float v) {
+        if (p.weighted) v *= if_weight(t, T);
+        if (write) stg_stream1(out + (int64_t)t * p.out_row_stride, (v - off) * inv);
+    };
+    float prev_raw = 0.f, cum = 0.f;
+    float u1 = 0.f, u2 = 0.f;   // unwrapped phase at t-1, t-2
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+        const float2 a = ldg_stream2(X + (int64_t)t * p.n_bins);
+        const float raw = atan2f(a.y, a.x);
+        if (p.mode == ACIDS_PHASE_RAW) {
+            emit(t, raw);
+            continue;
+        }
+        if (t > 0) cum += unwrap_correction(raw - prev_raw);
+        const float un = t > 0 ? raw + cum : raw;
+        prev_raw = raw;
+        if (p.mode == ACIDS_PHASE_UNWRAP) {
+            emit(t, un);
+        } else if (p.method == ACIDS_IF_FORWARD) {
+            // row 0 = phi_0, row t = (phi_t - phi_{t-1}) / 2; rows [:-1] then divided by pi
+            float v = t == 0 ? un : (un - u1) / 2.f;
+            if (t < T - 1) v = v / ACIDS_PI_F;
+            emit(t, v);
+        } else if (p.method == ACIDS_IF_BACKWARD) {
+            // row t = (phi_t - phi_{t+1}) / 2 for t < T-1, row T-1 = phi_{T-1}; rows [1:] divided by -pi
+            if (t > 0) {
+                float v = (u1 - un) / 2.f;
+                if (t - 1 >= 1) v = v / (-ACIDS_PI_F);
+                emit(t - 1, v);
+            }
+            if (t == T - 1) emit(t, t >= 1 ? un / (-ACIDS_PI_F) : un);
+        } else {
+            // central: row 0 = phi_0, row t = (phi_{t+1} - phi_{t-1}) / 4 / (2 pi), row T-1 = phi_{T-1}
+            if (t == 0) emit(0, un);
+            if (t >= 2) emit(t - 1, (un - u2) / 4.f / ACIDS_2PI_F);
+            if (t == T - 1 && t > 0) emit(t, un);
+        }
+        u2 = u1;
+        u1 = un;
+    }
+}
+
+struct PhaseInvParams {
+    const float* y;
+    int64_t B;
+    int n_frames, n_in;
+    int64_t y_clip_stride, y_row_stride;
+    int pad_last, mode, method;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    float* out;   // [B, n_frames, n_in + pad_last]
+};
+
+__global__ void __launch_bounds__(128) phase_inv_kernel(const PhaseInvParams p) {
+    const int nb = p.n_in + p.pad_last;
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= p.B * nb) return;
+    const int64_t b = col / nb;
+    const int f = (int)(col - b * nb);
+    float* __restrict__ out = p.out + b * (int64_t)p.n_frames * nb + f;
+    const int T = p.n_frames;
+    if (f >= p.n_in) {   // the zero bin appended when keep_nyquist=False (spectral_repr.py:371-374)
+        for (int t = 0; t < T; ++t) out[(int64_t)t * nb] = 0.f;
+        return;
+    }
+    const float* __restrict__ y = p.y + b * p.y_clip_stride + f;
+    const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
+    const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
+    auto den = [&](int t) { return __ldg(y + (int64_t)t * p.y_row_stride) * sc + off; };
+    if (p.mode != ACIDS_PHASE_IF) {
+        for (int t = 0; t < T; ++t) out[(int64_t)t * nb] = den(t);
+        return;
+    }
+    if (p.method == ACIDS_IF_FORWARD) {
+        // rows[:-1] *= pi; rows[1:] *= 2; cumsum over frames   (spectral_repr.py:365-367, utils/misc.py:82-86)
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            float v = den(t);
+            if (t < T - 1) v *= ACIDS_PI_F;
+            if (t >= 1) v *= 2.f;
+            acc += v;
+            out[(int64_t)t * nb] = acc;
+        }
+    } else if (p.method == ACIDS_IF_BACKWARD) {
+        // rows[1:] *= -pi; flip; rows[1:] *= 2; cumsum; flip  == suffix sum with the LAST row undoubled
+        float acc = 0.f;
+        for (int t = T - 1; t >= 0; --t) {
+            float v = den(t);
+            if (t >= 1) v *= -ACIDS_PI_F;
+            if (t < T - 1) v *= 2.f;
+            acc += v;
+            out[(int64_t)t * nb] = acc;
+        }
+    } else {
+        // central: rows[1:-1] *= 2 pi, then fint_central's two recurrences, python negative-index
+        // wrap-around included (utils/misc.py:96-104).  The column is its own scratch.
+        auto X = [&](int t) {
+            float v = den(t);
+            if (t >= 1 && t < T - 1) v *= ACIDS_2PI_F;
+            return v;
+        };
+        auto O = [&](int t) -> float& { return out[(int64_t)((t % T + T) % T) * nb]; };
+        for (int t = 0; t < T; ++t) O(t) = 0.f;
+        O(0) = X(0);
+        O(T - 1) = X(T - 1);
+        for (int i = 2; i < T; i += 2) O(i) = O(i - 2) + 4.f * X(i - 1);
+        for (int i = T - 1; i > 0; i -= 2) O(i - 2) = O(i) - 4.f * X(i - 1);
+    }
+}
+
+__global__ void polar_to_complex_kernel(const float* __restrict__ mag, const float* __restrict__ phase, int64_t n,
+                                        float2* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float s, c;
+        sincosf(__ldg(phase + i), &s, &c);
+        const float m = __ldg(mag + i);
+        stg_stream2(out + i, m * c, m * s);
+    }
+}
+
+static int check_band(const acids_band& band) {
+    ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0), ACIDS_EINVAL, "banded matrix without coefficients");
+    return ACIDS_OK;
+}
+
+}  // namespace acids
+
+using namespace acids;
+
+extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_bins, acids_band band, int contrast, float eps,
+                                  const float* offset, const float* scale, int drop_first, float* out,
+                                  int64_t out_row_stride, void* stream) {
+    ACIDS_REQUIRE(X && out, ACIDS_EINVAL, "mag_epilogue: NULL pointer");
+    ACIDS_REQUIRE(rows >= 0 && n_bins > 0 && n_bins < 65536, ACIDS_EINVAL, "mag_epilogue: bad sizes");
+    ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
+    ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
+    int rc = check_band(band);
+    if (rc) return rc;
+    if (rows == 0) return ACIDS_OK;
+    MagParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.rows = rows; p.n_bins = n_bins;
+    p.ep.meta = band.meta; p.ep.coef = band.coef; p.ep.n_cols = band.meta ? band.n_out : n_bins;
+    p.ep.contrast = contrast; p.ep.eps = eps; p.ep.drop_first = drop_first;
+    p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
+    const size_t smem = (size_t)8 * n_bins * sizeof(float);
+    static size_t reserved = 48 * 1024;
+    if (smem > reserved) {
+        ACIDS_REQUIRE(cudaFuncSetAttribute(mag_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                      ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
+        reserved = smem;
+    }
+    int64_t grid = (rows + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    mag_epilogue_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("mag_epilogue");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_mag_invert(const float* y, int64_t rows, int n_in, int64_t y_row_stride, int pad_last,
+                                acids_band inverse_band, int contrast, float eps, const float* offset,
+                                const float* scale, float* out, void* stream) {
+    ACIDS_REQUIRE(y && out, ACIDS_EINVAL, "mag_invert: NULL pointer");
+    ACIDS_REQUIRE(rows >= 0 && n_in > 0 && n_in < 65535 && (pad_last == 0 || pad_last == 1), ACIDS_EINVAL, "mag_invert: bad sizes");
+    ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
+    int rc = check_band(inverse_band);
+    if (rc) return rc;
+    if (rows == 0) return ACIDS_OK;
+    MagInvParams p{};
+    p.y = y; p.rows = rows; p.n_in = n_in; p.y_row_stride = y_row_stride; p.pad_last = pad_last;
+    p.meta = inverse_band.meta; p.coef = inverse_band.coef;
+    p.n_out = inverse_band.meta ? inverse_band.n_out : n_in + pad_last;
+    p.contrast = contrast; p.eps = eps; p.offset_ptr = offset; p.scale_ptr = scale; p.out = out;
+    const size_t smem = (size_t)8 * (n_in + pad_last) * sizeof(float);
+    static size_t reserved = 48 * 1024;
+    if (smem > reserved) {
+        ACIDS_REQUIRE(cudaFuncSetAttribute(mag_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                      ACIDS_ECUDA, "mag_invert: cannot reserve %zu B of shared memory", smem);
+        reserved = smem;
+    }
+    int64_t grid = (rows + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    mag_invert_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("mag_invert");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, int mode, int if_method,
+                               int weighted, const float* offset, const float* scale, int drop_first, float* out,
+                               int64_t out_clip_stride, int64_t out_row_stride, void* stream) {
+    ACIDS_REQUIRE(X && out, ACIDS_EINVAL, "phase_fwd: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 31) && n_bins > 0, ACIDS_EINVAL, "phase_fwd: bad sizes");
+    ACIDS_REQUIRE(mode >= 0 && mode <= 2 && if_method >= 0 && if_method <= 2, ACIDS_EINVAL, "phase_fwd: bad mode/method");
+    ACIDS_REQUIRE(!(mode == ACIDS_PHASE_IF && if_method == ACIDS_IF_CENTRAL && n_frames < 2), ACIDS_EINVAL,
+                  "phase_fwd: central differences need at least 2 frames");
+    ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
+    if (B == 0) return ACIDS_OK;
+    PhaseParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.B = B; p.n_frames = (int)n_frames; p.n_bins = n_bins;
+    p.mode = mode; p.method = if_method; p.weighted = (mode == ACIDS_PHASE_IF) ? weighted : 0;
+    p.offset_ptr = offset; p.scale_ptr = scale; p.drop_first = drop_first; p.out = out;
+    p.out_clip_stride = out_clip_stride; p.out_row_stride = out_row_stride;
+    const int64_t cols = B * n_bins;
+    phase_fwd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("phase_fwd");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_phase_inv(const float* y, int64_t B, int64_t n_frames, int n_in, int64_t y_clip_stride,
+                               int64_t y_row_stride, int pad_last, int mode, int if_method, const float* offset,
+                               const float* scale, float* out, void* stream) {
+    ACIDS_REQUIRE(y && out, ACIDS_EINVAL, "phase_inv: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 31) && n_in > 0, ACIDS_EINVAL, "phase_inv: bad sizes");
+    ACIDS_REQUIRE(mode >= 0 && mode <= 2 && if_method >= 0 && if_method <= 2, ACIDS_EINVAL, "phase_inv: bad mode/method");
+    ACIDS_REQUIRE(pad_last == 0 || pad_last == 1, ACIDS_EINVAL, "pad_last must be 0 or 1");
+    if (B == 0) return ACIDS_OK;
+    PhaseInvParams p{};
+    p.y = y; p.B = B; p.n_frames = (int)n_frames; p.n_in = n_in; p.y_clip_stride = y_clip_stride;
+    p.y_row_stride = y_row_stride; p.pad_last = pad_last; p.mode = mode; p.method = if_method;
+    p.offset_ptr = offset; p.scale_ptr = scale; p.out = out;
+    const int64_t cols = B * (n_in + pad_last);
+    phase_inv_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("phase_inv");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_polar_to_complex(const float* mag, const float* phase, int64_t n, float* out, void* stream) {
+    ACIDS_REQUIRE(mag && phase && out, ACIDS_EINVAL, "polar_to_complex: NULL pointer");
+    ACIDS_REQUIRE(n >= 0, ACIDS_EINVAL, "polar_to_complex: negative size");
+    if (n == 0) return ACIDS_OK;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    polar_to_complex_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mag, phase, n,
+                                                                                           reinterpret_cast<float2*>(out));
+    ACIDS_CHECK_LAUNCH("polar_to_complex");
+    return ACIDS_OK;
+}

@@ -1,0 +1,529 @@
+"""Tensor-level entry points: torch supplies device memory and the current stream, the work is done
+by the CUDA kernels behind the C ABI (include/acids_b200.h).  No op here has a CPU or eager path.
+
+Host (CPU) tensors are accepted for drop-in compatibility with the reference, whose tests feed CPU
+tensors: they are copied to the current CUDA device, processed there, and the result is copied
+back — the copies are part of the call, which is what `bench.py`'s `e2e` number measures.
+"""
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Band, CONTRAST_IDS, IF_METHOD_IDS, ONEHOT_IDS, PHASE_IF, PHASE_RAW, PHASE_UNWRAP
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.AcidsError("acids_transforms_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _dev(t: torch.Tensor) -> torch.Tensor:
+    """Tensor on the compute device (host tensors are staged to the current CUDA device)."""
+    if t.is_cuda:
+        return t
+    _require_cuda()
+    return t.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+
+
+def _ret(y: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    return y if like.is_cuda else y.to(like.device)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _scalar(t, device) -> Optional[torch.Tensor]:
+    """Normalize.offset / .scale as a 1-element float32 device tensor (or None)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        t = torch.tensor(float(t), dtype=torch.float32)
+    if t.numel() != 1:      # Normalize.offset starts as torch.zeros(0) before scale_data (norm.py:22)
+        raise RuntimeError("normalisation buffers are not set: call scale_data() first")
+    return t.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+
+
+class BandedMatrix:
+    """Column-banded view of a mostly-zero [n_in, n_out] matrix (the mel banks).
+
+    Column m keeps rows [start, start+count) — its first to last non-zero.  Device copies are made
+    lazily per device.  spectral_repr.py:173-189 builds these matrices dense; 99.6 % of the square
+    513x513 bank is zero.
+    """
+
+    def __init__(self, dense: torch.Tensor):
+        m = dense.detach().to("cpu", torch.float32).numpy()
+        if m.ndim == 3:
+            m = m[0]
+        self.n_in, self.n_out = int(m.shape[0]), int(m.shape[1])
+        if self.n_in >= 65536:
+            raise ValueError("banded matrix supports at most 65535 input rows")
+        meta = np.zeros((self.n_out, 2), np.int32)
+        coefs = []
+        off = 0
+        nz = m != 0
+        for c in range(self.n_out):
+            rows = np.flatnonzero(nz[:, c])
+            if rows.size:
+                s, e = int(rows[0]), int(rows[-1]) + 1
+                meta[c, 0] = s | ((e - s) << 16)
+                meta[c, 1] = off
+                coefs.append(m[s:e, c])
+                off += e - s
+            else:
+                meta[c, 0] = 0
+                meta[c, 1] = off
+        self.nnz_stored = off
+        self._meta = torch.from_numpy(meta)
+        self._coef = torch.from_numpy(np.concatenate(coefs) if coefs else np.zeros(1, np.float32)).contiguous()
+        self._dev = {}
+
+    def on(self, device) -> Band:
+        key = (device.type, device.index)
+        if key not in self._dev:
+            self._dev[key] = (self._meta.to(device), self._coef.to(device))
+        meta, coef = self._dev[key]
+        return Band(meta.data_ptr(), coef.data_ptr(), self.n_out)
+
+
+_NO_BAND = Band(None, None, 0)
+
+
+def _band(b: Optional[BandedMatrix], device) -> Band:
+    return b.on(device) if b is not None else _NO_BAND
+
+
+def _flat_batch(x: torch.Tensor, event_dims: int):
+    """reshape_batches (utils/misc.py:168-178): flatten leading dims, keep the last `event_dims`."""
+    batch = x.shape[:x.ndim - event_dims]
+    return x.reshape((-1,) + tuple(x.shape[x.ndim - event_dims:])).contiguous(), batch
+
+
+def n_frames_centered(L: int, hop: int) -> int:
+    return 1 + L // hop
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) STFT forward
+# ------------------------------------------------------------------------------------------------
+def _check_stft_input(x, n_fft, center=True):
+    if x.dtype != torch.float32:
+        raise RuntimeError("acids_b200: expected a float32 waveform, got %s" % x.dtype)
+    if center and not (0 < n_fft // 2 < x.shape[-1]):
+        # same condition torch's reflect padding enforces for torch.stft(center=True)
+        raise RuntimeError("Argument #4: Padding size should be less than the corresponding input dimension, "
+                           "but got: padding (%d, %d) at dimension 2 of input %s" % (n_fft // 2, n_fft // 2, list(x.shape)))
+
+
+def stft_fwd(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, center: bool = True) -> torch.Tensor:
+    """x [..., L] float32 -> complex64 [..., T, F]  (stft.py:97-104, dgt.py:63-70).
+    center=False: x is pre-framed [..., n, n_fft] -> [..., n, F]  (stft.py:248-253)."""
+    lib = _lib.load()
+    xd = _dev(x)
+    if center:
+        _check_stft_input(xd, n_fft)
+        xf, batch = _flat_batch(xd, 1)
+        B, L = xf.shape
+        T = n_frames_centered(L, hop)
+        hop_k, ldx = hop, L
+    else:
+        if xd.shape[-1] != n_fft:
+            raise RuntimeError("acids_b200: pre-framed input must have n_fft=%d samples per frame, got %d" % (n_fft, xd.shape[-1]))
+        if xd.dtype != torch.float32:
+            raise RuntimeError("acids_b200: expected float32 frames")
+        xf2, batch = _flat_batch(xd, 1)              # [rows, n_fft]
+        T = xf2.shape[0]
+        xf = xf2.reshape(1, -1)
+        B, L, hop_k, ldx = 1, xf.shape[1], n_fft, xf.shape[1]
+    F = n_fft // 2 + 1
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((B, T, F), dtype=torch.complex64, device=xf.device)
+    with torch.cuda.device(xf.device):
+        _lib.check(lib.acids_stft_fwd(_ptr(xf), B, L, ldx, _ptr(w), n_fft, hop_k, int(center), T, _ptr(out), _stream(xf.device)), lib)
+    out = out.reshape(tuple(batch) + ((T, F) if center else (F,)))
+    return _ret(out, x)
+
+
+def stft_mag_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, eps, offset, scale,
+                 drop_first: bool = False, out: Optional[torch.Tensor] = None, out_slot: int = 0, out_slots: int = 1):
+    """Fused STFT + Magnitude.forward: x [..., L] -> float32 [..., T, n_cols - drop]  (stft.py:101 + spectral_repr.py:215-226).
+    With out_slots = 2 the rows are written into slot `out_slot` of a stacked [..., T, 2, n] tensor (Polar*)."""
+    lib = _lib.load()
+    xd = _dev(x)
+    _check_stft_input(xd, n_fft)
+    xf, batch = _flat_batch(xd, 1)
+    B, L = xf.shape
+    T = n_frames_centered(L, hop)
+    n_cols = band.n_out if band is not None else n_fft // 2 + 1
+    n_keep = n_cols - int(drop_first)
+    dev = xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    own = out is None
+    if own:
+        out = torch.empty((B, T, out_slots, n_keep) if out_slots > 1 else (B, T, n_keep), dtype=torch.float32, device=dev)
+    row_stride = out_slots * n_keep
+    base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_stft_mag_fwd(_ptr(xf), B, L, L, _ptr(w), n_fft, hop, 1, T, _band(band, dev), CONTRAST_IDS[contrast],
+                                          float(eps), _ptr(off), _ptr(sc), int(drop_first), _ptr(base), T * row_stride,
+                                          row_stride, _stream(dev)), lib)
+    if not own:
+        return out
+    out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
+    return _ret(out, x)
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) Magnitude on a spectrum
+# ------------------------------------------------------------------------------------------------
+def _as_complex64(X):
+    if not torch.is_complex(X):
+        X = X.to(torch.float32).to(torch.complex64)     # abs() of a real tensor is still defined in the reference
+    return X.to(torch.complex64)
+
+
+def mag_epilogue(X, band: Optional[BandedMatrix], contrast, eps, offset, scale, drop_first=False,
+                 out: Optional[torch.Tensor] = None, out_slot: int = 0, out_slots: int = 1):
+    """Magnitude.forward: X [..., F] complex -> float32 [..., n_cols - drop]  (spectral_repr.py:215-226)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    Xf, batch = _flat_batch(Xd, 1)
+    rows, F = Xf.shape
+    if band is not None and band.n_in != F:
+        # the reference's matmul raises the same way when Magnitude.n_fft disagrees with the STFT's
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, F, band.n_in, band.n_out))
+    n_cols = band.n_out if band is not None else F
+    n_keep = n_cols - int(drop_first)
+    dev = Xf.device
+    own = out is None
+    if own:
+        out = torch.empty((rows, out_slots, n_keep) if out_slots > 1 else (rows, n_keep), dtype=torch.float32, device=dev)
+    row_stride = out_slots * n_keep
+    base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_mag_epilogue(_ptr(Xf), rows, F, _band(band, dev), CONTRAST_IDS[contrast], float(eps), _ptr(off),
+                                          _ptr(sc), int(drop_first), _ptr(base), row_stride, _stream(dev)), lib)
+    if not own:
+        return out
+    out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
+    return _ret(out, X)
+
+
+def mag_invert(y, inverse_band: Optional[BandedMatrix], contrast, eps, offset, scale, pad_last=False):
+    """Magnitude.invert: y [..., n_in] -> float32 [..., n_out]  (spectral_repr.py:228-240)."""
+    lib = _lib.load()
+    yd = _dev(y).to(torch.float32)
+    yf, batch = _flat_batch(yd, 1) if yd.is_contiguous() else (yd.reshape(-1, yd.shape[-1]), yd.shape[:-1])
+    if yf.stride(-1) != 1:
+        yf = yf.contiguous()
+    rows, n_in = yf.shape
+    n_val = n_in + int(pad_last)
+    if inverse_band is not None and inverse_band.n_in != n_val:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, n_val, inverse_band.n_in, inverse_band.n_out))
+    n_out = inverse_band.n_out if inverse_band is not None else n_val
+    dev = yf.device
+    out = torch.empty((rows, n_out), dtype=torch.float32, device=dev)
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_mag_invert(_ptr(yf), rows, n_in, yf.stride(0), int(pad_last), _band(inverse_band, dev),
+                                        CONTRAST_IDS[contrast], float(eps), _ptr(off), _ptr(sc), _ptr(out), _stream(dev)), lib)
+    return _ret(out.reshape(tuple(batch) + (n_out,)), y)
+
+
+def melspec_fwd(x, window, n_fft, hop, mel: BandedMatrix, power=2.0, offset=None, scale=None):
+    """MFCC.forward (= torchaudio MelSpectrogram): x [..., L] -> [..., n_mels, T]  (mel.py:68-73)."""
+    lib = _lib.load()
+    xd = _dev(x)
+    _check_stft_input(xd, n_fft)
+    xf, batch = _flat_batch(xd, 1)
+    B, L = xf.shape
+    T = n_frames_centered(L, hop)
+    dev = xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((B, mel.n_out, T), dtype=torch.float32, device=dev)
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_melspec_fwd(_ptr(xf), B, L, L, _ptr(w), n_fft, hop, T, mel.on(dev), float(power), _ptr(off), _ptr(sc),
+                                         _ptr(out), _stream(dev)), lib)
+    return _ret(out.reshape(tuple(batch) + (mel.n_out, T)), x)
+
+
+def mfcc_dct(mel, dct, top_db: Optional[float] = 80.0):
+    """dB + top_db floor + DCT-II: mel [..., n_mels, T] -> [..., n_mfcc, T]  (torchaudio MFCC, _transforms.py:701-718)."""
+    lib = _lib.load()
+    md = _dev(mel).to(torch.float32)
+    mf, batch = _flat_batch(md, 2)
+    B, n_mels, T = mf.shape
+    # torchaudio's amplitude_to_DB packs dim -3 as "channels": inputs with <= 3 dims share ONE max
+    group = B if md.ndim <= 3 else int(md.shape[-3])
+    dev = mf.device
+    d = _dev(dct).to(torch.float32).contiguous()
+    n_mfcc = d.shape[1]
+    out = torch.empty((B, n_mfcc, T), dtype=torch.float32, device=dev)
+    gmax = torch.empty((max(B // max(group, 1), 1),), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_mfcc_dct(_ptr(mf), B, n_mels, T, _ptr(d), n_mfcc, float(-1.0 if top_db is None else top_db),
+                                      max(group, 1), _ptr(gmax), _ptr(out), _stream(dev)), lib)
+    return _ret(out.reshape(tuple(batch) + (n_mfcc, T)), mel)
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) phase / IF
+# ------------------------------------------------------------------------------------------------
+def phase_fwd(X, mode: int, method="forward", weighted=False, offset=None, scale=None, drop_first=False,
+              out: Optional[torch.Tensor] = None, out_slot: int = 0, out_slots: int = 1):
+    """Phase.forward / IF.forward on X [..., T, F]  (spectral_repr.py:270-278, :319-357; utils/misc.py:12-26)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    if Xd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] spectrum)")
+    Xf, batch = _flat_batch(Xd, 2)
+    B, T, F = Xf.shape
+    n_keep = F - int(drop_first)
+    dev = Xf.device
+    own = out is None
+    if own:
+        out = torch.empty((B, T, out_slots, n_keep) if out_slots > 1 else (B, T, n_keep), dtype=torch.float32, device=dev)
+    row_stride = out_slots * n_keep
+    base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_phase_fwd(_ptr(Xf), B, T, F, mode, IF_METHOD_IDS[method], int(bool(weighted)), _ptr(off), _ptr(sc),
+                                       int(drop_first), _ptr(base), T * row_stride, row_stride, _stream(dev)), lib)
+    if not own:
+        return out
+    out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
+    return _ret(out, X)
+
+
+def phase_inv(y, mode: int, method="forward", offset=None, scale=None, pad_last=False):
+    """Phase.invert / IF.invert: y [..., T, n_in] -> phase [..., T, n_in + pad]  (spectral_repr.py:46-53, :359-375)."""
+    lib = _lib.load()
+    yd = _dev(y).to(torch.float32)
+    if yd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] tensor)")
+    yf = yd.reshape((-1,) + tuple(yd.shape[-2:]))
+    if yf.stride(-1) != 1 or (yf.shape[0] > 1 and yf.stride(0) < yf.shape[1] * yf.stride(1)):
+        yf = yf.contiguous()
+    B, T, n_in = yf.shape
+    dev = yf.device
+    out = torch.empty((B, T, n_in + int(pad_last)), dtype=torch.float32, device=dev)
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_phase_inv(_ptr(yf), B, T, n_in, yf.stride(0) if B > 1 else T * yf.stride(1), yf.stride(1),
+                                       int(pad_last), mode, IF_METHOD_IDS[method], _ptr(off), _ptr(sc), _ptr(out), _stream(dev)), lib)
+    return _ret(out.reshape(tuple(yd.shape[:-1]) + (n_in + int(pad_last),)), y)
+
+
+def polar_to_complex(mag, phase):
+    """mag * exp(i phase) -> complex64  (spectral_repr.py:452)."""
+    lib = _lib.load()
+    md = _dev(mag).to(torch.float32).contiguous()
+    pd = _dev(phase).to(torch.float32).contiguous()
+    if md.shape != pd.shape:
+        md, pd = torch.broadcast_tensors(md, pd)
+        md, pd = md.contiguous(), pd.contiguous()
+    out = torch.empty(md.shape, dtype=torch.complex64, device=md.device)
+    with torch.cuda.device(md.device):
+        _lib.check(lib.acids_polar_to_complex(_ptr(md), _ptr(pd), md.numel(), _ptr(out), _stream(md.device)), lib)
+    return _ret(out, mag)
+
+
+# ------------------------------------------------------------------------------------------------
+# (4) inverse
+# ------------------------------------------------------------------------------------------------
+def istft_envelope_ok(window: torch.Tensor, n_fft: int, hop: int, n_frames: int) -> bool:
+    """torch.istft's `window overlap add min` check (_refs/__init__.py:3794-3797), evaluated on the host.
+
+    It depends only on the window, so the reference's RuntimeError can be raised without a device
+    sync.  The envelope is periodic away from the edges, hence a clip of at most 2*ceil(N/hop)+2
+    frames has the same minimum over its trimmed core as the full-length one.
+    """
+    w2 = window.detach().to("cpu", torch.float64)[:n_fft].numpy() ** 2
+    t_eff = min(int(n_frames), 2 * ((n_fft + hop - 1) // hop) + 2)
+    length = n_fft + hop * (t_eff - 1)
+    env = np.zeros(length, np.float64)
+    for t in range(t_eff):
+        env[t * hop:t * hop + n_fft] += w2
+    core = env[n_fft // 2:length - n_fft // 2]
+    return core.size == 0 or bool(np.abs(core).min() > 1e-11)
+
+
+def istft_ola(X, window, n_fft, hop, check_envelope: bool = True):
+    """STFT.invert / DGT.invert complex branch: X [..., T, F] -> [..., hop (T-1)]  (stft.py:119-128, dgt.py:85-93)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    Xf, batch = _flat_batch(Xd, 2)
+    B, T, F = Xf.shape
+    if F != n_fft // 2 + 1:
+        raise RuntimeError("istft: expected %d frequency bins for n_fft=%d, got %d" % (n_fft // 2 + 1, n_fft, F))
+    if check_envelope and not istft_envelope_ok(window, n_fft, hop, T):
+        raise RuntimeError("istft(CUDA): window overlap add min: 1")
+    dev = Xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((B, hop * (T - 1)), dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.acids_istft_workspace_bytes(B, T, n_fft, hop))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_istft_ola(_ptr(Xf), B, T, n_fft, hop, _ptr(w), _ptr(out), _ptr(ws), ws_bytes, _stream(dev)), lib)
+    return _ret(out.reshape(tuple(batch) + (hop * (T - 1),)), X)
+
+
+def irfft_frames(X, window, n_fft):
+    """RealtimeSTFT.invert complex branch: irfft(X) * window, X [..., F] -> [..., n_fft]  (stft.py:259-266)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    Xf, batch = _flat_batch(Xd, 1)
+    rows, F = Xf.shape
+    if F != n_fft // 2 + 1:
+        raise RuntimeError("irfft: expected %d frequency bins for n_fft=%d, got %d" % (n_fft // 2 + 1, n_fft, F))
+    dev = Xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((rows, n_fft), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_irfft_frames(_ptr(Xf), rows, n_fft, _ptr(w), _ptr(out), _stream(dev)), lib)
+    return _ret(out.reshape(tuple(batch) + (n_fft,)), X)
+
+
+def ola_stream(frames, hop, keep, carry_in, gain) -> Tuple[torch.Tensor, torch.Tensor]:
+    """OverlapAdd.invert: frames [..., n, N] (+ carry [..., keep]) -> (out [..., (n-1) hop + N - keep], carry_out)  (oadd.py:91-104)."""
+    lib = _lib.load()
+    fd = _dev(frames).to(torch.float32)
+    ff, batch = _flat_batch(fd, 2)
+    B, n, N = ff.shape
+    dev = ff.device
+    total = (n - 1) * hop + N
+    out = torch.empty((B, total - keep), dtype=torch.float32, device=dev)
+    carry_out = torch.empty((B, keep), dtype=torch.float32, device=dev)
+    ci = None
+    if carry_in is not None:
+        ci = _dev(carry_in).to(torch.float32).reshape(B, keep).contiguous()
+    g = float(gain)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_ola_stream(_ptr(ff), B, n, N, hop, keep, _ptr(ci), g, _ptr(out), _ptr(carry_out), _stream(dev)), lib)
+    return (_ret(out.reshape(tuple(batch) + (total - keep,)), frames),
+            _ret(carry_out.reshape(tuple(batch) + (keep,)), frames))
+
+
+# ------------------------------------------------------------------------------------------------
+# (5) mu-law / one-hot
+# ------------------------------------------------------------------------------------------------
+def _log1p_mu(channels: int) -> float:
+    # the reference evaluates torch.log1p(torch.tensor(mu)) on the host in float32 (functional.py:697-698)
+    return float(torch.log1p(torch.tensor(channels - 1.0, dtype=torch.float32)))
+
+
+def mulaw_encode(x, channels=256, one_hot="none", reciprocal_divide: Optional[bool] = None):
+    """MuLaw.forward: float32 [..., L] -> int64 ([..., L] | [..., L, C] | [..., C, L])  (raw.py:280-292)."""
+    lib = _lib.load()
+    if reciprocal_divide is None:
+        # match the eager chain of the device the caller's data lives on: CUDA eager multiplies by the
+        # reciprocal of a host scalar, CPU eager divides (see oracle.np_oracle.mulaw_encode)
+        reciprocal_divide = x.is_cuda
+    xd = _dev(x)
+    if not xd.is_floating_point():
+        xd = xd.to(torch.float32)
+    xd = xd.to(torch.float32).contiguous()
+    dev = xd.device
+    L = xd.shape[-1] if xd.ndim else 1
+    outer = xd.numel() // max(L, 1)
+    if one_hot == "categorical":
+        out = torch.empty(tuple(xd.shape) + (channels,), dtype=torch.int64, device=dev)
+    elif one_hot == "channel":
+        out = torch.empty(tuple(xd.shape[:-1]) + (channels, L), dtype=torch.int64, device=dev)
+    else:
+        one_hot = "none"
+        out = torch.empty(xd.shape, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_mulaw_encode(_ptr(xd), outer, L, channels, _log1p_mu(channels), int(bool(reciprocal_divide)),
+                                          ONEHOT_IDS[one_hot], _ptr(out), _stream(dev)), lib)
+    return _ret(out, x)
+
+
+def mulaw_decode(q, channels=256):
+    """MuLaw.invert: int64 -> float32  (raw.py:314-316)."""
+    lib = _lib.load()
+    qd = _dev(q).to(torch.int64).contiguous()
+    out = torch.empty(qd.shape, dtype=torch.float32, device=qd.device)
+    with torch.cuda.device(qd.device):
+        _lib.check(lib.acids_mulaw_decode(_ptr(qd), qd.numel(), channels, _log1p_mu(channels), _ptr(out), _stream(qd.device)), lib)
+    return _ret(out, q)
+
+
+def one_hot(q, n_classes: int):
+    """OneHot.forward: int64 [...] -> int64 [..., n_classes]  (misc.py:176-179)."""
+    lib = _lib.load()
+    qd = _dev(q)
+    if qd.dtype != torch.int64:
+        raise RuntimeError("one_hot is only applicable to index tensor of type LongTensor.")
+    qd = qd.contiguous()
+    if n_classes < 1:
+        raise RuntimeError("one_hot: n_classes is not set (call scale_data first)")
+    out = torch.empty(tuple(qd.shape) + (n_classes,), dtype=torch.int64, device=qd.device)
+    with torch.cuda.device(qd.device):
+        _lib.check(lib.acids_one_hot(_ptr(qd), qd.numel(), n_classes, _ptr(out), _stream(qd.device)), lib)
+    return _ret(out, q)
+
+
+# ------------------------------------------------------------------------------------------------
+# statistics, raw-domain prologues
+# ------------------------------------------------------------------------------------------------
+def stats(x, contrast=None, eps=0.0) -> torch.Tensor:
+    """(min, max, mean, unbiased std) as a float64[4] DEVICE tensor — no host sync.
+    Complex input: statistics of contrast(|x|), what Magnitude.scale_data feeds Normalize (spectral_repr.py:242-245)."""
+    lib = _lib.load()
+    xd = _dev(x)
+    dev = xd.device
+    if torch.is_complex(xd):
+        xd = xd.to(torch.complex64).resolve_conj().contiguous()
+        kind = _lib.STATS_CABS_CONTRAST
+    else:
+        xd = xd.to(torch.float32).contiguous()
+        kind = _lib.STATS_REAL
+    if xd.numel() == 0:
+        raise RuntimeError("min(): Expected reduction dim to be specified for input.numel() == 0.")
+    scratch = torch.empty((int(lib.acids_stats_scratch_bytes()),), dtype=torch.uint8, device=dev)
+    out = torch.empty((4,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.acids_stats(_ptr(xd), xd.numel(), kind, CONTRAST_IDS[contrast], float(eps), _ptr(scratch), _ptr(out), _stream(dev)), lib)
+    return out
+
+
+def mono_mix(x):
+    """Mono(mode="mix"): [..., 2, L] -> [..., L] = (l + r) / 2  (raw.py:37-39)."""
+    lib = _lib.load()
+    xd = _dev(x).to(torch.float32)
+    xf, batch = _flat_batch(xd, 2)
+    B, C, L = xf.shape
+    assert C == 2
+    out = torch.empty((B, L), dtype=torch.float32, device=xf.device)
+    with torch.cuda.device(xf.device):
+        _lib.check(lib.acids_mono_mix(_ptr(xf), B, L, _ptr(out), _stream(xf.device)), lib)
+    return _ret(out.reshape(tuple(batch) + (L,)), x)
+
+
+def midside(x, pad_mid=True, inverse=False):
+    """MidSide.forward / invert on [..., 2, L]  (raw.py:145-180)."""
+    lib = _lib.load()
+    xd = _dev(x).to(torch.float32)
+    xf, batch = _flat_batch(xd, 2)
+    B, C, L = xf.shape
+    assert C == 2
+    out = torch.empty_like(xf)
+    with torch.cuda.device(xf.device):
+        _lib.check(lib.acids_midside(_ptr(xf), B, L, int(bool(pad_mid)), int(bool(inverse)), _ptr(out), _stream(xf.device)), lib)
+    return _ret(out.reshape(tuple(batch) + (2, L)), x)

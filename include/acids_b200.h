@@ -1,0 +1,203 @@
+/* acids_b200.h — C ABI of libacids_b200.so, the B200 (sm_100a) implementation of the
+ * acids_transforms spectral hot path.
+ *
+ * This is the drop-in boundary.  The reference is a pure-Python package whose
+ * arithmetic lives in torch/torchaudio calls; each entry point below replaces the call site(s)
+ * cited next to it (paths relative to the reference repository root).  The Python host in
+ * acids_transforms_b200/ binds these symbols with ctypes and exposes them through the
+ * reference's own nn.Module API; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types, no C++ exceptions cross this boundary;
+ *   - every pointer is a DEVICE pointer to contiguous memory unless a stride is passed;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work on it and return without
+ *     synchronising; the library never allocates or frees device memory;
+ *   - complex tensors are interleaved (re, im) float32 pairs, i.e. torch.complex64;
+ *   - return value: 0 on success, a negative ACIDS_E* code otherwise; acids_last_error()
+ *     gives the message for the calling thread;
+ *   - `offset` / `scale` are DEVICE pointers to one float each (the Normalize buffers,
+ *     norm.py:22-23) or NULL for "no normalisation" — no host sync is needed to use them.
+ */
+#ifndef ACIDS_B200_H
+#define ACIDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACIDS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ACIDS_API __attribute__((visibility("default")))
+#else
+#define ACIDS_API
+#endif
+
+#define ACIDS_OK 0
+#define ACIDS_EINVAL (-1)      /* bad argument (shape, NULL pointer, alignment)            */
+#define ACIDS_ENOTSUP (-2)     /* n_fft not a power of two in [32, 16384], or overlap too large */
+#define ACIDS_ECUDA (-3)       /* CUDA runtime error at launch                              */
+#define ACIDS_EWORKSPACE (-4)  /* caller-provided workspace too small                       */
+
+/* contrast ids — Magnitude.contrast, spectral_repr.py:191-201 */
+#define ACIDS_CONTRAST_NONE 0
+#define ACIDS_CONTRAST_LOG1P 1   /* log(1 + m) */
+#define ACIDS_CONTRAST_LOG 2     /* log(clamp(m, eps)) */
+#define ACIDS_CONTRAST_LOG10 3   /* log10(clamp(m, eps)) */
+
+/* IF methods — IF.get_if, spectral_repr.py:319-335 */
+#define ACIDS_IF_FORWARD 0
+#define ACIDS_IF_BACKWARD 1
+#define ACIDS_IF_CENTRAL 2
+
+/* phase-kernel modes */
+#define ACIDS_PHASE_RAW 0        /* angle(X)                      Phase(unwrap=False) */
+#define ACIDS_PHASE_UNWRAP 1     /* unwrap(angle(X)) over frames  Phase(unwrap=True)  */
+#define ACIDS_PHASE_IF 2         /* instantaneous frequency       IF                  */
+
+/* statistics input kinds for acids_stats */
+#define ACIDS_STATS_REAL 0           /* float32 values as they are                       */
+#define ACIDS_STATS_CABS_CONTRAST 1  /* complex64 in, statistics of contrast(|x|)        */
+
+/* one-hot layouts — MuLaw.one_hot, raw.py:285-292 */
+#define ACIDS_ONEHOT_NONE 0
+#define ACIDS_ONEHOT_CATEGORICAL 1   /* [..., L, C] */
+#define ACIDS_ONEHOT_CHANNEL 2       /* [..., C, L] */
+
+ACIDS_API int acids_abi_version(void);
+ACIDS_API const char* acids_last_error(void);
+
+/* A banded (sparse-by-columns) matrix: output column m sums rows [start[m], start[m]+count[m])
+ * of the input with weights coef[off[m] + u].  meta[2m] = start | (count << 16), meta[2m+1] = off.
+ * This is how the 99.6 %-sparse mel banks of spectral_repr.py:173-189 are applied. */
+typedef struct acids_band {
+    const int32_t* meta;   /* device, 2 * n_out ints, or NULL for "no projection" */
+    const float* coef;     /* device */
+    int32_t n_out;         /* number of output columns */
+} acids_band;
+
+/* ---- (1) framing + window + real FFT ------------------------------------------------------
+ * Replaces torch.stft(...).transpose(-2,-1) at stft.py:101-102 and dgt.py:67-68 (centre=1:
+ * reflect padding by n_fft/2, n_frames = 1 + L / hop), and torch.fft.rfft(x * window) on
+ * pre-framed input at stft.py:251 / dgt.py:287 (centre=0, hop = n_fft, L = n_frames * n_fft).
+ *   x [B, L] (row stride ldx), window [n_fft]  ->  out complex64 [B, n_frames, n_fft/2 + 1]   */
+ACIDS_API int acids_stft_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
+                   int n_fft, int hop, int center, int64_t n_frames, float* out, void* stream);
+
+/* ---- (2) fused STFT + |.| + banded mel + contrast + normalise ------------------------------
+ * Replaces the chain stft.py:101-102 -> spectral_repr.py:217-225 -> norm.py:41 without
+ * materialising the complex spectrum.  out float32: row (b, t) starts at
+ * out + b * out_clip_stride + t * out_row_stride and holds (n_cols - drop_first) values,
+ * where n_cols = band.n_out (or n_fft/2+1 without projection) and drop_first = 1 reproduces
+ * `keep_nyquist=False` (spectral_repr.py:224-225, which drops bin 0).                          */
+ACIDS_API int acids_stft_mag_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
+                       int n_fft, int hop, int center, int64_t n_frames, acids_band band,
+                       int contrast, float eps, const float* offset, const float* scale,
+                       int drop_first, float* out, int64_t out_clip_stride, int64_t out_row_stride,
+                       void* stream);
+
+/* Same epilogue on an existing spectrum: Magnitude.forward, spectral_repr.py:215-226.
+ *   X complex64 [rows, n_bins] -> out float32, row r at out + r * out_row_stride.              */
+ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_bins, acids_band band, int contrast,
+                       float eps, const float* offset, const float* scale, int drop_first,
+                       float* out, int64_t out_row_stride, void* stream);
+
+/* Magnitude.invert, spectral_repr.py:228-240: m = contrast^-1(y * scale + offset) [zero-padded by
+ * one bin when pad_last] @ inverse bank.  y [rows, n_in] (row stride y_row_stride) -> out [rows, n_out]. */
+ACIDS_API int acids_mag_invert(const float* y, int64_t rows, int n_in, int64_t y_row_stride, int pad_last,
+                     acids_band inverse_band, int contrast, float eps, const float* offset,
+                     const float* scale, float* out, void* stream);
+
+/* ---- (2b) mel spectrogram / MFCC: mel.py:68-73 (torchaudio MelSpectrogram) ------------------
+ * periodic-Hann STFT -> |X|^power -> banded mel [n_fft/2+1 -> n_mels] -> out [B, n_mels, n_frames]
+ * (frequency-major like torchaudio), optionally normalised.                                    */
+ACIDS_API int acids_melspec_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
+                      int n_fft, int hop, int64_t n_frames, acids_band mel, float power,
+                      const float* offset, const float* scale, float* out, void* stream);
+
+/* Opt-in DCT tail following torchaudio.transforms.MFCC (functional.py:390-404, :636-667):
+ * dB = 10 log10(clamp(mel, 1e-10)), floored at (max over a GROUP of clips) - top_db, then
+ * out = dct^T dB.  torchaudio takes that max per leading batch item over the packed
+ * (channel, mel, time) dims — and over the WHOLE tensor for inputs of 3 or fewer dims — so the
+ * caller says how many consecutive clips share one max (clips_per_group, must divide B).
+ *   mel [B, n_mels, n_frames], dct [n_mels, n_mfcc] -> out [B, n_mfcc, n_frames].
+ * group_max: device scratch of B / clips_per_group floats.  top_db < 0 disables the floor.      */
+ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct,
+                   int n_mfcc, float top_db, int64_t clips_per_group, float* group_max, float* out,
+                   void* stream);
+
+/* ---- (3) phase / unwrap / instantaneous frequency ------------------------------------------
+ * Phase.forward (spectral_repr.py:270-278), unwrap (utils/misc.py:12-26), IF.forward
+ * (spectral_repr.py:319-357).  X complex64 [B, n_frames, n_bins]; out float32 rows like (2).
+ * `weighted` applies the parabolic frame weighting of spectral_repr.py:337-345.               */
+ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, int mode,
+                    int if_method, int weighted, const float* offset, const float* scale,
+                    int drop_first, float* out, int64_t out_clip_stride, int64_t out_row_stride,
+                    void* stream);
+
+/* IF.invert (spectral_repr.py:359-375; fint_* utils/misc.py:82-104) and Phase.invert
+ * (mode RAW/UNWRAP: de-normalise only).  y rows like (2) -> phase float32 [B, n_frames, n_bins]
+ * (n_bins = n_in + pad_last).                                                                  */
+ACIDS_API int acids_phase_inv(const float* y, int64_t B, int64_t n_frames, int n_in, int64_t y_clip_stride,
+                    int64_t y_row_stride, int pad_last, int mode, int if_method,
+                    const float* offset, const float* scale, float* out, void* stream);
+
+/* SpectralRepresentation.invert tail, spectral_repr.py:452: out = mag * exp(i phase).          */
+ACIDS_API int acids_polar_to_complex(const float* mag, const float* phase, int64_t n, float* out, void* stream);
+
+/* ---- (4) inverse rFFT + synthesis window + overlap-add + envelope normalisation -------------
+ * Replaces torch.istft at stft.py:126-127 / dgt.py:92 (centre=1: output trimmed by n_fft/2 on both
+ * sides, length hop*(n_frames-1)), atomic-free: each CTA owns a span of output samples.
+ *   X complex64 [B, n_frames, n_fft/2+1], window [n_fft] -> out [B, hop*(n_frames-1)].
+ * workspace: device scratch of acids_istft_workspace_bytes(...) bytes (0 for the fused path).  */
+ACIDS_API int64_t acids_istft_workspace_bytes(int64_t B, int64_t n_frames, int n_fft, int hop);
+ACIDS_API int acids_istft_ola(const float* X, int64_t B, int64_t n_frames, int n_fft, int hop,
+                    const float* window, float* out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Per-frame inverse: torch.fft.irfft(X) * inv_window at stft.py:266 / dgt.py:302.
+ *   X complex64 [rows, n_fft/2+1] -> out [rows, n_fft].                                        */
+ACIDS_API int acids_irfft_frames(const float* X, int64_t rows, int n_fft, const float* window, float* out,
+                       void* stream);
+
+/* Streaming overlap-add with carry: OverlapAdd.invert, oadd.py:91-104.
+ *   frames [B, n, n_fft], carry_in [B, keep] (keep = (n_fft/hop - 1) * hop; NULL = zeros)
+ *   -> out [B, n*hop + n_fft - hop - keep... see oadd.py:97], carry_out [B, keep]; out is divided
+ *   by `gain`.  out_len = (n-1)*hop + n_fft - keep.                                             */
+ACIDS_API int acids_ola_stream(const float* frames, int64_t B, int64_t n, int n_fft, int hop, int64_t keep,
+                     const float* carry_in, float gain, float* out, float* carry_out, void* stream);
+
+/* ---- (5) mu-law and one-hot ------------------------------------------------------------------
+ * torchaudio mu_law_encoding / decoding (functional.py:690-700, :723-729) as used by raw.py:282-316.
+ * log1p_mu = float32 log1p(channels-1) evaluated by the caller the way the reference does (host).
+ * reciprocal_divide: 0 = IEEE division by log1p_mu (CPU eager chain), 1 = multiply by its
+ * float32 reciprocal (what the CUDA eager chain computes).  out int64.
+ * one_hot: ACIDS_ONEHOT_*; for CATEGORICAL out is [n, C], for CHANNEL [outer, C, inner]
+ * with n = outer * inner.                                                                       */
+ACIDS_API int acids_mulaw_encode(const float* x, int64_t outer, int64_t inner, int channels, float log1p_mu,
+                       int reciprocal_divide, int one_hot, int64_t* out, void* stream);
+ACIDS_API int acids_mulaw_decode(const int64_t* q, int64_t n, int channels, float log1p_mu, float* out,
+                       void* stream);
+/* F.one_hot for OneHot.forward, misc.py:176-179: q [n] int64 -> out [n, n_classes] int64.        */
+ACIDS_API int acids_one_hot(const int64_t* q, int64_t n, int n_classes, int64_t* out, void* stream);
+
+/* ---- Normalize.scale_data statistics: norm.py:26-38, spectral_repr.py:242-245 -----------------
+ * out4 (device, 4 doubles): min, max, mean, unbiased std of the (transformed) values.
+ * kind = ACIDS_STATS_REAL: x float32 [n]; ACIDS_STATS_CABS_CONTRAST: x complex64 [n], statistics of
+ * contrast(|x|).  scratch: device buffer of acids_stats_scratch_bytes() bytes.                   */
+ACIDS_API int64_t acids_stats_scratch_bytes(void);
+ACIDS_API int acids_stats(const float* x, int64_t n, int kind, int contrast, float eps, void* scratch,
+                double* out4, void* stream);
+
+/* ---- raw-domain prologues: raw.py:34-49 (Mono mix), raw.py:145-180 (MidSide) -------------------
+ * x [B, 2, L] -> mono [B, L] = (l + r) / 2;  mid/side [B, 2, L] (pad_mid: mid / sqrt(2)).        */
+ACIDS_API int acids_mono_mix(const float* x, int64_t B, int64_t L, float* out, void* stream);
+ACIDS_API int acids_midside(const float* x, int64_t B, int64_t L, int pad_mid, int inverse, float* out,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACIDS_B200_H */
