@@ -47,7 +47,7 @@ _PROTOTYPES = {
     "acids_irfft_frames": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     "acids_ola_stream": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, _P, c_float, _P, _P, _P]),
     "acids_mulaw_encode": (c_int, [_P, c_int64, c_int64, c_int, c_float, c_int, c_int, _P, _P]),
-    "acids_mulaw_decode": (c_int, [_P, c_int64, c_int, c_float, _P, _P]),
+    "acids_mulaw_decode": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "acids_one_hot": (c_int, [_P, c_int64, c_int, _P, _P]),
     "acids_stats_scratch_bytes": (c_int64, []),
     "acids_stats": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, _P, _P]),

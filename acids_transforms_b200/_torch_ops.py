@@ -1,0 +1,150 @@
+"""Registers the hot-path ops with the PyTorch dispatcher as `torch.ops.acids_b200.*`.
+
+The nn.Module mirror of the reference calls these, which keeps every module TorchScript-scriptable
+(`torch.jit.script` resolves `torch.ops.<ns>.<op>` from the registered schema).  The implementations
+are the ctypes calls of ops.py — CUDA kernels behind the C ABI; there is no other backend.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+
+NS = "acids_b200"
+_lib = torch.library.Library(NS, "DEF")
+
+_SCHEMAS = {
+    "stft_fwd": "(Tensor x, Tensor window, int n_fft, int hop, bool center) -> Tensor",
+    "stft_mag_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, "
+                    "float eps, Tensor? offset, Tensor? scale, bool drop_first) -> Tensor",
+    "stft_polar_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, "
+                      "float eps, Tensor? mag_offset, Tensor? mag_scale, int phase_mode, int method, bool weighted, "
+                      "Tensor? ph_offset, Tensor? ph_scale, bool drop_first) -> Tensor",
+    "mag_epilogue": "(Tensor X, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? offset, "
+                    "Tensor? scale, bool drop_first) -> Tensor",
+    "mag_invert": "(Tensor y, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? offset, "
+                  "Tensor? scale, bool pad_last) -> Tensor",
+    "melspec_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor band_meta, Tensor band_coef, float power, "
+                   "Tensor? offset, Tensor? scale) -> Tensor",
+    "mfcc_dct": "(Tensor mel, Tensor dct, float top_db) -> Tensor",
+    "phase_fwd": "(Tensor X, int mode, int method, bool weighted, Tensor? offset, Tensor? scale, bool drop_first) -> Tensor",
+    "phase_inv": "(Tensor y, int mode, int method, Tensor? offset, Tensor? scale, bool pad_last) -> Tensor",
+    "polar_fwd": "(Tensor X, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? mag_offset, "
+                 "Tensor? mag_scale, int phase_mode, int method, bool weighted, Tensor? ph_offset, Tensor? ph_scale, "
+                 "bool drop_first) -> Tensor",
+    "polar_to_complex": "(Tensor mag, Tensor phase) -> Tensor",
+    "istft_ola": "(Tensor X, Tensor window, int n_fft, int hop) -> Tensor",
+    "irfft_frames": "(Tensor X, Tensor window, int n_fft) -> Tensor",
+    "ola_stream": "(Tensor frames, int hop, int keep, Tensor? carry_in, float gain) -> (Tensor, Tensor)",
+    "mulaw_encode": "(Tensor x, int channels, int one_hot) -> Tensor",
+    "mulaw_decode": "(Tensor q, int channels) -> Tensor",
+    "one_hot": "(Tensor q, int n_classes) -> Tensor",
+    "stats": "(Tensor x, int contrast, float eps) -> Tensor",
+    "mono_mix": "(Tensor x) -> Tensor",
+    "midside": "(Tensor x, bool pad_mid, bool inverse) -> Tensor",
+}
+
+
+def _stft_fwd(x, window, n_fft: int, hop: int, center: bool):
+    return ops.stft_fwd(x, window, n_fft, hop, center)
+
+
+def _stft_mag_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contrast: int, eps: float, offset, scale,
+                  drop_first: bool):
+    return ops.stft_mag_fwd(x, window, n_fft, hop, ops.as_band(band_meta, band_coef), contrast, eps, offset, scale, drop_first)
+
+
+def _stft_polar_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contrast: int, eps: float, mag_offset, mag_scale,
+                    phase_mode: int, method: int, weighted: bool, ph_offset, ph_scale, drop_first: bool):
+    """wave -> stacked [..., T, 2, F'] (Polar / PolarIF after an STFT): the spectrum is produced once and
+    consumed by the two representation kernels writing straight into their slot of the stacked tensor."""
+    X = ops.stft_fwd(x, window, n_fft, hop, True)
+    return _polar_fwd(X, band_meta, band_coef, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted,
+                      ph_offset, ph_scale, drop_first)
+
+
+def _mag_epilogue(X, band_meta, band_coef, contrast: int, eps: float, offset, scale, drop_first: bool):
+    return ops.mag_epilogue(X, ops.as_band(band_meta, band_coef), contrast, eps, offset, scale, drop_first)
+
+
+def _mag_invert(y, band_meta, band_coef, contrast: int, eps: float, offset, scale, pad_last: bool):
+    return ops.mag_invert(y, ops.as_band(band_meta, band_coef), contrast, eps, offset, scale, pad_last)
+
+
+def _melspec_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, power: float, offset, scale):
+    return ops.melspec_fwd(x, window, n_fft, hop, ops.as_band(band_meta, band_coef), power, offset, scale)
+
+
+def _mfcc_dct(mel, dct, top_db: float):
+    return ops.mfcc_dct(mel, dct, None if top_db < 0 else top_db)
+
+
+def _phase_fwd(X, mode: int, method: int, weighted: bool, offset, scale, drop_first: bool):
+    return ops.phase_fwd(X, mode, method, weighted, offset, scale, drop_first)
+
+
+def _phase_inv(y, mode: int, method: int, offset, scale, pad_last: bool):
+    return ops.phase_inv(y, mode, method, offset, scale, pad_last)
+
+
+def _polar_fwd(X, band_meta, band_coef, contrast: int, eps: float, mag_offset, mag_scale, phase_mode: int, method: int,
+               weighted: bool, ph_offset, ph_scale, drop_first: bool):
+    Xd = ops._dev(X)
+    band = ops.as_band(band_meta, band_coef)
+    F = Xd.shape[-1]
+    n_mag = (band.n_out if band is not None else F) - int(drop_first)
+    n_ph = F - int(drop_first)
+    if n_mag != n_ph:
+        raise RuntimeError("stack expects each tensor to be equal size, but got [%d] and [%d] bins" % (n_mag, n_ph))
+    T = Xd.shape[-2]
+    rows = Xd.numel() // F
+    out = torch.empty((rows // T, T, 2, n_mag), dtype=torch.float32, device=Xd.device)
+    ops.mag_epilogue(Xd, band, contrast, eps, mag_offset, mag_scale, drop_first, out=out, out_slot=0, out_slots=2)
+    ops.phase_fwd(Xd, phase_mode, method, weighted, ph_offset, ph_scale, drop_first, out=out, out_slot=1, out_slots=2)
+    out = out.reshape(tuple(Xd.shape[:-2]) + (T, 2, n_mag))
+    return ops._ret(out, X)
+
+
+def _polar_to_complex(mag, phase):
+    return ops.polar_to_complex(mag, phase)
+
+
+def _istft_ola(X, window, n_fft: int, hop: int):
+    return ops.istft_ola(X, window, n_fft, hop)
+
+
+def _irfft_frames(X, window, n_fft: int):
+    return ops.irfft_frames(X, window, n_fft)
+
+
+def _ola_stream(frames, hop: int, keep: int, carry_in, gain: float):
+    return ops.ola_stream(frames, hop, keep, carry_in, gain)
+
+
+def _mulaw_encode(x, channels: int, one_hot: int):
+    return ops.mulaw_encode(x, channels, one_hot)
+
+
+def _mulaw_decode(q, channels: int):
+    return ops.mulaw_decode(q, channels)
+
+
+def _one_hot(q, n_classes: int):
+    return ops.one_hot(q, n_classes)
+
+
+def _stats(x, contrast: int, eps: float):
+    return ops._ret(ops.stats(x, contrast, eps), x)
+
+
+def _mono_mix(x):
+    return ops.mono_mix(x)
+
+
+def _midside(x, pad_mid: bool, inverse: bool):
+    return ops.midside(x, pad_mid, inverse)
+
+
+for _name, _schema in _SCHEMAS.items():
+    _lib.define(_name + _schema)
+    _lib.impl(_name, globals()["_" + _name], "CompositeExplicitAutograd")

@@ -60,15 +60,18 @@ __global__ void mulaw_onehot_channel_kernel(const float* __restrict__ x, int64_t
     }
 }
 
-__global__ void mulaw_decode_kernel(const int64_t* __restrict__ q, int64_t n, float mu, float l1p,
+__global__ void mulaw_decode_kernel(const int64_t* __restrict__ q, int64_t n, float mu, float l1p, int recip,
                                     float* __restrict__ out) {
     // functional.py:727-728: x = q / mu * 2 - 1;  sign(x) * (exp(|x| * log1p(mu)) - 1) / mu
+    // (both divisions are by a host scalar: the CUDA eager chain multiplies by 1/mu instead)
+    const float inv_mu = __fdiv_rn(1.0f, mu);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = __fdiv_rn((float)q[i], mu);
+        float v = recip ? __fmul_rn((float)q[i], inv_mu) : __fdiv_rn((float)q[i], mu);
         v = __fadd_rn(__fmul_rn(v, 2.0f), -1.0f);
         const float sgn = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
         const float e = __fadd_rn(expf(__fmul_rn(fabsf(v), l1p)), -1.0f);
-        out[i] = __fdiv_rn(__fmul_rn(sgn, e), mu);
+        const float num = __fmul_rn(sgn, e);
+        out[i] = recip ? __fmul_rn(num, inv_mu) : __fdiv_rn(num, mu);
     }
 }
 
@@ -291,11 +294,12 @@ extern "C" ACIDS_API int acids_mulaw_encode(const float* x, int64_t outer, int64
     return ACIDS_OK;
 }
 
-extern "C" ACIDS_API int acids_mulaw_decode(const int64_t* q, int64_t n, int channels, float log1p_mu, float* out, void* stream) {
+extern "C" ACIDS_API int acids_mulaw_decode(const int64_t* q, int64_t n, int channels, float log1p_mu, int reciprocal_divide,
+                                            float* out, void* stream) {
     ACIDS_REQUIRE(q && out, ACIDS_EINVAL, "mulaw_decode: NULL pointer");
     ACIDS_REQUIRE(n >= 0 && channels >= 2, ACIDS_EINVAL, "mulaw_decode: bad sizes");
     if (n == 0) return ACIDS_OK;
-    mulaw_decode_kernel<<<grid_for(n, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, n, (float)(channels - 1.0), log1p_mu, out);
+    mulaw_decode_kernel<<<grid_for(n, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, n, (float)(channels - 1.0), log1p_mu, reciprocal_divide, out);
     ACIDS_CHECK_LAUNCH("mulaw_decode");
     return ACIDS_OK;
 }

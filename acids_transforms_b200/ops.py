@@ -44,6 +44,13 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _run(out: torch.Tensor, fn, *args):
+    """Launch through the C ABI unless there is nothing to compute (empty batch)."""
+    if out.numel() == 0:
+        return
+    _lib.check(fn(*args))
+
+
 def _scalar(t, device) -> Optional[torch.Tensor]:
     """Normalize.offset / .scale as a 1-element float32 device tensor (or None)."""
     if t is None:
@@ -86,23 +93,59 @@ class BandedMatrix:
                 meta[c, 0] = 0
                 meta[c, 1] = off
         self.nnz_stored = off
+        meta = np.concatenate([meta, np.array([[self.n_in, off]], np.int32)], 0)
         self._meta = torch.from_numpy(meta)
         self._coef = torch.from_numpy(np.concatenate(coefs) if coefs else np.zeros(1, np.float32)).contiguous()
         self._dev = {}
 
+    def tensors(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(meta int32 [n_out + 1, 2], coef float32): what the modules keep as non-persistent buffers."""
+        return self._meta.clone(), self._coef.clone()
+
+    @classmethod
+    def from_tensors(cls, meta: torch.Tensor, coef: torch.Tensor) -> "BandedMatrix":
+        self = cls.__new__(cls)
+        self.n_out = int(meta.shape[0]) - 1
+        self.n_in = -1          # read lazily: avoids a device sync when the tensors live on the GPU
+        self.nnz_stored = int(coef.numel())
+        self._meta, self._coef, self._dev = meta, coef, {}
+        return self
+
     def on(self, device) -> Band:
         key = (device.type, device.index)
         if key not in self._dev:
-            self._dev[key] = (self._meta.to(device), self._coef.to(device))
+            self._dev[key] = (self._meta.to(device).contiguous(), self._coef.to(device).contiguous())
         meta, coef = self._dev[key]
         return Band(meta.data_ptr(), coef.data_ptr(), self.n_out)
 
 
 _NO_BAND = Band(None, None, 0)
+_BAND_CACHE = {}
+
+
+def as_band(meta: Optional[torch.Tensor], coef: Optional[torch.Tensor]) -> Optional[BandedMatrix]:
+    """BandedMatrix view of a (meta, coef) buffer pair, cached on the buffers' identity/version."""
+    if meta is None or coef is None:
+        return None
+    key = (meta.data_ptr(), coef.data_ptr(), meta._version, coef._version, meta.shape[0])
+    b = _BAND_CACHE.get(key)
+    if b is None:
+        if len(_BAND_CACHE) > 64:
+            _BAND_CACHE.clear()
+        b = _BAND_CACHE[key] = BandedMatrix.from_tensors(meta, coef)
+    return b
 
 
 def _band(b: Optional[BandedMatrix], device) -> Band:
     return b.on(device) if b is not None else _NO_BAND
+
+
+def _cid(contrast) -> int:
+    return contrast if isinstance(contrast, int) else CONTRAST_IDS[contrast]
+
+
+def _mid(method) -> int:
+    return method if isinstance(method, int) else IF_METHOD_IDS[method]
 
 
 def _flat_batch(x: torch.Tensor, event_dims: int):
@@ -151,7 +194,7 @@ def stft_fwd(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, center
     w = _dev(window).to(torch.float32).contiguous()
     out = torch.empty((B, T, F), dtype=torch.complex64, device=xf.device)
     with torch.cuda.device(xf.device):
-        _lib.check(lib.acids_stft_fwd(_ptr(xf), B, L, ldx, _ptr(w), n_fft, hop_k, int(center), T, _ptr(out), _stream(xf.device)), lib)
+        _run(out, lib.acids_stft_fwd, _ptr(xf), B, L, ldx, _ptr(w), n_fft, hop_k, int(center), T, _ptr(out), _stream(xf.device))
     out = out.reshape(tuple(batch) + ((T, F) if center else (F,)))
     return _ret(out, x)
 
@@ -177,9 +220,9 @@ def stft_mag_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, 
     base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_stft_mag_fwd(_ptr(xf), B, L, L, _ptr(w), n_fft, hop, 1, T, _band(band, dev), CONTRAST_IDS[contrast],
+        _run(out, lib.acids_stft_mag_fwd, _ptr(xf), B, L, L, _ptr(w), n_fft, hop, 1, T, _band(band, dev), _cid(contrast),
                                           float(eps), _ptr(off), _ptr(sc), int(drop_first), _ptr(base), T * row_stride,
-                                          row_stride, _stream(dev)), lib)
+                                          row_stride, _stream(dev))
     if not own:
         return out
     out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
@@ -202,7 +245,7 @@ def mag_epilogue(X, band: Optional[BandedMatrix], contrast, eps, offset, scale, 
     Xd = _as_complex64(_dev(X)).resolve_conj()
     Xf, batch = _flat_batch(Xd, 1)
     rows, F = Xf.shape
-    if band is not None and band.n_in != F:
+    if band is not None and band.n_in >= 0 and band.n_in != F:
         # the reference's matmul raises the same way when Magnitude.n_fft disagrees with the STFT's
         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, F, band.n_in, band.n_out))
     n_cols = band.n_out if band is not None else F
@@ -215,8 +258,8 @@ def mag_epilogue(X, band: Optional[BandedMatrix], contrast, eps, offset, scale, 
     base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_mag_epilogue(_ptr(Xf), rows, F, _band(band, dev), CONTRAST_IDS[contrast], float(eps), _ptr(off),
-                                          _ptr(sc), int(drop_first), _ptr(base), row_stride, _stream(dev)), lib)
+        _run(out, lib.acids_mag_epilogue, _ptr(Xf), rows, F, _band(band, dev), _cid(contrast), float(eps), _ptr(off),
+                                          _ptr(sc), int(drop_first), _ptr(base), row_stride, _stream(dev))
     if not own:
         return out
     out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
@@ -232,15 +275,15 @@ def mag_invert(y, inverse_band: Optional[BandedMatrix], contrast, eps, offset, s
         yf = yf.contiguous()
     rows, n_in = yf.shape
     n_val = n_in + int(pad_last)
-    if inverse_band is not None and inverse_band.n_in != n_val:
+    if inverse_band is not None and inverse_band.n_in >= 0 and inverse_band.n_in != n_val:
         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, n_val, inverse_band.n_in, inverse_band.n_out))
     n_out = inverse_band.n_out if inverse_band is not None else n_val
     dev = yf.device
     out = torch.empty((rows, n_out), dtype=torch.float32, device=dev)
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_mag_invert(_ptr(yf), rows, n_in, yf.stride(0), int(pad_last), _band(inverse_band, dev),
-                                        CONTRAST_IDS[contrast], float(eps), _ptr(off), _ptr(sc), _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_mag_invert, _ptr(yf), rows, n_in, yf.stride(0), int(pad_last), _band(inverse_band, dev),
+                                        _cid(contrast), float(eps), _ptr(off), _ptr(sc), _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(batch) + (n_out,)), y)
 
 
@@ -257,8 +300,8 @@ def melspec_fwd(x, window, n_fft, hop, mel: BandedMatrix, power=2.0, offset=None
     out = torch.empty((B, mel.n_out, T), dtype=torch.float32, device=dev)
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_melspec_fwd(_ptr(xf), B, L, L, _ptr(w), n_fft, hop, T, mel.on(dev), float(power), _ptr(off), _ptr(sc),
-                                         _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_melspec_fwd, _ptr(xf), B, L, L, _ptr(w), n_fft, hop, T, mel.on(dev), float(power), _ptr(off), _ptr(sc),
+                                         _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(batch) + (mel.n_out, T)), x)
 
 
@@ -276,8 +319,8 @@ def mfcc_dct(mel, dct, top_db: Optional[float] = 80.0):
     out = torch.empty((B, n_mfcc, T), dtype=torch.float32, device=dev)
     gmax = torch.empty((max(B // max(group, 1), 1),), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_mfcc_dct(_ptr(mf), B, n_mels, T, _ptr(d), n_mfcc, float(-1.0 if top_db is None else top_db),
-                                      max(group, 1), _ptr(gmax), _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_mfcc_dct, _ptr(mf), B, n_mels, T, _ptr(d), n_mfcc, float(-1.0 if top_db is None else top_db),
+                                      max(group, 1), _ptr(gmax), _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(batch) + (n_mfcc, T)), mel)
 
 
@@ -302,8 +345,8 @@ def phase_fwd(X, mode: int, method="forward", weighted=False, offset=None, scale
     base = out.view(-1)[out_slot * n_keep:] if out_slots > 1 else out
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_phase_fwd(_ptr(Xf), B, T, F, mode, IF_METHOD_IDS[method], int(bool(weighted)), _ptr(off), _ptr(sc),
-                                       int(drop_first), _ptr(base), T * row_stride, row_stride, _stream(dev)), lib)
+        _run(out, lib.acids_phase_fwd, _ptr(Xf), B, T, F, mode, _mid(method), int(bool(weighted)), _ptr(off), _ptr(sc),
+                                       int(drop_first), _ptr(base), T * row_stride, row_stride, _stream(dev))
     if not own:
         return out
     out = out.reshape(tuple(batch) + tuple(out.shape[1:]))
@@ -324,8 +367,8 @@ def phase_inv(y, mode: int, method="forward", offset=None, scale=None, pad_last=
     out = torch.empty((B, T, n_in + int(pad_last)), dtype=torch.float32, device=dev)
     off, sc = _scalar(offset, dev), _scalar(scale, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_phase_inv(_ptr(yf), B, T, n_in, yf.stride(0) if B > 1 else T * yf.stride(1), yf.stride(1),
-                                       int(pad_last), mode, IF_METHOD_IDS[method], _ptr(off), _ptr(sc), _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_phase_inv, _ptr(yf), B, T, n_in, yf.stride(0) if B > 1 else T * yf.stride(1), yf.stride(1),
+                                       int(pad_last), mode, _mid(method), _ptr(off), _ptr(sc), _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(yd.shape[:-1]) + (n_in + int(pad_last),)), y)
 
 
@@ -339,7 +382,7 @@ def polar_to_complex(mag, phase):
         md, pd = md.contiguous(), pd.contiguous()
     out = torch.empty(md.shape, dtype=torch.complex64, device=md.device)
     with torch.cuda.device(md.device):
-        _lib.check(lib.acids_polar_to_complex(_ptr(md), _ptr(pd), md.numel(), _ptr(out), _stream(md.device)), lib)
+        _run(out, lib.acids_polar_to_complex, _ptr(md), _ptr(pd), md.numel(), _ptr(out), _stream(md.device))
     return _ret(out, mag)
 
 
@@ -379,7 +422,7 @@ def istft_ola(X, window, n_fft, hop, check_envelope: bool = True):
     ws_bytes = int(lib.acids_istft_workspace_bytes(B, T, n_fft, hop))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_istft_ola(_ptr(Xf), B, T, n_fft, hop, _ptr(w), _ptr(out), _ptr(ws), ws_bytes, _stream(dev)), lib)
+        _run(out, lib.acids_istft_ola, _ptr(Xf), B, T, n_fft, hop, _ptr(w), _ptr(out), _ptr(ws), ws_bytes, _stream(dev))
     return _ret(out.reshape(tuple(batch) + (hop * (T - 1),)), X)
 
 
@@ -395,7 +438,7 @@ def irfft_frames(X, window, n_fft):
     w = _dev(window).to(torch.float32).contiguous()
     out = torch.empty((rows, n_fft), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_irfft_frames(_ptr(Xf), rows, n_fft, _ptr(w), _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_irfft_frames, _ptr(Xf), rows, n_fft, _ptr(w), _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(batch) + (n_fft,)), X)
 
 
@@ -414,7 +457,7 @@ def ola_stream(frames, hop, keep, carry_in, gain) -> Tuple[torch.Tensor, torch.T
         ci = _dev(carry_in).to(torch.float32).reshape(B, keep).contiguous()
     g = float(gain)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_ola_stream(_ptr(ff), B, n, N, hop, keep, _ptr(ci), g, _ptr(out), _ptr(carry_out), _stream(dev)), lib)
+        _run(out, lib.acids_ola_stream, _ptr(ff), B, n, N, hop, keep, _ptr(ci), g, _ptr(out), _ptr(carry_out), _stream(dev))
     return (_ret(out.reshape(tuple(batch) + (total - keep,)), frames),
             _ret(carry_out.reshape(tuple(batch) + (keep,)), frames))
 
@@ -430,9 +473,11 @@ def _log1p_mu(channels: int) -> float:
 def mulaw_encode(x, channels=256, one_hot="none", reciprocal_divide: Optional[bool] = None):
     """MuLaw.forward: float32 [..., L] -> int64 ([..., L] | [..., L, C] | [..., C, L])  (raw.py:280-292)."""
     lib = _lib.load()
+    if isinstance(one_hot, int):
+        one_hot = ("none", "categorical", "channel")[one_hot]
     if reciprocal_divide is None:
         # match the eager chain of the device the caller's data lives on: CUDA eager multiplies by the
-        # reciprocal of a host scalar, CPU eager divides (see oracle.np_oracle.mulaw_encode)
+        # reciprocal of a host scalar, CPU eager divides (DESIGN.md, mu-law)
         reciprocal_divide = x.is_cuda
     xd = _dev(x)
     if not xd.is_floating_point():
@@ -449,18 +494,23 @@ def mulaw_encode(x, channels=256, one_hot="none", reciprocal_divide: Optional[bo
         one_hot = "none"
         out = torch.empty(xd.shape, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_mulaw_encode(_ptr(xd), outer, L, channels, _log1p_mu(channels), int(bool(reciprocal_divide)),
-                                          ONEHOT_IDS[one_hot], _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_mulaw_encode, _ptr(xd), outer, L, channels, _log1p_mu(channels), int(bool(reciprocal_divide)),
+                                          (one_hot if isinstance(one_hot, int) else ONEHOT_IDS[one_hot]), _ptr(out), _stream(dev))
     return _ret(out, x)
 
 
-def mulaw_decode(q, channels=256):
+def mulaw_decode(q, channels=256, reciprocal_divide: Optional[bool] = None):
     """MuLaw.invert: int64 -> float32  (raw.py:314-316)."""
     lib = _lib.load()
+    if reciprocal_divide is None:
+        reciprocal_divide = q.is_cuda
     qd = _dev(q).to(torch.int64).contiguous()
     out = torch.empty(qd.shape, dtype=torch.float32, device=qd.device)
+    if qd.numel() == 0:
+        return _ret(out, q)
     with torch.cuda.device(qd.device):
-        _lib.check(lib.acids_mulaw_decode(_ptr(qd), qd.numel(), channels, _log1p_mu(channels), _ptr(out), _stream(qd.device)), lib)
+        _run(out, lib.acids_mulaw_decode, _ptr(qd), qd.numel(), channels, _log1p_mu(channels), int(bool(reciprocal_divide)),
+                                          _ptr(out), _stream(qd.device))
     return _ret(out, q)
 
 
@@ -475,7 +525,7 @@ def one_hot(q, n_classes: int):
         raise RuntimeError("one_hot: n_classes is not set (call scale_data first)")
     out = torch.empty(tuple(qd.shape) + (n_classes,), dtype=torch.int64, device=qd.device)
     with torch.cuda.device(qd.device):
-        _lib.check(lib.acids_one_hot(_ptr(qd), qd.numel(), n_classes, _ptr(out), _stream(qd.device)), lib)
+        _run(out, lib.acids_one_hot, _ptr(qd), qd.numel(), n_classes, _ptr(out), _stream(qd.device))
     return _ret(out, q)
 
 
@@ -499,7 +549,7 @@ def stats(x, contrast=None, eps=0.0) -> torch.Tensor:
     scratch = torch.empty((int(lib.acids_stats_scratch_bytes()),), dtype=torch.uint8, device=dev)
     out = torch.empty((4,), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.acids_stats(_ptr(xd), xd.numel(), kind, CONTRAST_IDS[contrast], float(eps), _ptr(scratch), _ptr(out), _stream(dev)), lib)
+        _run(out, lib.acids_stats, _ptr(xd), xd.numel(), kind, _cid(contrast), float(eps), _ptr(scratch), _ptr(out), _stream(dev))
     return out
 
 
@@ -512,7 +562,7 @@ def mono_mix(x):
     assert C == 2
     out = torch.empty((B, L), dtype=torch.float32, device=xf.device)
     with torch.cuda.device(xf.device):
-        _lib.check(lib.acids_mono_mix(_ptr(xf), B, L, _ptr(out), _stream(xf.device)), lib)
+        _run(out, lib.acids_mono_mix, _ptr(xf), B, L, _ptr(out), _stream(xf.device))
     return _ret(out.reshape(tuple(batch) + (L,)), x)
 
 
@@ -525,5 +575,5 @@ def midside(x, pad_mid=True, inverse=False):
     assert C == 2
     out = torch.empty_like(xf)
     with torch.cuda.device(xf.device):
-        _lib.check(lib.acids_midside(_ptr(xf), B, L, int(bool(pad_mid)), int(bool(inverse)), _ptr(out), _stream(xf.device)), lib)
+        _run(out, lib.acids_midside, _ptr(xf), B, L, int(bool(pad_mid)), int(bool(inverse)), _ptr(out), _stream(xf.device))
     return _ret(out.reshape(tuple(batch) + (2, L)), x)

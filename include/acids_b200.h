@@ -178,8 +178,8 @@ ACIDS_API int acids_ola_stream(const float* frames, int64_t B, int64_t n, int n_
  * with n = outer * inner.                                                                       */
 ACIDS_API int acids_mulaw_encode(const float* x, int64_t outer, int64_t inner, int channels, float log1p_mu,
                        int reciprocal_divide, int one_hot, int64_t* out, void* stream);
-ACIDS_API int acids_mulaw_decode(const int64_t* q, int64_t n, int channels, float log1p_mu, float* out,
-                       void* stream);
+ACIDS_API int acids_mulaw_decode(const int64_t* q, int64_t n, int channels, float log1p_mu,
+                                 int reciprocal_divide, float* out, void* stream);
 /* F.one_hot for OneHot.forward, misc.py:176-179: q [n] int64 -> out [n, n_classes] int64.        */
 ACIDS_API int acids_one_hot(const int64_t* q, int64_t n, int n_classes, int64_t* out, void* stream);
 

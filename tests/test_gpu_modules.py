@@ -1,0 +1,276 @@
+"""GPU tests at the drop-in boundary: the nn.Module API of the reference (forward / invert / scale_data,
+`+` chains, TorchScript) driving the CUDA kernels, checked against golden vectors minted from the
+unmodified reference.  The second half replays the reference's own test-suite flow
+(test/test_transforms.py:28-102: reflection over the classes, their test_* hooks, the four `+` chains)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_parity, branch_cut, if_mask, load_golden
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def T():
+    assert torch.cuda.is_available()
+    from acids_transforms_b200 import transforms, _lib
+    _lib.load()
+    return transforms
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().resolve_conj().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configurations at fixture size, through the module API
+# ---------------------------------------------------------------------------------------------
+def test_cfg1_chain(T):
+    """Mono + STFT(1024,256) + Magnitude() — scale_data then forward, CPU tensors in and out like the reference run."""
+    g = load_golden("chain_cfg1")
+    ch = T.Mono() + T.STFT(n_fft=1024, hop_length=256) + T.Magnitude()
+    x = torch.from_numpy(g["x"])                       # host tensor: staged to the GPU and back by the ops
+    ch.scale_data(x)
+    assert abs(float(ch[2].norm.offset) - float(g["offset"])) <= 1e-5 and abs(float(ch[2].norm.scale) - float(g["scale"])) <= 1e-4 * float(g["scale"])
+    y = ch(x)
+    assert y.device.type == "cpu" and tuple(y.shape) == g["y"].shape
+    assert_parity(y.numpy(), g["y"], REL, "cfg1")
+    assert_parity(ch.forward_unfused(x).numpy(), g["y"], REL, "cfg1 unfused")
+
+
+def test_cfg2_chain_eager_and_scripted(T):
+    """DGT(1024,256) + Magnitude(mel, unipolar, log1p) — README.md:52-67 — eager, on-device, and TorchScript."""
+    g = load_golden("chain_cfg2")
+    ch = (T.DGT(sr=44100, n_fft=1024, hop_length=256, inversion_mode="random") + T.Magnitude(mel=True, mode="unipolar", contrast="log1p")).cuda()
+    x = cu(g["x"])
+    assert ch.invertible and ch.scriptable
+    sc = torch.jit.script(ch)
+    for tr in (ch, sc):
+        tr.scale_data(x)
+        y = tr(x)
+        assert y.is_cuda
+        assert_parity(host(y), g["y"], REL, "cfg2")
+    assert abs(float(ch[1].norm.offset) - float(g["offset"])) <= 1e-5
+    assert abs(float(ch[1].norm.scale) - float(g["scale"])) <= 1e-4 * float(g["scale"])
+    y, t = sc.forward_with_time(x, torch.zeros(3, device="cuda"))
+    assert tuple(t.shape) == (3, 33) and abs(float(t[0, 1]) - 256 / 44100) < 1e-7
+    xi = sc.invert(y)                                   # Magnitude.invert -> DGT.invert(random phase)
+    assert tuple(xi.shape) == (3, 8192) and bool(torch.isfinite(xi).all())
+
+
+def test_cfg4_chain(T):
+    """MidSide + STFT(4096,1024) + PolarIF forward and inverse."""
+    g = load_golden("chain_cfg4")
+    ch = (T.MidSide() + T.STFT(n_fft=4096, hop_length=1024) + T.PolarIF(
+        magnitude_args={"mode": "bipolar", "n_fft": 4096}, phase_args={"mode": "bipolar"})).cuda()
+    x = cu(g["x"])
+    ch.scale_data(x)
+    y = ch(x)
+    assert tuple(y.shape) == g["y"].shape            # [1, 2, 13, 2, 2049]
+    assert_parity(host(y[..., 0, :]), g["y"][..., 0, :], REL, "cfg4 magnitude")
+    X = host(ch[1](ch[0](x)))
+    ok = if_mask(X)
+    assert_parity(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, g["y"][..., 1, :], 0), 2e-4, "cfg4 IF")
+    # the normalisation was fitted on data whose frame-0 phases are +-pi by rounding noise: compare with slack
+    assert abs(float(ch[2].magnitude.norm.scale) - float(g["mag_scale"])) <= 1e-4 * float(g["mag_scale"])
+    ch[2].magnitude.norm.offset, ch[2].magnitude.norm.scale = cu(g["mag_offset"]), cu(g["mag_scale"])
+    ch[2].phase.norm.offset, ch[2].phase.norm.scale = cu(g["ph_offset"]), cu(g["ph_scale"])
+    xi = ch.invert(cu(g["y"]))
+    assert_parity(host(xi), g["x_inv"], REL, "cfg4 inverse")
+
+
+def test_polar_modules(T):
+    g = load_golden("polar_1024")
+    X = cu(g["X"])
+    for tag, cls in (("polar", T.Polar), ("polarif", T.PolarIF)):
+        p = cls().cuda()
+        p.scale_data(X)
+        y = host(p(X))
+        ok = if_mask(g["X"]) if tag == "polarif" else ~branch_cut(g["X"])
+        assert_parity(y[..., 0, :], g[tag + "_y"][..., 0, :], REL, tag + " mag")
+        # offsets fitted on this GPU can differ from the CPU reference by a +-pi flip of an ill-conditioned bin:
+        # judge the phase slot with the reference's own statistics
+        p.phase.norm.offset, p.phase.norm.scale = cu(g[tag + "_ph_offset"]), cu(g[tag + "_ph_scale"])
+        y = host(p(X))
+        assert_parity(np.where(ok, y[..., 1, :], 0), np.where(ok, g[tag + "_y"][..., 1, :], 0), REL, tag + " phase")
+        p.magnitude.norm.offset, p.magnitude.norm.scale = cu(g[tag + "_mag_offset"]), cu(g[tag + "_mag_scale"])
+        assert_parity(host(p.invert(cu(g[tag + "_y"]))), g[tag + "_inv"], REL, tag + " invert")
+        # the generic stack path (two kernels + torch.stack) equals the in-place stacked write
+        assert torch.equal(p._stacked_forward(X), p(X))
+
+
+def test_mfcc_module(T):
+    g = load_golden("mfcc")
+    m = T.MFCC(n_fft=2048, hop_length=512, n_mels=128).cuda()
+    y = m(cu(g["x"]))
+    assert_parity(host(y), g["y"], REL, "MFCC (= mel spectrogram)")
+    m40 = T.MFCC(n_fft=2048, hop_length=512, n_mels=128, n_mfcc=40).cuda()
+    assert_parity(host(m40(cu(g["x"]))), g["y_dct40"], REL, "MFCC n_mfcc=40")
+    mg = T.MFCC(norm_mode="gaussian").cuda()
+    x2 = cu(g["x2"])
+    mg.scale_data(mg.mel_power(x2))
+    assert abs(float(mg.norm.offset) - float(g["y2_gauss_offset"])) <= 1e-4 * abs(float(g["y2_gauss_scale"]))
+    assert_parity(host(mg(x2)), g["y2_gauss"], REL, "MFCC gaussian")
+    with pytest.raises(T.NotInvertibleError):
+        m.invert(y)
+
+
+def test_mulaw_modules(T):
+    import torchaudio
+    g = load_golden("mulaw")
+    x = cu(g["x"])
+    ch = (T.Stereo() + T.MuLaw(channels=256) + T.OneHot(n_classes=256)).cuda()
+    xs = x[:2, :4096].reshape(1, 2, 4096)
+    y = ch(xs)
+    assert y.dtype == torch.int64 and tuple(y.shape) == (1, 2, 4096, 256)
+    assert torch.equal(y.argmax(-1), torchaudio.functional.mu_law_encoding(xs, 256))
+    back = ch.invert(y)
+    assert_parity(host(back), host(torchaudio.functional.mu_law_decoding(y.argmax(-1), 256)), 1e-6, "chain invert")
+    for layout in ("channel", "categorical"):
+        m = T.MuLaw(one_hot=layout)
+        q = m(x[:, :64].contiguous())
+        assert np.array_equal(host(q), g["q64_" + layout])
+        assert torch.equal(m.decode(q), torchaudio.functional.mu_law_decoding(cu(g["q"][:, :64]), 256))
+    # host tensors follow the CPU eager chain (IEEE division): equals the reference's CPU output
+    qc = T.MuLaw()(torch.from_numpy(g["x"]))
+    assert int((qc.numpy() != g["q"]).sum()) <= 2
+
+
+def test_streaming_modules(T):
+    for tag, cls in (("rtstft", T.RealtimeSTFT), ("rtdgt", T.RealtimeDGT)):
+        g = load_golden("stream_" + tag)
+        oa = T.OverlapAdd(512, 128).cuda()
+        rt = cls(n_fft=512, hop_length=128).cuda()
+        x = cu(g["x"])
+        for i, chunk in enumerate(x.split(2048, -1)):
+            fr = oa(chunk)
+            assert_parity(host(fr), g["frames_%d" % i], 1e-7, "frames")
+            X = rt(fr)
+            assert_parity(host(X), g["X_%d" % i], REL, "rt fwd")
+            out = oa.invert(rt.invert(X))
+            assert_parity(host(out), g["out_%d" % i], REL, "stream out")
+
+
+def test_phaseless_inversion(T):
+    x = cu(load_golden("stft_1024_256")["x"])
+    s = T.STFT(inversion_mode="keep_input").cuda()
+    X = s(x)
+    assert tuple(s.phase_buffer.shape) == (2, 33, 513)                     # filled because keep_input consumes it
+    y = s.invert(X.abs())                                                   # magnitude + kept phase == exact inverse
+    assert float((y - x[:, :y.shape[1]]).abs().max()) < 1e-4
+    s2 = T.STFT().cuda()
+    s2(x)
+    assert s2.phase_buffer.numel() == 0                                     # documented deviation: not tracked by default
+    yr = s2.invert(X.abs(), inversion_mode="random")
+    assert tuple(yr.shape) == (2, 8192) and bool(torch.isfinite(yr).all())
+    yg = s2.invert(X.abs(), inversion_mode="griffin_lim")
+    assert tuple(yg.shape) == (2, 8192)
+    # Griffin-Lim is randomly initialised: judge spectral convergence, not samples
+    conv = float(((s2(yg).abs() - X[:, :33].abs()).norm() / X.abs().norm()))
+    assert conv < 0.35, "griffin-lim spectral convergence %.3f" % conv
+    ys = s2.invert(X.abs(), inversion_mode="sinebank")
+    assert ys.shape[0] == 2 and bool(torch.isfinite(ys).all())
+    d = T.DGT().cuda()
+    with pytest.raises(NotImplementedError):
+        d.invert(d(x).abs())                                                # PGHI: out of scope this round
+
+
+def test_normalize_module(T):
+    g = load_golden("normalize")
+    x = cu(g["x"])
+    for mode in ("unipolar", "bipolar", "gaussian"):
+        n = T.Normalize(mode)
+        n.scale_data(x)
+        assert n.offset.is_cuda and n.offset.ndim == 0
+        assert abs(float(n.offset) - float(g[mode + "_offset"])) <= 1e-5 and abs(float(n.scale) - float(g[mode + "_scale"])) <= 1e-5
+        assert_parity(host(n(x)), g[mode + "_y"], 1e-5, mode)
+        assert not n.needs_scaling
+    T.Normalize().test_forward(x)          # the reference's only numeric asserts (norm.py:60-67): min/max/mean/std
+    T.Normalize().test_inversion(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own test-suite flow (test/test_transforms.py) on this implementation
+# ---------------------------------------------------------------------------------------------
+def audio_classes(T):
+    out = []
+    for name in dir(T):
+        obj = getattr(T, name)
+        if isinstance(obj, type) and issubclass(obj, T.AudioTransform) and name not in ("AudioTransform", "ComposeAudioTransform"):
+            out.append(obj)
+    return out
+
+
+@pytest.fixture(scope="module")
+def raw():
+    """Stand-in for the reference's fixture (3 stereo clips zero-padded to a common length, [3, 2, L])."""
+    rng = np.random.default_rng(7)
+    L = 40000
+    x = np.zeros((3, 2, L), np.float32)
+    n = np.arange(L)
+    x[0] = 0.4 * np.sin(2 * np.pi * 220.0 * n / 44100)[None] * np.array([[1.0], [0.7]])
+    x[1, :, :30000] = 0.3 * rng.standard_normal((2, 30000))
+    x[2, :, :9000] = (np.exp(-n[:9000] / 1500.0) * np.sin(2 * np.pi * 60.0 * n[:9000] / 44100))[None]
+    return torch.from_numpy(x.astype(np.float32)).cuda()
+
+
+def test_reference_suite_forward_and_realtime(T, raw):
+    for cls in audio_classes(T):
+        tr = cls().cuda()
+        time = torch.zeros(raw.shape[:-1], device=raw.device)
+        tr.test_forward(raw)
+        tr.test_forward(raw, time)
+        cls().cuda().realtime().cuda().test_forward(raw, time)
+
+
+def test_reference_suite_inversion(T, raw):
+    for cls in audio_classes(T):
+        tr = cls().cuda()
+        if not tr.invertible:
+            continue
+        outs = tr.test_inversion(raw)
+        for k, v in outs.items():
+            assert bool(torch.isfinite(v).all()), (cls.__name__, k)
+        if cls.__name__ in ("STFT", "Real", "Imaginary", "Phase", "Cartesian"):    # (Polar: the inverse mel bank is a pseudo-inverse, quirk A8)
+            d = outs["direct"]
+            err = float((d - raw[..., :d.shape[-1]]).abs().max())
+            assert err < 2e-3, (cls.__name__, err)          # analysis/synthesis round trips reproduce the input
+
+
+def test_reference_suite_scripted(T):
+    for cls in audio_classes(T):
+        tr = cls()
+        if not tr.scriptable:
+            continue
+        sc = torch.jit.script(tr.cuda())
+        cls.test_scripted_transform(sc, invert=tr.invertible)
+
+
+def test_reference_suite_combinations(T, raw):
+    combos = {
+        "stft+magnitude": T.STFT() + T.Magnitude(),
+        "stereo+mulaw+onehot": T.Stereo() + T.MuLaw(channels=256) + T.OneHot(n_classes=256),
+        "stft+polar": T.STFT() + T.Polar(),
+        "overlap+stft": T.OverlapAdd() + T.RealtimeSTFT(),
+    }
+    for name, tr in combos.items():
+        tr = tr.cuda()
+        tr.realtime()
+        if tr.needs_scaling:
+            tr.scale_data(raw)
+        time = torch.zeros(*raw.shape[:-1], device=raw.device)
+        y, t = tr.forward_with_time(raw, time)
+        if tr.invertible and name != "stft+magnitude":
+            xi = tr.invert(y)
+            assert bool(torch.isfinite(xi.float()).all()), name
+        if name == "stft+magnitude":
+            xi = tr.invert(y, inversion_mode="random")
+            assert xi.shape[:2] == raw.shape[:2]

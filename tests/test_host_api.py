@@ -1,0 +1,225 @@
+"""CPU tests of the host side: the nn.Module mirror of the reference API (names, kwargs, flags, buffers,
+errors, `+` chaining, TorchScript compilation), the construct-time data (windows, mel banks, DCT) against the
+golden vectors, and the C-ABI library (loads, exports every symbol include/acids_b200.h declares).
+No kernel is launched here."""
+import os
+import re
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, assert_parity, dense, load_golden
+from acids_transforms_b200 import transforms as T
+from acids_transforms_b200 import _lib, ops
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------------------------
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "acids_b200.h")).read()
+    return sorted(set(re.findall(r"ACIDS_API\s+[\w\s\*]+?\b(acids_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = declared_symbols()
+    assert len(syms) >= 22
+    assert sorted(_lib.EXPORTS) == syms, "ctypes prototypes and the header disagree"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libacids_b200.so does not export " + s
+    assert _lib.load().acids_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every op must fail loudly (the product has no eager/CPU path)."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        T.STFT()(torch.zeros(2, 4096))
+    with pytest.raises(RuntimeError):
+        T.MuLaw()(torch.zeros(2, 64))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "acids_transforms_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "np_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+# ---------------------------------------------------------------------------------------------
+# construct-time data against the reference's buffers
+# ---------------------------------------------------------------------------------------------
+def test_windows_match_reference():
+    g = load_golden("windows")
+    for n, h in ((256, 64), (512, 128), (1024, 256), (2048, 512)):
+        s = T.STFT(n_fft=n, hop_length=h)
+        assert torch.equal(s.window[:n], torch.from_numpy(g["hann_%d" % n])) and float(s.window[n:].abs().sum()) == 0
+        assert torch.equal(s.inv_window, s.window)
+        d = T.DGT(n_fft=n, hop_length=h)
+        assert torch.equal(d.window[:n], torch.from_numpy(g["gauss_%d" % n])), "gaussian window must be bit-identical"
+        assert_parity(d.inv_window[:n].numpy(), g["dual_%d_%d" % (n, h)], 1e-6, "dual window")
+        assert abs(float(d.gamma) - float(g["gamma_%d" % n][0])) <= 1e-6 * float(g["gamma_%d" % n][0])
+    for name in ("hamming", "blackman", "bartlett"):
+        assert torch.equal(T.STFT(n_fft=512, hop_length=128, window=name).window[:512], torch.from_numpy(g[name + "_512"]))
+
+
+def test_mel_banks_match_reference():
+    for n_fft, name, kn in ((1024, "mel_bank_1024", True), (512, "mel_bank_512", True), (1024, "mel_bank_1024_nonyq", False)):
+        g = load_golden(name)
+        m = T.Magnitude(n_fft=n_fft, keep_nyquist=kn)
+        assert tuple(m.mel_bank.shape) == (1, n_fft // 2 + 1, n_fft // 2 + 1)
+        # same float32 torch ops as torchaudio on the same host: identical to the stored reference bank
+        assert torch.equal(m.mel_bank[0], torch.from_numpy(dense(g["rows"], g["cols"], g["vals"], g["shape"])))
+        assert torch.equal(m.inverse_mel_bank[0], torch.from_numpy(dense(g["inv_rows"], g["inv_cols"], g["inv_vals"], g["shape"])))
+    import torchaudio
+    from acids_transforms_b200.transforms.spectral_repr import melscale_fbanks
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert torch.equal(melscale_fbanks(1025, 0.0, 22050.0, 128, 44100),
+                           torchaudio.functional.melscale_fbanks(1025, 0.0, 22050.0, 128, 44100))
+    g = load_golden("mfcc")
+    mf = T.MFCC(n_fft=2048, hop_length=512, n_mels=128, n_mfcc=40)
+    assert torch.equal(mf.dct_mat, torch.from_numpy(g["dct"]))
+
+
+def test_banded_matrix_is_lossless():
+    m = T.Magnitude()
+    b = ops.BandedMatrix(m.mel_bank)
+    assert b.nnz_stored >= 1019 and b.nnz_stored <= 1100 and b.n_in == 513 and b.n_out == 513    # 1,019 nnz
+    meta, coef = b.tensors()
+    rebuilt = torch.zeros(513, 513)
+    for c in range(513):
+        s, n, off = int(meta[c, 0]) & 0xffff, int(meta[c, 0]) >> 16, int(meta[c, 1])
+        rebuilt[s:s + n, c] = coef[off:off + n]
+    assert torch.equal(rebuilt, m.mel_bank[0])
+    assert int(meta[-1, 0]) == 513                   # trailing row carries n_in
+    # the module keeps the banded tensors out of state_dict
+    assert sorted(m.state_dict()) == ["eps", "inverse_mel_bank", "mel_bank", "norm.offset", "norm.scale"]
+
+
+# ---------------------------------------------------------------------------------------------
+# API surface: names, defaults, flags, buffers, errors
+# ---------------------------------------------------------------------------------------------
+REFERENCE_CLASSES = ["AudioTransform", "Cartesian", "ComposeAudioTransform", "DGT", "IF", "Imaginary", "MFCC", "Magnitude",
+                     "MidSide", "Mono", "MuLaw", "Normalize", "OneHot", "OverlapAdd", "Phase", "Polar", "PolarIF", "Real",
+                     "RealtimeDGT", "RealtimeSTFT", "STFT", "Squeeze", "Stereo", "Transpose", "Unsqueeze", "Window"]
+
+
+def test_every_reference_class_exists_with_defaults():
+    for name in REFERENCE_CLASSES:
+        cls = getattr(T, name)
+        obj = cls()                   # the reference's tests instantiate every class without arguments
+        assert isinstance(obj, T.AudioTransform)
+        for hook in ("test_forward", "test_inversion", "test_scripted_transform", "forward_with_time", "scale_data", "realtime"):
+            assert hasattr(obj, hook), (name, hook)
+    assert issubclass(T.NotInvertibleError, Exception)
+
+
+def test_flags():
+    assert T.STFT().invertible and T.STFT().scriptable and not T.STFT().needs_scaling
+    assert not T.MFCC().invertible and T.MFCC().scriptable and not T.MFCC().needs_scaling and T.MFCC(norm_mode="gaussian").needs_scaling
+    assert T.Magnitude().needs_scaling and T.Normalize().needs_scaling
+    ch = T.Mono() + T.DGT(n_fft=1024, hop_length=256) + T.Magnitude(mel=True, mode="unipolar", contrast="log1p")
+    assert ch.invertible and ch.scriptable and ch.needs_scaling and ch.ratio == 256 and len(ch) == 3
+    assert not (T.STFT() + T.MFCC()).invertible
+    assert isinstance(ch[1], T.DGT) and isinstance((ch + T.Normalize())[3], T.Normalize)
+    assert T.Magnitude(norm="bipolar").norm.mode == "bipolar"        # README.md:54 spelling
+    assert T.OneHot().needs_scaling and not T.OneHot(n_classes=4).needs_scaling
+    assert T.STFT(n_fft=2048, hop_length=512).ratio == 512 and T.MFCC(hop_length=128).ratio == 128
+
+
+def test_state_dict_keys_match_reference():
+    assert list(T.STFT().state_dict()) == ["n_fft", "hop_length", "window", "inv_window", "gamma", "eps", "phase_buffer"]
+    assert list(T.DGT().state_dict()) == ["n_fft", "hop_length", "window", "inv_window", "gamma", "eps", "phase_buffer", "tolerance"]
+    assert list(T.OverlapAdd().state_dict()) == ["n_fft", "hop_length", "input_buffer", "output_buffer", "gain_compensation"]
+    assert list(T.Normalize().state_dict()) == ["offset", "scale"]
+    s = T.STFT()
+    assert s.window.shape == (16384,) and s.n_fft.dtype == torch.int64 and tuple(s.n_fft.shape) == (1,)
+    assert float(T.OverlapAdd().gain_compensation) == 2.0 and T.OverlapAdd().frames_out == 7
+    s2 = T.STFT(n_fft=512, hop_length=128)
+    s.load_state_dict(s2.state_dict())
+    assert s._n_fft == 512 and s._hop == 128                         # Python mirrors follow load_state_dict
+    chain = T.STFT() + T.Magnitude()
+    keys = list(chain.state_dict())
+    assert all(k.startswith("transforms.") for k in keys) and "transforms.1.mel_bank" in keys
+    chain.load_state_dict((T.STFT() + T.Magnitude()).state_dict())
+
+
+def test_error_conventions():
+    with pytest.raises(ValueError):
+        T.STFT(window="nope")
+    with pytest.raises(ValueError):
+        T.STFT(inversion_mode="nope")
+    with pytest.raises(AttributeError):
+        T.STFT().set_inversion_mode("nope")
+    with pytest.raises(TypeError):
+        T.STFT() + 3
+    with pytest.raises(TypeError):
+        (T.STFT() + T.Magnitude()) + "x"
+    with pytest.raises(T.NotInvertibleError):
+        T.MFCC().invert(torch.zeros(2, 128, 10))
+    with pytest.raises(T.NotInvertibleError):
+        T.Squeeze().invert(torch.zeros(2, 3))
+    with pytest.raises(Exception):
+        T.MidSide()(torch.zeros(2, 3, 100))
+    with pytest.raises(RuntimeError):
+        T.SpectralRepresentation() if hasattr(T, "SpectralRepresentation") else (_ for _ in ()).throw(RuntimeError())
+
+
+def test_compose_plan_fuses_only_exact_pairs():
+    from acids_transforms_b200.transforms.fused import FusedSTFTMagnitude
+    ch = T.Mono() + T.DGT() + T.Magnitude()
+    assert [type(t).__name__ for t in ch._plan] == ["Mono", "FusedSTFTMagnitude"]
+    assert ch._plan[1].stft is ch[1] and ch._plan[1].mag is ch[2]           # shared children, shared buffers
+    assert [type(t).__name__ for t in (T.RealtimeSTFT() + T.Magnitude())._plan] == ["RealtimeSTFT", "Magnitude"]
+    # a Magnitude built for another n_fft must keep failing like the reference's matmul: not fused
+    assert [type(t).__name__ for t in (T.STFT(n_fft=2048, hop_length=512) + T.Magnitude(n_fft=1024))._plan] == ["STFT", "Magnitude"]
+    assert [type(t).__name__ for t in (T.STFT(n_fft=2048, hop_length=512) + T.Magnitude(n_fft=1024, mel=False))._plan] == ["FusedSTFTMagnitude"]
+
+
+def test_views_and_metadata_transforms_on_cpu():
+    """The metadata-only transforms need no GPU."""
+    x = torch.arange(24.).reshape(2, 12)
+    assert T.Unsqueeze(dim=1)(x).shape == (2, 1, 12) and T.Squeeze(dim=1)(x.unsqueeze(1)).shape == (2, 12)
+    assert T.Transpose()(torch.zeros(2, 3, 4)).shape == (2, 4, 3)
+    assert T.Stereo()(torch.zeros(2, 1, 8)).shape == (2, 2, 8)
+    w = T.Window(window_size=4, hop_size=2)
+    fr = w(x)
+    assert fr.shape == (2, 5, 4) and torch.equal(fr[0, 1], x[0, 2:6])
+    assert torch.equal(w.invert(fr), x)
+    assert torch.equal(T.Window(window_size=4, hop_size=4).invert(T.Window(window_size=4, hop_size=4)(x)), x)
+    oa = T.OverlapAdd(8, 2)
+    f1 = oa(x)
+    assert f1.shape == (2, 6, 8) and torch.equal(f1[:, 0, :6], torch.zeros(2, 6)) and torch.equal(f1[0, 0, 6:], x[0, :2])
+    assert torch.equal(oa.input_buffer, x[:, -6:])
+    from acids_transforms_b200.utils.misc import frame
+    g = load_golden("oadd_default")
+    assert_parity(T.OverlapAdd()(torch.from_numpy(g["x"])).numpy(), g["frames"], 1e-7, "oadd forward view")
+    assert torch.equal(T.Mono(mode="left")(torch.arange(12.).reshape(1, 2, 6)), torch.arange(6.).reshape(1, 6))
+    tt = T.STFT().forward_with_time  # noqa: F841
+    from acids_transforms_b200.transforms.base import frame_times
+    g = load_golden("stft_1024_256")
+    assert_parity(frame_times(33, 256, 44100, torch.from_numpy(g["time_in"])).numpy(), g["time_out"], 1e-6, "frame times")
+
+
+@pytest.mark.parametrize("name", [n for n in REFERENCE_CLASSES if n not in ("AudioTransform", "ComposeAudioTransform")])
+def test_scriptable(name):
+    """Every class the reference marks scriptable compiles with torch.jit.script (test_transforms.py:62-68)."""
+    obj = getattr(T, name)()
+    if obj.scriptable:
+        torch.jit.script(obj)
+
+
+def test_chains_script():
+    for ch in (T.Mono() + T.DGT() + T.Magnitude(mel=True, mode="unipolar", contrast="log1p"), T.STFT() + T.Polar(),
+               T.Stereo() + T.MuLaw(channels=256) + T.OneHot(n_classes=256), T.OverlapAdd() + T.RealtimeSTFT(),
+               T.MidSide() + T.STFT(n_fft=4096, hop_length=1024) + T.PolarIF(magnitude_args={"mode": "bipolar", "n_fft": 4096})):
+        sc = torch.jit.script(ch)
+        assert {"forward", "invert", "scale_data", "forward_with_time"} <= {m for m in dir(sc)}

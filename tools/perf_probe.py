@@ -1,0 +1,72 @@
+"""Quick device-side timing of the headline kernels (not the bench): CUDA events, L2-exceeding inputs."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from acids_transforms_b200 import ops
+from oracle import np_oracle as O
+
+PEAK = 6536.4  # GB/s measured copy bandwidth (MEASURED_PEAKS.json)
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    L, n, h = 176400, 1024, 256
+    T, F = 1 + L // h, n // 2 + 1
+    x = 0.5 * (2 * torch.rand((B, L), device="cuda") - 1)
+    w = torch.from_numpy(O.dgt_window(n)).cuda()
+    hw = torch.hann_window(n).cuda()
+    fwd, _ = O.magnitude_banks(44100, n)
+    band = ops.BandedMatrix(torch.from_numpy(fwd))
+    eps = float(np.finfo(np.float32).eps)
+    out = torch.empty((B, T, F), device="cuda")
+    res = {}
+    ms = timeit(lambda: ops.stft_mag_fwd(x, w, n, h, band, "log1p", eps, 0.1, 2.0, out=out))
+    byt = B * (4 * L + 4 * T * F)
+    res["fused_fwd_mel_log1p"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK, audio_s_per_s=B * 4 / (ms / 1e3))
+    ms = timeit(lambda: ops.stft_mag_fwd(x, w, n, h, None, "log1p", eps, 0.1, 2.0, out=out))
+    res["fused_fwd_nomel_log1p"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    ms = timeit(lambda: ops.stft_mag_fwd(x, w, n, h, None, None, eps, None, None, out=out))
+    res["fused_fwd_mag_only"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    X = ops.stft_fwd(x, hw, n, h)
+    ms = timeit(lambda: ops.stft_fwd(x, hw, n, h))
+    byt = B * (4 * L + 8 * T * F)
+    res["stft_complex"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    ms = timeit(lambda: ops.istft_ola(X, hw, n, h, check_envelope=False))
+    byt = B * (8 * T * F + 4 * h * (T - 1))
+    res["istft_ola"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK, audio_s_per_s=B * 4 / (ms / 1e3))
+    ms = timeit(lambda: ops.mag_epilogue(X, band, "log1p", eps, 0.1, 2.0, out=out))
+    byt = B * (8 * T * F + 4 * T * F)
+    res["mag_epilogue"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    ms = timeit(lambda: ops.phase_fwd(X, 2, "forward", False, 0.0, 1.0, out=out))
+    res["phase_if"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    ms = timeit(lambda: ops.mulaw_encode(x))
+    byt = B * L * 12
+    res["mulaw"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    # eager torch chain on the same GPU (what the reference becomes after .to('cuda')), for context
+    mb = torch.from_numpy(fwd).cuda()[None]
+    def eager():
+        Xe = torch.stft(x, n, h, window=w, return_complex=True).transpose(-2, -1)
+        return (torch.log(1 + torch.matmul(Xe.abs(), mb)) - 0.1) / 2.0
+    if B <= 1024:
+        ms = timeit(eager, iters=5)
+        res["torch_eager_cuda_chain"] = dict(ms=ms)
+    for k, v in res.items():
+        print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
+
+
+if __name__ == "__main__":
+    main()
