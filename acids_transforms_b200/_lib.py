@@ -20,7 +20,7 @@ ONEHOT_IDS = {"none": 0, "categorical": 1, "channel": 2}
 
 class Band(Structure):
     """acids_band: banded (column-sparse) matrix descriptor."""
-    _fields_ = [("meta", c_void_p), ("coef", c_void_p), ("n_out", c_int32)]
+    _fields_ = [("meta", c_void_p), ("coef", c_void_p), ("n_out", c_int32), ("coef_len", c_int32)]
 
 
 class AcidsError(RuntimeError):

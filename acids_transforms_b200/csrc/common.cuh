@@ -8,7 +8,9 @@
 
 namespace acids {
 
+struct EpiParams;
 void set_error(const char* fmt, ...);           // capi.cu (thread-local message)
+int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, float eps, int drop_first, size_t smem_budget);  // stft_fwd.cu
 int num_sms();                                  // cached cudaDevAttrMultiProcessorCount
 
 #define ACIDS_REQUIRE(cond, code, ...)   \
@@ -55,23 +57,39 @@ __device__ __forceinline__ void stg_stream1(float* p, float x) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(x) : "memory");
 }
 
-// ---- epilogue shared by the fused STFT kernel and the stand-alone Magnitude kernel -------------
+// ---- epilogue shared by the fused STFT kernel and the stand-alone Magnitude kernels -------------
+//
+// Banded matrix, "group-ELL" layout (built by the host, see ops.BandedMatrix): output columns are taken
+// in groups of 32 (one warp); group g applies cnt[g] taps to every column, column m reading the input rows
+// start[m] .. start[m] + cnt[g] - 1 (columns with a narrower band are zero padded, start[] is shifted so the
+// window never leaves the input).  meta = [(cnt[g], base[g]) pairs | start[0..n_out)], coefficient u of
+// column m sits at coef[(base[g] + u) * 32 + (m & 31)]: lanes read consecutive floats, the trip count is
+// warp uniform, nothing diverges.
 struct EpiParams {
     const int32_t* meta;     // banded matrix (or nullptr)
     const float* coef;
-    int n_cols;              // columns before drop_first
+    int n_cols;              // output columns before drop_first
     int contrast;
     float eps;
-    float offset;            // already loaded from the device scalars
-    float inv_scale;
+    float inv_scale;         // 1 / scale                 (filled on the device from the Normalize buffers)
+    float neg_off_scaled;    // -offset / scale
     int drop_first;
+    int band_bytes_meta;     // bytes of meta / coef to stage in shared memory (0: read through L1)
+    int band_bytes_coef;
 };
 
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float apply_contrast(float a, int mode, float eps) {
-    // spectral_repr.py:191-201.  log(1 + m) is evaluated literally (not log1p), like the reference.
-    if (mode == ACIDS_CONTRAST_LOG1P) return logf(1.0f + a);
-    if (mode == ACIDS_CONTRAST_LOG) return logf(fmaxf(a, eps));
-    if (mode == ACIDS_CONTRAST_LOG10) return log10f(fmaxf(a, eps));
+    // spectral_repr.py:191-201.  log(1 + m) is evaluated literally (not log1p), like the reference;
+    // lg2.approx has 2^-22 relative error, two orders below the 1e-4 parity budget.
+    if (mode == ACIDS_CONTRAST_LOG1P) return __logf(1.0f + a);
+    if (mode == ACIDS_CONTRAST_LOG) return __logf(fmaxf(a, eps));
+    if (mode == ACIDS_CONTRAST_LOG10) return __log10f(fmaxf(a, eps));
     return a;
 }
 
@@ -83,31 +101,121 @@ __device__ __forceinline__ float invert_contrast(float y, int mode, float eps) {
     return y;
 }
 
-// One row: `val` holds n_in non-negative values in shared memory (|X| or |X|^p); the T threads of
-// the group produce columns tid, tid+T, ... : banded projection -> contrast -> normalise -> store.
-template <int T>
-__device__ __forceinline__ void epilogue_row(const float* __restrict__ val, int tid, const EpiParams& ep,
-                                             float* __restrict__ out_row, int64_t col_stride, bool valid) {
-    for (int m = tid; m < ep.n_cols; m += T) {
-        float a;
-        if (ep.meta != nullptr) {
-            const int2 me = __ldg(reinterpret_cast<const int2*>(ep.meta) + m);
-            const int start = me.x & 0xffff, cnt = me.x >> 16;
-            const float* c = ep.coef + me.y;
-            a = 0.f;
-            for (int u = 0; u < cnt; ++u) a = fmaf(val[start + u], __ldg(c + u), a);
-        } else {
-            a = val[m];
+// K taps of one column, straight-line
+template <int K>
+__device__ __forceinline__ float taps(const float* __restrict__ v, const float* __restrict__ c) {
+    float a = 0.f;
+#pragma unroll
+    for (int u = 0; u < K; ++u) a = fmaf(v[u], c[u << 5], a);
+    return a;
+}
+
+// sum_u val[start + u] * coef[u] for output column m.  The tap count is uniform over a group of 32 columns,
+// so the switch does not diverge inside a warp and every case is branch-free.
+__device__ __forceinline__ float band_column(const float* __restrict__ val, const int32_t* __restrict__ meta,
+                                             const float* __restrict__ coef, int n_groups, int m) {
+    const int2 gi = *reinterpret_cast<const int2*>(meta + 2 * (m >> 5));      // (cnt, base)
+    const float* __restrict__ v = val + meta[2 * n_groups + m];
+    const float* __restrict__ c = coef + (gi.y << 5) + (m & 31);
+    switch (gi.x) {
+        case 0: return 0.f;
+        case 1: return taps<1>(v, c);
+        case 2: return taps<2>(v, c);
+        case 3: return taps<3>(v, c);
+        case 4: return taps<4>(v, c);
+        case 5: return taps<5>(v, c);
+        case 6: return taps<6>(v, c);
+        case 7: return taps<7>(v, c);
+        case 8: return taps<8>(v, c);
+        default: {
+            float a = 0.f;
+            for (int u = 0; u < gi.x; ++u) a = fmaf(v[u], c[u << 5], a);
+            return a;
         }
-        a = apply_contrast(a, ep.contrast, ep.eps);
-        a = (a - ep.offset) * ep.inv_scale;
-        if (valid && m >= ep.drop_first) stg_stream1(out_row + (int64_t)(m - ep.drop_first) * col_stride, a);
     }
 }
 
-__device__ __forceinline__ void load_norm(const float* offset, const float* scale, float& off, float& inv) {
-    off = offset ? __ldg(offset) : 0.f;
-    inv = scale ? 1.0f / __ldg(scale) : 1.0f;
+template <int CONTRAST>
+__device__ __forceinline__ float contrast_ct(float a, float eps) {
+    // spectral_repr.py:191-201.  log(1 + m) is evaluated literally (not log1p), like the reference;
+    // lg2.approx has 2^-22 relative error, two orders below the 1e-4 parity budget.
+    if (CONTRAST == ACIDS_CONTRAST_LOG1P) return __logf(1.0f + a);
+    if (CONTRAST == ACIDS_CONTRAST_LOG) return __logf(fmaxf(a, eps));
+    if (CONTRAST == ACIDS_CONTRAST_LOG10) return __log10f(fmaxf(a, eps));
+    return a;
+}
+
+template <int T, int CONTRAST, bool BAND>
+__device__ __forceinline__ void epilogue_cols(const float* __restrict__ val, int tid, const EpiParams& ep,
+                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
+                                              float* __restrict__ o, int64_t step, bool valid) {
+    // o points at this thread's first column (already shifted by drop_first); consecutive columns of a thread
+    // are T apart, i.e. `step` floats in the output
+    const int n_groups = (ep.n_cols + 31) >> 5;
+    for (int m = tid; m < ep.n_cols; m += T, o += step) {
+        float a = BAND ? band_column(val, meta, coef, n_groups, m) : val[m];
+        a = fmaf(contrast_ct<CONTRAST>(a, ep.eps), ep.inv_scale, ep.neg_off_scaled);
+        if (valid && m >= ep.drop_first) stg_stream1(o, a);
+    }
+}
+
+// One row: `val` holds the non-negative inputs (|X| or |X|^p) in shared memory; the T threads of the group
+// produce columns tid, tid+T, ...: banded projection -> contrast -> normalise -> streaming store.
+// The (uniform) contrast mode and band presence are dispatched once per row, not once per column.
+template <int T>
+__device__ __forceinline__ void epilogue_row(const float* __restrict__ val, int tid, const EpiParams& ep,
+                                             const int32_t* __restrict__ meta, const float* __restrict__ coef,
+                                             float* __restrict__ out_row, int64_t col_stride, bool valid) {
+    float* o = out_row + (int64_t)(tid - ep.drop_first) * col_stride;
+    const int64_t step = (int64_t)T * col_stride;
+    if (meta != nullptr) {
+        switch (ep.contrast) {
+            case ACIDS_CONTRAST_LOG1P: epilogue_cols<T, ACIDS_CONTRAST_LOG1P, true>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG: epilogue_cols<T, ACIDS_CONTRAST_LOG, true>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG10: epilogue_cols<T, ACIDS_CONTRAST_LOG10, true>(val, tid, ep, meta, coef, o, step, valid); break;
+            default: epilogue_cols<T, ACIDS_CONTRAST_NONE, true>(val, tid, ep, meta, coef, o, step, valid); break;
+        }
+    } else {
+        switch (ep.contrast) {
+            case ACIDS_CONTRAST_LOG1P: epilogue_cols<T, ACIDS_CONTRAST_LOG1P, false>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG: epilogue_cols<T, ACIDS_CONTRAST_LOG, false>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG10: epilogue_cols<T, ACIDS_CONTRAST_LOG10, false>(val, tid, ep, meta, coef, o, step, valid); break;
+            default: epilogue_cols<T, ACIDS_CONTRAST_NONE, false>(val, tid, ep, meta, coef, o, step, valid); break;
+        }
+    }
+}
+
+// stage the banded matrix in shared memory (all threads of the CTA); returns the pointers to use
+__device__ __forceinline__ void stage_band(const EpiParams& ep, unsigned char* smem_band, const int32_t*& meta,
+                                           const float*& coef) {
+    meta = ep.meta;
+    coef = ep.coef;
+    if (ep.meta != nullptr && ep.band_bytes_meta > 0) {
+        int32_t* sm = reinterpret_cast<int32_t*>(smem_band);
+        float* sc = reinterpret_cast<float*>(smem_band + ep.band_bytes_meta);
+        for (int i = threadIdx.x; i < ep.band_bytes_meta / 4; i += blockDim.x) sm[i] = __ldg(ep.meta + i);
+        for (int i = threadIdx.x; i < ep.band_bytes_coef / 4; i += blockDim.x) sc[i] = __ldg(ep.coef + i);
+        meta = sm;
+        coef = sc;
+    }
+}
+
+__device__ __forceinline__ void load_norm(const float* offset, const float* scale, EpiParams& ep) {
+    // (x - offset) / scale as one FFMA: x * (1/scale) + (-offset/scale)   (norm.py:40-41)
+    const float off = offset ? __ldg(offset) : 0.f;
+    ep.inv_scale = scale ? 1.0f / __ldg(scale) : 1.0f;
+    ep.neg_off_scaled = -off * ep.inv_scale;
+}
+
+// bytes of shared memory the banded matrix needs, or 0 when it should stay in global memory
+static inline void band_smem_plan(const acids_band& band, int64_t coef_floats, int64_t meta_ints, size_t budget, EpiParams& ep) {
+    ep.band_bytes_meta = ep.band_bytes_coef = 0;
+    if (!band.meta) return;
+    const size_t need = (size_t)(meta_ints + coef_floats) * 4;
+    if (need <= budget) {
+        ep.band_bytes_meta = (int)(meta_ints * 4);
+        ep.band_bytes_coef = (int)(coef_floats * 4);
+    }
 }
 
 }  // namespace acids

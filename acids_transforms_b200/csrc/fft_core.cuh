@@ -137,11 +137,23 @@ ACIDS_HD cf unit(int num, int den) {
     return mk(c, s);
 }
 
-// Shared-memory index swizzle for the exchange that follows pass P (pad one slot every 2^PADLOG).
+// Shared-memory index swizzle for the exchange buffers (pad one slot every 2^PADLOG slots).
+// swz(base + c) == swz(base) + swz(c) whenever (base mod 2^PADLOG) + (c mod 2^PADLOG) < 2^PADLOG, which
+// holds for every (pass, butterfly, slot) of every plan (checked exhaustively by tests/emu/emu_fft.cpp):
+// each access is one per-thread base plus a compile-time immediate.
 template <int PADLOG>
 ACIDS_HD int swz(int i) {
     return i + (i >> PADLOG);
 }
+template <int PADLOG>
+ACIDS_HD constexpr int swzc(int c) {
+    return c + (c >> PADLOG);
+}
+#if !defined(__CUDA_ARCH__) && defined(ACIDS_EMU_CHECK)
+#define ACIDS_EMU_ASSERT(cond) do { if (!(cond)) { printf("emu assert failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); abort(); } } while (0)
+#else
+#define ACIDS_EMU_ASSERT(cond) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Plan: N real points, T threads per frame, up to 4 passes.  For the forward transform the LAST
@@ -167,7 +179,11 @@ struct Plan {
     }
     static constexpr int nb(int p) { return M / radix(p); }          // butterflies in pass p
     static constexpr int bpt(int p) { return nb(p) / T_; }           // butterflies per thread
-    // twiddle storage: pass p >= 1 keeps (R-1) factors per butterfly it owns
+    // twiddle storage: pass p >= 1 keeps (R-1) factors per butterfly it owns; when T is a multiple of Ns the
+    // twiddle index k = (tid + T b) mod Ns does not depend on b and ONE set serves all of a thread's butterflies
+    // (tw_shared is overridden to false for the paired pass by FrameFFT, whose butterflies are not tid + T b)
+    static constexpr bool tw_shared(int p) { return p > 0 && (T_ % ns(p)) == 0; }
+    static constexpr int tw_sets(int p, bool paired) { return (tw_shared(p) && !paired) ? 1 : bpt(p); }
     static constexpr int tw_count(int p) { return p == 0 ? 0 : bpt(p) * (radix(p) - 1); }
     static constexpr int tw_off(int p) {
         int s = 0;
@@ -188,6 +204,12 @@ struct Pairing {
     static ACIDS_HD int jb(int tid, int c) {
         int pi = tid + P::T * c;
         return pi == 0 ? NB / 2 : NB - pi;
+    }
+    // k1(tid, c, s) = (s < R/2 ? klo : khi) + s * NB: two per-thread bases, the rest is an immediate
+    static ACIDS_HD int klo(int tid, int c) { return tid + P::T * c; }       // 0 for the self-mirrored pair
+    static ACIDS_HD int khi(int tid, int c) {
+        int pi = tid + P::T * c;
+        return pi != 0 ? pi : NB / 2 - (R / 2) * NB;
     }
     // bin index of untangle slot s of pair c: X[k1] and X[M - k1] come out of it
     static ACIDS_HD int k1(int tid, int c, int s) {
@@ -210,8 +232,11 @@ struct FrameFFT {
     int tid;
 
     template <int PASS>
+    static constexpr bool tw_is_shared() { return PASS != PAIRED && P::tw_shared(PASS); }
+
+    template <int PASS>
     ACIDS_HD void init_pass() {
-        constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = P::bpt(PASS);
+        constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = tw_is_shared<PASS>() ? 1 : P::bpt(PASS);
         if (PASS > 0) {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
@@ -269,8 +294,9 @@ struct FrameFFT {
 #pragma unroll
         for (int b = 0; b < B; ++b) {
             if (PASS > 0) {
+                constexpr int bs = tw_is_shared<PASS>() ? 0 : 1;
 #pragma unroll
-                for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], tw[P::tw_off(PASS) + b * (R - 1) + (r - 1)]);
+                for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], tw[P::tw_off(PASS) + bs * b * (R - 1) + (r - 1)]);
             }
             Dft<R, INV>::run(v + b * R);
         }
@@ -278,20 +304,30 @@ struct FrameFFT {
 
     template <int PASS>
     ACIDS_HD void store(const cf* v, cf* s) const {
-        constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS), NS = P::ns(PASS);
 #pragma unroll
-        for (int b = 0; b < B; ++b)
+        for (int b = 0; b < B; ++b) {
+            cf* sb = s + swz<P::PADLOG>(out_index<PASS>(b, 0));
 #pragma unroll
-            for (int q = 0; q < R; ++q) s[swz<P::PADLOG>(out_index<PASS>(b, q))] = v[b * R + q];
+            for (int q = 0; q < R; ++q) {
+                ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q)) == swz<P::PADLOG>(out_index<PASS>(b, 0)) + swzc<P::PADLOG>(q * NS));
+                sb[swzc<P::PADLOG>(q * NS)] = v[b * R + q];
+            }
+        }
     }
 
     template <int PASS>
     ACIDS_HD void load(cf* v, const cf* s) const {
-        constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS), NB = P::nb(PASS);
 #pragma unroll
-        for (int b = 0; b < B; ++b)
+        for (int b = 0; b < B; ++b) {
+            const cf* sb = s + swz<P::PADLOG>(in_index<PASS>(b, 0));
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[b * R + r] = s[swz<P::PADLOG>(in_index<PASS>(b, r))];
+            for (int r = 0; r < R; ++r) {
+                ACIDS_EMU_ASSERT(swz<P::PADLOG>(in_index<PASS>(b, r)) == swz<P::PADLOG>(in_index<PASS>(b, 0)) + swzc<P::PADLOG>(r * NB));
+                v[b * R + r] = sb[swzc<P::PADLOG>(r * NB)];
+            }
+        }
     }
 
     // ---- forward untangle (after the paired last pass): v holds Z, produce X -------------------

@@ -35,20 +35,27 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
                                               cf* v, cf* s, int g) {
     constexpr int M = P::M, T = P::T, V = P::V;
     using PR = typename FrameFFT<P, true>::PR;
+    constexpr int RP = PR::R, NBP = PR::NB;
     auto gsync = [&]() { group_sync<T, THREADS>(g); };
     cf i1[V / 2], i2[V / 2], ex;
     if (valid) {
+        const float2* __restrict__ r2 = reinterpret_cast<const float2*>(row);
 #pragma unroll
-        for (int c = 0; c < PR::PC; ++c)
+        for (int c = 0; c < PR::PC; ++c) {
+            // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
+            const float2* lo = r2 + PR::klo(fft.tid, c);
+            const float2* hi = r2 + PR::khi(fft.tid, c);
+            const float2* mlo = r2 + (M - PR::klo(fft.tid, c));
+            const float2* mhi = r2 + (M - PR::khi(fft.tid, c));
 #pragma unroll
-            for (int q = 0; q < PR::R; ++q) {
-                const int k = PR::k1(fft.tid, c, q);
-                const float2 a = ldg_stream2(reinterpret_cast<const float2*>(row + k));
-                const float2 d = ldg_stream2(reinterpret_cast<const float2*>(row + (M - k)));
-                i1[c * PR::R + q] = mk(a.x, a.y);
-                i2[c * PR::R + q] = mk(d.x, d.y);
+            for (int q = 0; q < RP; ++q) {
+                const float2 a = ldg_stream2((q < RP / 2 ? lo : hi) + q * NBP);
+                const float2 d = ldg_stream2((q < RP / 2 ? mlo : mhi) - q * NBP);
+                i1[c * RP + q] = mk(a.x, a.y);
+                i2[c * RP + q] = mk(d.x, d.y);
             }
-        const float2 e = __ldg(reinterpret_cast<const float2*>(row + M / 2));
+        }
+        const float2 e = __ldg(r2 + M / 2);
         ex = mk(e.x, e.y);
     } else {
 #pragma unroll
@@ -78,44 +85,57 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
     }
 }
 
-template <class P, int THREADS>
-__global__ void __launch_bounds__(THREADS) istft_ola_kernel(const InvParams p) {
-    constexpr int N = P::N, T = P::T, V = P::V, G = THREADS / T;
-    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP);
+// launch shape per plan (see FwdCfg): small frame groups run 128-thread CTAs
+template <class P>
+struct InvCfg {
+    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
+    static constexpr int MINB = P::T <= 32 ? 3 : (P::T <= 256 ? 2 : 1);
+    static constexpr int G = THREADS / P::T;
+};
+
+template <class P>
+__global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola_kernel(const InvParams p) {
+    constexpr int THREADS = InvCfg<P>::THREADS;
+    constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = THREADS / T;
+    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP), NSL = P::ns(LP);
     using FFT = FrameFFT<P, true>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
     float* ring = reinterpret_cast<float*>(reinterpret_cast<cf*>(smem_raw) + (size_t)G * P::SMEM_CF);
-    float* g2 = ring + (size_t)p.ring * N;
+    float* g2 = ring + (size_t)p.ring * N;           // window^2, for the envelope at the clip edges
+    float2* swin = reinterpret_cast<float2*>(g2 + N);  // synthesis window pairs with irfft's 1/N folded in
+    float* inv_env = reinterpret_cast<float*>(swin + M);   // 1 / sum_i g^2[r + i hop]: the interior envelope
 
     FFT fft;
     fft.init(tid);
-    // synthesis window taps of this thread's output samples, with irfft's 1/N folded in
-    float2 win[V];
-#pragma unroll
-    for (int b = 0; b < BL; ++b)
-#pragma unroll
-        for (int q = 0; q < RL; ++q) {
-            const int n = fft.template out_index<LP>(b, q);
-            win[b * RL + q] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
-        }
+    const int hop = p.hop;
     for (int i = threadIdx.x; i < N; i += THREADS) {
         const float w = __ldg(p.window + i);
         g2[i] = w * w;
     }
+    for (int n = threadIdx.x; n < M; n += THREADS)
+        swin[n] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
+    __syncthreads();
+    const bool aligned = (N % hop) == 0;             // integer overlap: every hop segment sees the same frames
+    if (aligned)
+        for (int r = threadIdx.x; r < hop; r += THREADS) {
+            float e = 0.f;
+            for (int i = N / hop - 1; i >= 0; --i) e += g2[r + i * hop];     // ascending frame order, like col2im
+            inv_env[r] = 1.0f / e;
+        }
 
     const int64_t clip = blockIdx.x / p.chunks_per_clip;
     const int ch = blockIdx.x % p.chunks_per_clip;
+    const int nT = p.n_frames;
     const int ta = ch * p.chunk_frames;
-    const int tb = min(p.n_frames, ta + p.chunk_frames);
-    const int hop = p.hop;
+    const int tb = min(nT, ta + p.chunk_frames);
     // padded-sample span owned by this CTA
     const int64_t own_lo = (int64_t)ta * hop;
-    const int64_t own_hi = (tb == p.n_frames) ? (int64_t)(p.n_frames - 1) * hop + N : (int64_t)tb * hop;
+    const int64_t own_hi = (tb == nT) ? (int64_t)(nT - 1) * hop + N : (int64_t)tb * hop;
     const int t_start = max(0, ta - (p.ovc - 1));
     int64_t emitted = own_lo;
-    const cf* __restrict__ Xc = p.X + clip * (int64_t)p.n_frames * P::F;
+    const cf* __restrict__ Xc = p.X + clip * (int64_t)nT * P::F;
     float* __restrict__ outc = p.out + clip * p.out_len;
     __syncthreads();
 
@@ -127,29 +147,58 @@ __global__ void __launch_bounds__(THREADS) istft_ola_kernel(const InvParams p) {
         if (valid) {
             float2* slot = reinterpret_cast<float2*>(ring + (size_t)(t % p.ring) * N);
 #pragma unroll
-            for (int b = 0; b < BL; ++b)
+            for (int b = 0; b < BL; ++b) {
+                // last-pass outputs sit at n = (tid + T b) + q * Ns: one base, compile-time offsets
+                float2* dst = slot + (tid + T * b);
+                const float2* wv = swin + (tid + T * b);
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
-                    const int n = fft.template out_index<LP>(b, q);
-                    slot[n] = make_float2(v[b * RL + q].x * win[b * RL + q].x, v[b * RL + q].y * win[b * RL + q].y);
+                    const float2 w = wv[q * NSL];
+                    dst[q * NSL] = make_float2(v[b * RL + q].x * w.x, v[b * RL + q].y * w.y);
                 }
+            }
         }
         __syncthreads();
         // gather every sample that no later frame can touch
         const int t_done = min(tr + G, tb) - 1;
-        const int64_t hi = (t_done == p.n_frames - 1) ? own_hi : min(own_hi, (int64_t)(t_done + 1) * hop);
-        for (int64_t np = emitted + threadIdx.x; np < hi; np += THREADS) {
-            const int64_t num = np - N + hop;
-            const int t_lo = num > 0 ? (int)(num / hop) : 0;
-            const int t_hi = min((int64_t)p.n_frames - 1, np / hop);
-            float acc = 0.f, env = 0.f;
-            for (int tt = t_lo; tt <= t_hi; ++tt) {
-                const int m = (int)(np - (int64_t)tt * hop);
-                acc += ring[(size_t)(tt % p.ring) * N + m];
-                env += g2[m];
+        const int64_t hi = (t_done == nT - 1) ? own_hi : min(own_hi, (int64_t)(t_done + 1) * hop);
+        if (aligned) {
+            // whole hop segments; segment q gets frames [max(0, q - ov + 1), min(nT - 1, q)]
+            const int ov = N / hop;
+            const int q0 = (int)(emitted / hop), q1 = (int)(hi / hop);
+            for (int q = q0; q < q1; ++q) {
+                const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
+                const bool interior = (t_hi - t_lo + 1) == ov;
+                const int64_t nbase = (int64_t)q * hop - p.trim;
+                for (int r = threadIdx.x; r < hop; r += THREADS) {
+                    float acc = 0.f;
+                    for (int tt = t_lo; tt <= t_hi; ++tt) acc += ring[(size_t)(tt % p.ring) * N + r + (q - tt) * hop];
+                    float y;
+                    if (interior) {
+                        y = acc * inv_env[r];
+                    } else {
+                        float env = 0.f;
+                        for (int tt = t_lo; tt <= t_hi; ++tt) env += g2[r + (q - tt) * hop];
+                        y = acc / env;
+                    }
+                    const int64_t n = nbase + r;
+                    if (n >= 0 && n < p.out_len) stg_stream1(outc + n, y);
+                }
             }
-            const int64_t n = np - p.trim;
-            if (n >= 0 && n < p.out_len) stg_stream1(outc + n, acc / env);
+        } else {
+            for (int64_t np = emitted + threadIdx.x; np < hi; np += THREADS) {
+                const int64_t num = np - N + hop;
+                const int t_lo = num > 0 ? (int)(num / hop) : 0;
+                const int t_hi = (int)min((int64_t)nT - 1, np / hop);
+                float acc = 0.f, env = 0.f;
+                for (int tt = t_lo; tt <= t_hi; ++tt) {
+                    const int m = (int)(np - (int64_t)tt * hop);
+                    acc += ring[(size_t)(tt % p.ring) * N + m];
+                    env += g2[m];
+                }
+                const int64_t n = np - p.trim;
+                if (n >= 0 && n < p.out_len) stg_stream1(outc + n, acc / env);
+            }
         }
         if (hi > emitted) emitted = hi;
         __syncthreads();
@@ -164,24 +213,21 @@ struct InvFramesParams {
     float* out;
 };
 
-template <class P, int THREADS>
-__global__ void __launch_bounds__(THREADS) irfft_frames_kernel(const InvFramesParams p) {
-    constexpr int N = P::N, T = P::T, V = P::V, G = THREADS / T;
-    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP);
+template <class P>
+__global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) irfft_frames_kernel(const InvFramesParams p) {
+    constexpr int THREADS = InvCfg<P>::THREADS;
+    constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = THREADS / T;
+    constexpr int LP = P::NP - 1, RL = P::radix(LP), BL = P::bpt(LP), NSL = P::ns(LP);
     using FFT = FrameFFT<P, true>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
+    float2* swin = reinterpret_cast<float2*>(reinterpret_cast<cf*>(smem_raw) + (size_t)G * P::SMEM_CF);
     FFT fft;
     fft.init(tid);
-    float2 win[V];
-#pragma unroll
-    for (int b = 0; b < BL; ++b)
-#pragma unroll
-        for (int q = 0; q < RL; ++q) {
-            const int n = fft.template out_index<LP>(b, q);
-            win[b * RL + q] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
-        }
+    for (int n = threadIdx.x; n < M; n += THREADS)
+        swin[n] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
+    __syncthreads();
     const int64_t units = (p.rows + G - 1) / G;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
         const int64_t r = u * G + g;
@@ -189,14 +235,16 @@ __global__ void __launch_bounds__(THREADS) irfft_frames_kernel(const InvFramesPa
         cf v[V];
         inverse_frame<P, THREADS>(fft, p.X + r * (int64_t)P::F, valid, v, s, g);
         if (valid) {
-            float2* dst = reinterpret_cast<float2*>(p.out + r * (int64_t)N);
 #pragma unroll
-            for (int b = 0; b < BL; ++b)
+            for (int b = 0; b < BL; ++b) {
+                float2* dst = reinterpret_cast<float2*>(p.out + r * (int64_t)N) + (tid + T * b);
+                const float2* wv = swin + (tid + T * b);
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
-                    const int n = fft.template out_index<LP>(b, q);
-                    stg_stream2(dst + n, v[b * RL + q].x * win[b * RL + q].x, v[b * RL + q].y * win[b * RL + q].y);
+                    const float2 w = wv[q * NSL];
+                    stg_stream2(dst + q * NSL, v[b * RL + q].x * w.x, v[b * RL + q].y * w.y);
                 }
+            }
         }
         group_sync<T, THREADS>(g);   // next frame's store<0> must not overtake this frame's last reads
     }
@@ -244,14 +292,16 @@ __global__ void ola_gather_kernel(const OlaParams p) {
 
 template <class P>
 struct InvLaunch {
-    static constexpr int THREADS = P::T > 256 ? P::T : 256;
-    static constexpr int G = THREADS / P::T;
-    static size_t smem_ola(int ovc) {
-        return (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float);
+    static constexpr int THREADS = InvCfg<P>::THREADS;
+    static constexpr int G = InvCfg<P>::G;
+    static size_t smem_ola(int ovc, int hop) {
+        // exchange buffers | frame ring | window^2 | window pairs | interior inverse envelope
+        return (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float) +
+               (size_t)P::M * sizeof(float2) + (size_t)hop * sizeof(float);
     }
     static int ola(InvParams p, cudaStream_t st) {
-        auto kern = istft_ola_kernel<P, THREADS>;
-        const size_t smem = smem_ola(p.ovc);
+        auto kern = istft_ola_kernel<P>;
+        const size_t smem = smem_ola(p.ovc, p.hop);
         static size_t reserved = 0;
         if (smem > reserved) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -280,8 +330,8 @@ struct InvLaunch {
         return ACIDS_OK;
     }
     static int frames(const InvFramesParams& p, cudaStream_t st) {
-        auto kern = irfft_frames_kernel<P, THREADS>;
-        constexpr size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf);
+        auto kern = irfft_frames_kernel<P>;
+        constexpr size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)P::M * sizeof(float2);
         static int ctas_per_sm = 0;
         if (ctas_per_sm == 0) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -324,7 +374,7 @@ static const size_t kMaxSmem = 227 * 1024;
 static int fused_fits(int n_fft, int hop, bool& fits) {
     const int ovc = (n_fft + hop - 1) / hop;
     size_t need = 0;
-    ACIDS_INV_SWITCH(n_fft, need = InvLaunch<PL>::smem_ola(ovc));
+    ACIDS_INV_SWITCH(n_fft, need = InvLaunch<PL>::smem_ola(ovc, hop));
     fits = need <= kMaxSmem;
     return ACIDS_OK;
 }

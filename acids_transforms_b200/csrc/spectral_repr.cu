@@ -21,21 +21,25 @@ struct MagParams {
 };
 
 __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* val = smem + (size_t)warp * p.n_bins;
+    float* val = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.n_bins;
     EpiParams ep = p.ep;
-    load_norm(p.offset_ptr, p.scale_ptr, ep.offset, ep.inv_scale);
+    load_norm(p.offset_ptr, p.scale_ptr, ep);
+    const int32_t* bmeta;
+    const float* bcoef;
+    stage_band(ep, smem_raw + (size_t)8 * p.n_bins * sizeof(float), bmeta, bcoef);
+    __syncthreads();
     const int64_t wpg = (int64_t)gridDim.x * 8;
     for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < p.rows; r += wpg) {
         const float2* __restrict__ row = p.X + r * p.n_bins;
         __syncwarp();
         for (int k = lane; k < p.n_bins; k += 32) {
             const float2 a = ldg_stream2(row + k);
-            val[k] = sqrtf(a.x * a.x + a.y * a.y);
+            val[k] = fast_sqrt(a.x * a.x + a.y * a.y);
         }
         __syncwarp();
-        epilogue_row<32>(val, lane, ep, p.out + r * p.out_row_stride, 1, true);
+        epilogue_row<32>(val, lane, ep, bmeta, bcoef, p.out + r * p.out_row_stride, 1, true);
     }
 }
 
@@ -75,16 +79,7 @@ __global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
         __syncwarp();
         float* __restrict__ out = p.out + r * (int64_t)p.n_out;
         for (int m = lane; m < p.n_out; m += 32) {
-            float a;
-            if (p.meta) {
-                const int2 me = __ldg(reinterpret_cast<const int2*>(p.meta) + m);
-                const int start = me.x & 0xffff, cnt = me.x >> 16;
-                const float* c = p.coef + me.y;
-                a = 0.f;
-                for (int u = 0; u < cnt; ++u) a = fmaf(val[start + u], __ldg(c + u), a);
-            } else {
-                a = val[m];
-            }
+            const float a = p.meta ? band_column(val, p.meta, p.coef, (p.n_out + 31) >> 5, m) : val[m];
             stg_stream1(out + m, a);
         }
     }
@@ -258,7 +253,8 @@ __global__ void polar_to_complex_kernel(const float* __restrict__ mag, const flo
 }
 
 static int check_band(const acids_band& band) {
-    ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0), ACIDS_EINVAL, "banded matrix without coefficients");
+    ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0 && (band.coef_len & 31) == 0), ACIDS_EINVAL,
+                  "malformed banded matrix (n_out=%d coef_len=%d)", band.n_out, band.coef_len);
     return ACIDS_OK;
 }
 
@@ -278,10 +274,10 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     if (rows == 0) return ACIDS_OK;
     MagParams p{};
     p.X = reinterpret_cast<const float2*>(X); p.rows = rows; p.n_bins = n_bins;
-    p.ep.meta = band.meta; p.ep.coef = band.coef; p.ep.n_cols = band.meta ? band.n_out : n_bins;
-    p.ep.contrast = contrast; p.ep.eps = eps; p.ep.drop_first = drop_first;
+    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, 24 * 1024);
+    if (rc) return rc;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
-    const size_t smem = (size_t)8 * n_bins * sizeof(float);
+    const size_t smem = (size_t)8 * n_bins * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
     static size_t reserved = 48 * 1024;
     if (smem > reserved) {
         ACIDS_REQUIRE(cudaFuncSetAttribute(mag_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,

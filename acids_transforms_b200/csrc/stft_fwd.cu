@@ -8,7 +8,7 @@
 //
 // HBM traffic per frame (ideal = achieved): hop*4 B in, (n_fft/2+1)*8 B out (complex mode) or
 // n_cols*4 B out (fused mode).  Everything else lives in registers and 4.3 KB of shared memory
-// per frame group.
+// per frame group (+ the banded mel matrix, staged once per CTA).
 #include "common.cuh"
 #include "plans.cuh"
 
@@ -31,12 +31,30 @@ struct FwdParams {
     int vec_ok;      // rows and frame starts are 8-byte aligned: float2 loads allowed
 };
 
-template <class P, int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS) stft_fwd_kernel(const FwdParams p) {
+// launch shape per plan: small frame groups run 128-thread CTAs at 4 CTAs / SM (<= 128 registers)
+template <class P>
+struct FwdCfg {
+    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
+    static constexpr int MINB = P::T <= 32 ? 4 : (P::T <= 256 ? 2 : 1);
+    static constexpr int G = THREADS / P::T;
+};
+
+// |X|^power from the squared magnitude; pmode: 1 -> magnitude, 2 -> power spectrum, 0 -> general exponent
+__device__ __forceinline__ float pow_value(float re, float im, int pmode, float power) {
+    const float p2 = re * re + im * im;
+    if (pmode == 1) return fast_sqrt(p2);
+    if (pmode == 2) return p2;
+    return powf(fast_sqrt(p2), power);
+}
+
+template <class P, int MODE>
+__global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_kernel(const FwdParams p) {
+    constexpr int THREADS = FwdCfg<P>::THREADS;
     constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = THREADS / T;
-    constexpr int R0 = P::radix(0), B0 = P::bpt(0);
+    constexpr int R0 = P::radix(0), B0 = P::bpt(0), NB0 = P::nb(0);
     using FFT = FrameFFT<P, false>;
     using PR = typename FFT::PR;
+    constexpr int RP = PR::R, NBP = PR::NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
@@ -46,24 +64,33 @@ __global__ void __launch_bounds__(THREADS) stft_fwd_kernel(const FwdParams p) {
     //      the factor of the even/odd split) ----
     FFT fft;
     fft.init(tid);
-    float2 win[V];
-#pragma unroll
-    for (int b = 0; b < B0; ++b)
-#pragma unroll
-        for (int r = 0; r < R0; ++r) {
-            const int n = fft.template in_index<0>(b, r);
-            win[b * R0 + r] = make_float2(0.5f * __ldg(p.window + 2 * n), 0.5f * __ldg(p.window + 2 * n + 1));
-        }
+    // analysis window as (w[2n], w[2n+1]) / 2 pairs in shared memory: the pass-0 operands of a thread are
+    // consecutive float2 across the group, so the reads are conflict free and cost no registers
+    float2* swin = reinterpret_cast<float2*>(smem_raw + (size_t)G * P::SMEM_CF * sizeof(cf));
+    for (int n = threadIdx.x; n < M; n += THREADS)
+        swin[n] = make_float2(0.5f * __ldg(p.window + 2 * n), 0.5f * __ldg(p.window + 2 * n + 1));
     EpiParams ep = p.ep;
-    if (MODE == MODE_REAL) load_norm(p.offset_ptr, p.scale_ptr, ep.offset, ep.inv_scale);
+    const int32_t* bmeta = nullptr;
+    const float* bcoef = nullptr;
+    if (MODE == MODE_REAL) {
+        load_norm(p.offset_ptr, p.scale_ptr, ep);
+        stage_band(ep, smem_raw + (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)M * sizeof(float2), bmeta, bcoef);
+    }
+    __syncthreads();
 
+    const int pmode = p.power == 1.0f ? 1 : (p.power == 2.0f ? 2 : 0);
     const int64_t upc = (p.n_frames + G - 1) / G;        // units per clip
     const int64_t total = p.B * upc;
     const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
 
-    for (int64_t u = u0; u < u1; ++u) {
-        const int64_t b = u / upc;
-        const int64_t t = (u - b * upc) * G + g;
+    int64_t b = u0 / upc;                   // clip and unit-in-clip advance incrementally: no division per frame
+    int64_t uc = u0 - b * upc;
+    for (int64_t u = u0; u < u1; ++u, ++uc) {
+        if (uc == upc) {
+            uc = 0;
+            ++b;
+        }
+        const int64_t t = uc * G + g;
         const bool valid = t < p.n_frames;
         const int64_t s0 = t * p.hop - p.pad;
         const float* __restrict__ xb = p.x + b * p.ldx;
@@ -71,14 +98,17 @@ __global__ void __launch_bounds__(THREADS) stft_fwd_kernel(const FwdParams p) {
         // ---- load + window (pass-0 operand order) ----
         cf v[V];
         if (valid && p.vec_ok && s0 >= 0 && s0 + N <= p.L) {
-            const float2* __restrict__ src = reinterpret_cast<const float2*>(xb + s0);
 #pragma unroll
-            for (int b0 = 0; b0 < B0; ++b0)
+            for (int b0 = 0; b0 < B0; ++b0) {
+                const float2* __restrict__ src = reinterpret_cast<const float2*>(xb + s0) + (tid + T * b0);
+                const float2* __restrict__ wv = swin + (tid + T * b0);
 #pragma unroll
                 for (int r = 0; r < R0; ++r) {
-                    const float2 a = __ldg(src + fft.template in_index<0>(b0, r));
-                    v[b0 * R0 + r] = mk(a.x * win[b0 * R0 + r].x, a.y * win[b0 * R0 + r].y);
+                    const float2 a = __ldg(src + r * NB0);
+                    const float2 w = wv[r * NB0];
+                    v[b0 * R0 + r] = mk(a.x * w.x, a.y * w.y);
                 }
+            }
         } else if (valid) {
             // edge frame: reflect padding (torch.stft center=True, pad_mode="reflect")
 #pragma unroll
@@ -95,7 +125,7 @@ __global__ void __launch_bounds__(THREADS) stft_fwd_kernel(const FwdParams p) {
                         i = i < 0 ? 0 : (i >= p.L ? p.L - 1 : i);
                         e[h] = __ldg(xb + i);
                     }
-                    v[b0 * R0 + r] = mk(e[0] * win[b0 * R0 + r].x, e[1] * win[b0 * R0 + r].y);
+                    v[b0 * R0 + r] = mk(e[0] * swin[n].x, e[1] * swin[n].y);
                 }
         } else {
 #pragma unroll
@@ -130,57 +160,62 @@ __global__ void __launch_bounds__(THREADS) stft_fwd_kernel(const FwdParams p) {
 
         if (MODE == MODE_COMPLEX) {
             if (valid) {
-                cf* __restrict__ row = reinterpret_cast<cf*>(p.out) + (b * p.n_frames + t) * (int64_t)P::F;
+                float2* __restrict__ row = reinterpret_cast<float2*>(p.out) + (b * p.n_frames + t) * (int64_t)P::F;
 #pragma unroll
-                for (int c = 0; c < PR::PC; ++c)
+                for (int c = 0; c < PR::PC; ++c) {
+                    // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
+                    float2* lo = row + PR::klo(tid, c);
+                    float2* hi = row + PR::khi(tid, c);
+                    float2* mlo = row + (M - PR::klo(tid, c));
+                    float2* mhi = row + (M - PR::khi(tid, c));
 #pragma unroll
-                    for (int q = 0; q < PR::R; ++q) {
-                        const int k = PR::k1(tid, c, q);
-                        stg_stream2(reinterpret_cast<float2*>(row + k), o1[c * PR::R + q].x, o1[c * PR::R + q].y);
-                        stg_stream2(reinterpret_cast<float2*>(row + (M - k)), o2[c * PR::R + q].x, o2[c * PR::R + q].y);
+                    for (int q = 0; q < RP; ++q) {
+                        stg_stream2((q < RP / 2 ? lo : hi) + q * NBP, o1[c * RP + q].x, o1[c * RP + q].y);
+                        stg_stream2((q < RP / 2 ? mlo : mhi) - q * NBP, o2[c * RP + q].x, o2[c * RP + q].y);
                     }
-                if (tid == 0) stg_stream2(reinterpret_cast<float2*>(row + M / 2), ex.x, ex.y);
+                }
+                if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
         } else {
             float* __restrict__ val = reinterpret_cast<float*>(s);
             gsync();   // every thread has finished reading s for the last pass
 #pragma unroll
-            for (int c = 0; c < PR::PC; ++c)
+            for (int c = 0; c < PR::PC; ++c) {
+                float* lo = val + PR::klo(tid, c);
+                float* hi = val + PR::khi(tid, c);
+                float* mlo = val + (M - PR::klo(tid, c));
+                float* mhi = val + (M - PR::khi(tid, c));
 #pragma unroll
-                for (int q = 0; q < PR::R; ++q) {
-                    const int k = PR::k1(tid, c, q);
-                    const cf a = o1[c * PR::R + q], d = o2[c * PR::R + q];
-                    float pa = a.x * a.x + a.y * a.y, pd = d.x * d.x + d.y * d.y;
-                    if (p.power == 1.0f) { pa = sqrtf(pa); pd = sqrtf(pd); }
-                    else if (p.power != 2.0f) { pa = powf(sqrtf(pa), p.power); pd = powf(sqrtf(pd), p.power); }
-                    val[k] = pa;
-                    val[M - k] = pd;
+                for (int q = 0; q < RP; ++q) {
+                    (q < RP / 2 ? lo : hi)[q * NBP] = pow_value(o1[c * RP + q].x, o1[c * RP + q].y, pmode, p.power);
+                    (q < RP / 2 ? mlo : mhi)[-q * NBP] = pow_value(o2[c * RP + q].x, o2[c * RP + q].y, pmode, p.power);
                 }
-            if (tid == 0) {
-                float pe = ex.x * ex.x + ex.y * ex.y;
-                if (p.power == 1.0f) pe = sqrtf(pe);
-                else if (p.power != 2.0f) pe = powf(sqrtf(pe), p.power);
-                val[M / 2] = pe;
             }
+            if (tid == 0) val[M / 2] = pow_value(ex.x, ex.y, pmode, p.power);
             gsync();
             float* out_row = p.out + b * p.out_clip_stride + t * p.out_row_stride;
-            epilogue_row<T>(val, tid, ep, out_row, p.out_col_stride, valid);
+            epilogue_row<T>(val, tid, ep, bmeta, bcoef, out_row, p.out_col_stride, valid);
         }
     }
 }
 
+static const size_t kBandSmemBudget = 24 * 1024;
+
 template <class P, int MODE>
-static int launch_fwd(const FwdParams& p, cudaStream_t st) {
-    constexpr int THREADS = P::T > 256 ? P::T : 256;
-    constexpr int G = THREADS / P::T;
-    constexpr size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf);
-    auto kern = stft_fwd_kernel<P, MODE, THREADS>;
+static int launch_fwd(FwdParams p, cudaStream_t st) {
+    constexpr int THREADS = FwdCfg<P>::THREADS;
+    constexpr int G = FwdCfg<P>::G;
+    const size_t band_bytes = (MODE == MODE_REAL) ? (size_t)p.ep.band_bytes_meta + p.ep.band_bytes_coef : 0;
+    const size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)P::M * sizeof(float2) + band_bytes;
+    auto kern = stft_fwd_kernel<P, MODE>;
+    static size_t reserved = 0;
     static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
+    if (smem > reserved || ctas_per_sm == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("stft_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
             return ACIDS_ECUDA;
         }
+        reserved = smem;
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem);
         ctas_per_sm = nb > 0 ? nb : 1;
@@ -231,15 +266,16 @@ static int fill_common(FwdParams& p, const float* x, int64_t B, int64_t L, int64
     return ACIDS_OK;
 }
 
-static int fill_epilogue(FwdParams& p, acids_band band, int n_bins, int contrast, float eps, const float* offset,
-                         const float* scale, int drop_first) {
+int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, float eps, int drop_first, size_t smem_budget) {
     ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
     ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
-    p.ep.meta = band.meta; p.ep.coef = band.coef;
-    p.ep.n_cols = band.meta ? band.n_out : n_bins;
-    ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0), ACIDS_EINVAL, "banded matrix without coefficients");
-    p.ep.contrast = contrast; p.ep.eps = eps; p.ep.offset = 0.f; p.ep.inv_scale = 1.f; p.ep.drop_first = drop_first;
-    p.offset_ptr = offset; p.scale_ptr = scale;
+    ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0 && band.coef_len >= 0 && (band.coef_len & 31) == 0), ACIDS_EINVAL,
+                  "malformed banded matrix (n_out=%d coef_len=%d)", band.n_out, band.coef_len);
+    ep.meta = band.meta; ep.coef = band.coef;
+    ep.n_cols = band.meta ? band.n_out : n_bins;
+    ep.contrast = contrast; ep.eps = eps; ep.inv_scale = 1.f; ep.neg_off_scaled = 0.f; ep.drop_first = drop_first;
+    const int64_t meta_ints = band.meta ? (int64_t)band.n_out + 2 * (((int64_t)band.n_out + 31) / 32) : 0;
+    band_smem_plan(band, band.coef_len, meta_ints, smem_budget, ep);
     return ACIDS_OK;
 }
 
@@ -264,9 +300,10 @@ extern "C" ACIDS_API int acids_stft_mag_fwd(const float* x, int64_t B, int64_t L
     FwdParams p{};
     int rc = fill_common(p, x, B, L, ldx, window, n_fft, hop, center, n_frames);
     if (rc) return rc;
-    rc = fill_epilogue(p, band, n_fft / 2 + 1, contrast, eps, offset, scale, drop_first);
+    rc = fill_epilogue(p.ep, band, n_fft / 2 + 1, contrast, eps, drop_first, kBandSmemBudget);
     if (rc) return rc;
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "stft_mag_fwd: NULL output");
+    p.offset_ptr = offset; p.scale_ptr = scale;
     p.out = out; p.out_clip_stride = out_clip_stride; p.out_row_stride = out_row_stride; p.out_col_stride = 1;
     p.power = 1.0f;
     return dispatch_fwd<MODE_REAL>(n_fft, p, static_cast<cudaStream_t>(stream));
@@ -280,9 +317,10 @@ extern "C" ACIDS_API int acids_melspec_fwd(const float* x, int64_t B, int64_t L,
     if (rc) return rc;
     ACIDS_REQUIRE(mel.meta && mel.coef && mel.n_out > 0, ACIDS_EINVAL, "melspec_fwd: mel bank required");
     ACIDS_REQUIRE(power > 0.f, ACIDS_EINVAL, "melspec_fwd: power must be > 0");
-    rc = fill_epilogue(p, mel, n_fft / 2 + 1, ACIDS_CONTRAST_NONE, 0.f, offset, scale, 0);
+    rc = fill_epilogue(p.ep, mel, n_fft / 2 + 1, ACIDS_CONTRAST_NONE, 0.f, 0, kBandSmemBudget);
     if (rc) return rc;
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "melspec_fwd: NULL output");
+    p.offset_ptr = offset; p.scale_ptr = scale;
     // frequency-major output [B, n_mels, n_frames] like torchaudio (mel.py:70)
     p.out = out; p.out_clip_stride = (int64_t)mel.n_out * n_frames; p.out_row_stride = 1; p.out_col_stride = n_frames;
     p.power = power;

@@ -63,11 +63,13 @@ def _scalar(t, device) -> Optional[torch.Tensor]:
 
 
 class BandedMatrix:
-    """Column-banded view of a mostly-zero [n_in, n_out] matrix (the mel banks).
+    """Column-banded ("group-ELL") view of a mostly-zero [n_in, n_out] matrix — the mel banks.
 
-    Column m keeps rows [start, start+count) — its first to last non-zero.  Device copies are made
-    lazily per device.  spectral_repr.py:173-189 builds these matrices dense; 99.6 % of the square
-    513x513 bank is zero.
+    spectral_repr.py:173-189 builds these matrices dense; 99.6 % of the square 513x513 bank is zero
+    (SURVEY.md §8a A5).  Layout (include/acids_b200.h, acids_band): columns in groups of 32; group g applies
+    cnt[g] = its widest band to every column, column m reading rows start[m] .. start[m]+cnt[g]-1 with zero
+    padded coefficients.  meta = (cnt, base)[n_groups] ++ start[n_out] ++ (n_in, coef_len) (the trailing pair is
+    host-side bookkeeping).  Device copies are made lazily per device.
     """
 
     def __init__(self, dense: torch.Tensor):
@@ -75,39 +77,50 @@ class BandedMatrix:
         if m.ndim == 3:
             m = m[0]
         self.n_in, self.n_out = int(m.shape[0]), int(m.shape[1])
-        if self.n_in >= 65536:
-            raise ValueError("banded matrix supports at most 65535 input rows")
-        meta = np.zeros((self.n_out, 2), np.int32)
-        coefs = []
-        off = 0
         nz = m != 0
-        for c in range(self.n_out):
-            rows = np.flatnonzero(nz[:, c])
-            if rows.size:
-                s, e = int(rows[0]), int(rows[-1]) + 1
-                meta[c, 0] = s | ((e - s) << 16)
-                meta[c, 1] = off
-                coefs.append(m[s:e, c])
-                off += e - s
-            else:
-                meta[c, 0] = 0
-                meta[c, 1] = off
-        self.nnz_stored = off
-        meta = np.concatenate([meta, np.array([[self.n_in, off]], np.int32)], 0)
-        self._meta = torch.from_numpy(meta)
-        self._coef = torch.from_numpy(np.concatenate(coefs) if coefs else np.zeros(1, np.float32)).contiguous()
+        first = np.where(nz.any(0), nz.argmax(0), 0)
+        last = np.where(nz.any(0), self.n_in - 1 - nz[::-1].argmax(0), -1)
+        width = (last - first + 1).clip(min=0)
+        self.nnz_stored = int(width.sum())
+        n_groups = (self.n_out + 31) // 32
+        start = np.zeros(self.n_out, np.int32)
+        ginfo = np.zeros((n_groups, 2), np.int32)
+        blocks = []
+        base = 0
+        for g in range(n_groups):
+            cols = np.arange(g * 32, min(self.n_out, g * 32 + 32))
+            cnt = int(width[cols].max()) if cols.size else 0
+            blk = np.zeros((cnt, 32), np.float32)
+            for c in cols:
+                s0 = int(min(first[c], self.n_in - cnt)) if cnt else 0      # keep the window inside the input
+                s0 = max(s0, 0)
+                start[c] = s0
+                if width[c]:
+                    blk[first[c] - s0:first[c] - s0 + width[c], c - g * 32] = m[first[c]:last[c] + 1, c]
+            ginfo[g] = (cnt, base)
+            base += cnt
+            blocks.append(blk)
+        coef = np.concatenate(blocks, 0).reshape(-1) if base else np.zeros(0, np.float32)
+        self.coef_len = int(coef.size)
+        meta = np.concatenate([ginfo.reshape(-1), start, np.array([self.n_in, self.coef_len], np.int32)])
+        self._meta = torch.from_numpy(meta.astype(np.int32))
+        self._coef = torch.from_numpy(coef if coef.size else np.zeros(32, np.float32)).contiguous()
         self._dev = {}
 
     def tensors(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(meta int32 [n_out + 1, 2], coef float32): what the modules keep as non-persistent buffers."""
+        """(meta int32, coef float32): what the modules keep as non-persistent buffers."""
         return self._meta.clone(), self._coef.clone()
 
     @classmethod
     def from_tensors(cls, meta: torch.Tensor, coef: torch.Tensor) -> "BandedMatrix":
         self = cls.__new__(cls)
-        self.n_out = int(meta.shape[0]) - 1
+        # meta = (cnt, base)[ceil(n_out / 32)] ++ start[n_out] ++ (n_in, coef_len): solve for n_out
+        total = int(meta.numel()) - 2
+        n_out = next(n for n in range(max(total - 2 * ((total + 31) // 32) - 2, 0), total + 1) if n + 2 * ((n + 31) // 32) == total)
+        self.n_out = n_out
         self.n_in = -1          # read lazily: avoids a device sync when the tensors live on the GPU
-        self.nnz_stored = int(coef.numel())
+        self.coef_len = int(coef.numel())
+        self.nnz_stored = self.coef_len
         self._meta, self._coef, self._dev = meta, coef, {}
         return self
 
@@ -116,10 +129,10 @@ class BandedMatrix:
         if key not in self._dev:
             self._dev[key] = (self._meta.to(device).contiguous(), self._coef.to(device).contiguous())
         meta, coef = self._dev[key]
-        return Band(meta.data_ptr(), coef.data_ptr(), self.n_out)
+        return Band(meta.data_ptr(), coef.data_ptr(), self.n_out, self.coef_len)
 
 
-_NO_BAND = Band(None, None, 0)
+_NO_BAND = Band(None, None, 0, 0)
 _BAND_CACHE = {}
 
 
@@ -127,7 +140,7 @@ def as_band(meta: Optional[torch.Tensor], coef: Optional[torch.Tensor]) -> Optio
     """BandedMatrix view of a (meta, coef) buffer pair, cached on the buffers' identity/version."""
     if meta is None or coef is None:
         return None
-    key = (meta.data_ptr(), coef.data_ptr(), meta._version, coef._version, meta.shape[0])
+    key = (meta.data_ptr(), coef.data_ptr(), meta._version, coef._version, meta.numel())
     b = _BAND_CACHE.get(key)
     if b is None:
         if len(_BAND_CACHE) > 64:

@@ -64,7 +64,7 @@ class MFCC(AudioTransform):
         self.power = 2.0
         self.n_mels = 0
         self.register_buffer("window", torch.zeros(0), persistent=False)
-        self.register_buffer("mel_meta", torch.zeros(0, 2, dtype=torch.int32), persistent=False)
+        self.register_buffer("mel_meta", torch.zeros(0, dtype=torch.int32), persistent=False)
         self.register_buffer("mel_coef", torch.zeros(0), persistent=False)
         self.register_buffer("dct_mat", torch.zeros(0, 0), persistent=False)
         self.set_transform(n_fft, n_mels, hop_length, power)
@@ -80,6 +80,11 @@ class MFCC(AudioTransform):
         meta, coef = _ops.BandedMatrix(fb).tensors()
         self.mel_meta, self.mel_coef = meta.to(dev), coef.to(dev)
         self.dct_mat = create_dct(self.n_mfcc, self.n_mels).to(dev) if self.n_mfcc > 0 else torch.zeros(0, 0, device=dev)
+
+    @torch.jit.unused
+    def dense_bank(self) -> torch.Tensor:
+        """The [n_fft/2+1, n_mels] HTK filterbank torchaudio's MelSpectrogram would hold (mel.py:43-44)."""
+        return melscale_fbanks(self.n_fft // 2 + 1, 0.0, float(self.sr // 2), self.n_mels, self.sr)
 
     @torch.jit.export
     def mel_power(self, x: torch.Tensor) -> torch.Tensor:

@@ -232,9 +232,9 @@ class Magnitude(_Representation):
         self.register_buffer("mel_bank", fwd)
         self.register_buffer("inverse_mel_bank", inv)
         # banded views of the (99.6 % zero) banks, what the kernels consume; derived, hence not persistent
-        self.register_buffer("mel_meta", torch.zeros(0, 2, dtype=torch.int32), persistent=False)
+        self.register_buffer("mel_meta", torch.zeros(0, dtype=torch.int32), persistent=False)
         self.register_buffer("mel_coef", torch.zeros(0), persistent=False)
-        self.register_buffer("inv_meta", torch.zeros(0, 2, dtype=torch.int32), persistent=False)
+        self.register_buffer("inv_meta", torch.zeros(0, dtype=torch.int32), persistent=False)
         self.register_buffer("inv_coef", torch.zeros(0), persistent=False)
         self.refresh_bands()
         self.register_load_state_dict_post_hook(lambda m, _: m.refresh_bands())

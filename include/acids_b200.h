@@ -69,13 +69,17 @@ extern "C" {
 ACIDS_API int acids_abi_version(void);
 ACIDS_API const char* acids_last_error(void);
 
-/* A banded (sparse-by-columns) matrix: output column m sums rows [start[m], start[m]+count[m])
- * of the input with weights coef[off[m] + u].  meta[2m] = start | (count << 16), meta[2m+1] = off.
- * This is how the 99.6 %-sparse mel banks of spectral_repr.py:173-189 are applied. */
+/* A banded (sparse-by-columns) matrix in "group-ELL" layout.  This is how the 99.6 %-sparse mel banks of
+ * spectral_repr.py:173-189 are applied.  Output columns are taken in groups of 32; group g applies cnt[g]
+ * taps to each of its columns, column m reading input rows start[m] .. start[m] + cnt[g] - 1 (narrower
+ * bands are zero padded; start[m] + cnt[g] never exceeds the number of input rows).
+ *   meta = (cnt[g], base[g]) for g in [0, ceil(n_out / 32))  followed by  start[0 .. n_out)
+ *   tap u of column m = coef[(base[g] + u) * 32 + (m & 31)],  coef_len = 32 * sum_g cnt[g]             */
 typedef struct acids_band {
-    const int32_t* meta;   /* device, 2 * n_out ints, or NULL for "no projection" */
-    const float* coef;     /* device */
+    const int32_t* meta;   /* device, n_out + 2 * ceil(n_out / 32) ints, or NULL for "no projection" */
+    const float* coef;     /* device, coef_len floats */
     int32_t n_out;         /* number of output columns */
+    int32_t coef_len;
 } acids_band;
 
 /* ---- (1) framing + window + real FFT ------------------------------------------------------

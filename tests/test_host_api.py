@@ -90,16 +90,24 @@ def test_mel_banks_match_reference():
 
 
 def test_banded_matrix_is_lossless():
+    """The group-ELL layout the kernels consume (include/acids_b200.h, acids_band) reproduces the dense bank exactly."""
     m = T.Magnitude()
+    for dense_bank in (m.mel_bank[0], m.inverse_mel_bank[0], T.MFCC(n_fft=2048, n_mels=128).dense_bank()):
+        b = ops.BandedMatrix(dense_bank)
+        meta, coef = (t.numpy() for t in b.tensors())
+        n, ng = b.n_out, (b.n_out + 31) // 32
+        assert meta.size == n + 2 * ng + 2 and int(meta[-2]) == b.n_in and int(meta[-1]) == b.coef_len == coef.size
+        rebuilt = np.zeros((b.n_in, n), np.float32)
+        for c in range(n):
+            cnt, base, s0 = int(meta[2 * (c // 32)]), int(meta[2 * (c // 32) + 1]), int(meta[2 * ng + c])
+            assert 0 <= s0 and s0 + cnt <= b.n_in                     # a column's window never leaves the input
+            for u in range(cnt):
+                rebuilt[s0 + u, c] += coef[(base + u) * 32 + (c & 31)]
+        assert np.array_equal(rebuilt, dense_bank.numpy())
+        b2 = ops.BandedMatrix.from_tensors(*b.tensors())
+        assert b2.n_out == b.n_out and b2.coef_len == b.coef_len
     b = ops.BandedMatrix(m.mel_bank)
-    assert b.nnz_stored >= 1019 and b.nnz_stored <= 1100 and b.n_in == 513 and b.n_out == 513    # 1,019 nnz
-    meta, coef = b.tensors()
-    rebuilt = torch.zeros(513, 513)
-    for c in range(513):
-        s, n, off = int(meta[c, 0]) & 0xffff, int(meta[c, 0]) >> 16, int(meta[c, 1])
-        rebuilt[s:s + n, c] = coef[off:off + n]
-    assert torch.equal(rebuilt, m.mel_bank[0])
-    assert int(meta[-1, 0]) == 513                   # trailing row carries n_in
+    assert b.nnz_stored == 1019 and b.n_in == 513 and b.n_out == 513        # SURVEY §8a A5: 1,019 non-zeros
     # the module keeps the banded tensors out of state_dict
     assert sorted(m.state_dict()) == ["eps", "inverse_mel_bank", "mel_bank", "norm.offset", "norm.scale"]
 
