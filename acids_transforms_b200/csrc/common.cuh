@@ -101,88 +101,121 @@ __device__ __forceinline__ float invert_contrast(float y, int mode, float eps) {
     return y;
 }
 
-// K taps of one column, straight-line
-template <int K>
-__device__ __forceinline__ float taps(const float* __restrict__ v, const float* __restrict__ c) {
-    float a = 0.f;
-#pragma unroll
-    for (int u = 0; u < K; ++u) a = fmaf(v[u], c[u << 5], a);
-    return a;
+__device__ __forceinline__ float fast_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // x >= eps > FLT_MIN on every path that calls this
+    return r;
 }
 
-// sum_u val[start + u] * coef[u] for output column m.  The tap count is uniform over a group of 32 columns,
-// so the switch does not diverge inside a warp and every case is branch-free.
-__device__ __forceinline__ float band_column(const float* __restrict__ val, const int32_t* __restrict__ meta,
-                                             const float* __restrict__ coef, int n_groups, int m) {
+// contrast up to the constant factor that epilogue folds into the normalisation FFMA (see contrast_gain)
+template <int CONTRAST>
+__device__ __forceinline__ float contrast_core(float a, float eps) {
+    // spectral_repr.py:191-201.  log(1 + m) is evaluated literally (not log1p), like the reference;
+    // lg2.approx has 2^-22 relative error, two orders below the 1e-4 parity budget.
+    if (CONTRAST == ACIDS_CONTRAST_LOG1P) return fast_lg2(1.0f + a);
+    if (CONTRAST == ACIDS_CONTRAST_LOG || CONTRAST == ACIDS_CONTRAST_LOG10) return fast_lg2(fmaxf(a, eps));
+    return a;
+}
+__device__ __forceinline__ float contrast_gain(int contrast) {
+    if (contrast == ACIDS_CONTRAST_LOG1P || contrast == ACIDS_CONTRAST_LOG) return 0.69314718055994530942f;   // ln 2
+    if (contrast == ACIDS_CONTRAST_LOG10) return 0.30102999566398119521f;                                      // log10 2
+    return 1.0f;
+}
+
+// K taps of one column for NF rows: the K coefficients are loaded once and reused for every row
+template <int K, int NF>
+__device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride, const float* __restrict__ c, float (&a)[NF]) {
+    float w[K > 0 ? K : 1];
+#pragma unroll
+    for (int u = 0; u < K; ++u) w[u] = c[u << 5];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < K; ++u) acc = fmaf(v[f * val_stride + u], w[u], acc);
+        a[f] = acc;
+    }
+}
+
+// Banded projection of column m for NF rows (rows are val_stride floats apart).  The tap count is uniform over
+// a group of 32 columns, so the switch does not diverge inside a warp and every case is branch-free.
+template <int NF>
+__device__ __forceinline__ void band_column(const float* __restrict__ val, int val_stride, const int32_t* __restrict__ meta,
+                                            const float* __restrict__ coef, int n_groups, int m, float (&a)[NF]) {
     const int2 gi = *reinterpret_cast<const int2*>(meta + 2 * (m >> 5));      // (cnt, base)
     const float* __restrict__ v = val + meta[2 * n_groups + m];
     const float* __restrict__ c = coef + (gi.y << 5) + (m & 31);
     switch (gi.x) {
-        case 0: return 0.f;
-        case 1: return taps<1>(v, c);
-        case 2: return taps<2>(v, c);
-        case 3: return taps<3>(v, c);
-        case 4: return taps<4>(v, c);
-        case 5: return taps<5>(v, c);
-        case 6: return taps<6>(v, c);
-        case 7: return taps<7>(v, c);
-        case 8: return taps<8>(v, c);
-        default: {
-            float a = 0.f;
-            for (int u = 0; u < gi.x; ++u) a = fmaf(v[u], c[u << 5], a);
-            return a;
+        case 0: taps<0, NF>(v, val_stride, c, a); break;
+        case 1: taps<1, NF>(v, val_stride, c, a); break;
+        case 2: taps<2, NF>(v, val_stride, c, a); break;
+        case 3: taps<3, NF>(v, val_stride, c, a); break;
+        case 4: taps<4, NF>(v, val_stride, c, a); break;
+        case 5: taps<5, NF>(v, val_stride, c, a); break;
+        case 6: taps<6, NF>(v, val_stride, c, a); break;
+        case 7: taps<7, NF>(v, val_stride, c, a); break;
+        case 8: taps<8, NF>(v, val_stride, c, a); break;
+        default:
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float acc = 0.f;
+                for (int u = 0; u < gi.x; ++u) acc = fmaf(v[f * val_stride + u], c[u << 5], acc);
+                a[f] = acc;
+            }
+    }
+}
+
+template <int NT, int NF, int CONTRAST, bool BAND>
+__device__ __forceinline__ void epilogue_cols(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
+                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
+                                              float* __restrict__ o, int64_t col_step, int64_t row_step, int n_valid) {
+    // o points at this thread's first column of row 0 (already shifted by drop_first); consecutive columns of a
+    // thread are NT apart (col_step floats), consecutive rows row_step floats
+    const int n_groups = (ep.n_cols + 31) >> 5;
+    const float gain = ep.inv_scale * contrast_gain(CONTRAST);
+    for (int m = tid; m < ep.n_cols; m += NT, o += col_step) {
+        float a[NF];
+        if (BAND) {
+            band_column<NF>(val, val_stride, meta, coef, n_groups, m, a);
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a[f] = val[f * val_stride + m];
+        }
+        if (m >= ep.drop_first) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                if (f < n_valid) stg_stream1(o + f * row_step, fmaf(contrast_core<CONTRAST>(a[f], ep.eps), gain, ep.neg_off_scaled));
         }
     }
 }
 
-template <int CONTRAST>
-__device__ __forceinline__ float contrast_ct(float a, float eps) {
-    // spectral_repr.py:191-201.  log(1 + m) is evaluated literally (not log1p), like the reference;
-    // lg2.approx has 2^-22 relative error, two orders below the 1e-4 parity budget.
-    if (CONTRAST == ACIDS_CONTRAST_LOG1P) return __logf(1.0f + a);
-    if (CONTRAST == ACIDS_CONTRAST_LOG) return __logf(fmaxf(a, eps));
-    if (CONTRAST == ACIDS_CONTRAST_LOG10) return __log10f(fmaxf(a, eps));
-    return a;
-}
-
-template <int T, int CONTRAST, bool BAND>
-__device__ __forceinline__ void epilogue_cols(const float* __restrict__ val, int tid, const EpiParams& ep,
+// NF rows at once: `val` holds the non-negative inputs (|X| or |X|^p) of NF rows in shared memory; NT threads
+// produce columns tid, tid+NT, ... of every row: banded projection -> contrast -> normalise -> streaming store.
+// Per-column work (band metadata, coefficients, dispatch) is paid once for the NF rows; the (uniform) contrast
+// mode and band presence are dispatched once per call.
+template <int NT, int NF>
+__device__ __forceinline__ void epilogue_rows(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
                                               const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                              float* __restrict__ o, int64_t step, bool valid) {
-    // o points at this thread's first column (already shifted by drop_first); consecutive columns of a thread
-    // are T apart, i.e. `step` floats in the output
-    const int n_groups = (ep.n_cols + 31) >> 5;
-    for (int m = tid; m < ep.n_cols; m += T, o += step) {
-        float a = BAND ? band_column(val, meta, coef, n_groups, m) : val[m];
-        a = fmaf(contrast_ct<CONTRAST>(a, ep.eps), ep.inv_scale, ep.neg_off_scaled);
-        if (valid && m >= ep.drop_first) stg_stream1(o, a);
-    }
-}
-
-// One row: `val` holds the non-negative inputs (|X| or |X|^p) in shared memory; the T threads of the group
-// produce columns tid, tid+T, ...: banded projection -> contrast -> normalise -> streaming store.
-// The (uniform) contrast mode and band presence are dispatched once per row, not once per column.
-template <int T>
-__device__ __forceinline__ void epilogue_row(const float* __restrict__ val, int tid, const EpiParams& ep,
-                                             const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                             float* __restrict__ out_row, int64_t col_stride, bool valid) {
-    float* o = out_row + (int64_t)(tid - ep.drop_first) * col_stride;
-    const int64_t step = (int64_t)T * col_stride;
+                                              float* __restrict__ out_row0, int64_t col_stride, int64_t row_stride, int n_valid) {
+    float* o = out_row0 + (int64_t)(tid - ep.drop_first) * col_stride;
+    const int64_t cs = (int64_t)NT * col_stride;
+#define ACIDS_EPI(C, B) epilogue_cols<NT, NF, C, B>(val, val_stride, tid, ep, meta, coef, o, cs, row_stride, n_valid)
     if (meta != nullptr) {
         switch (ep.contrast) {
-            case ACIDS_CONTRAST_LOG1P: epilogue_cols<T, ACIDS_CONTRAST_LOG1P, true>(val, tid, ep, meta, coef, o, step, valid); break;
-            case ACIDS_CONTRAST_LOG: epilogue_cols<T, ACIDS_CONTRAST_LOG, true>(val, tid, ep, meta, coef, o, step, valid); break;
-            case ACIDS_CONTRAST_LOG10: epilogue_cols<T, ACIDS_CONTRAST_LOG10, true>(val, tid, ep, meta, coef, o, step, valid); break;
-            default: epilogue_cols<T, ACIDS_CONTRAST_NONE, true>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG1P: ACIDS_EPI(ACIDS_CONTRAST_LOG1P, true); break;
+            case ACIDS_CONTRAST_LOG: ACIDS_EPI(ACIDS_CONTRAST_LOG, true); break;
+            case ACIDS_CONTRAST_LOG10: ACIDS_EPI(ACIDS_CONTRAST_LOG10, true); break;
+            default: ACIDS_EPI(ACIDS_CONTRAST_NONE, true); break;
         }
     } else {
         switch (ep.contrast) {
-            case ACIDS_CONTRAST_LOG1P: epilogue_cols<T, ACIDS_CONTRAST_LOG1P, false>(val, tid, ep, meta, coef, o, step, valid); break;
-            case ACIDS_CONTRAST_LOG: epilogue_cols<T, ACIDS_CONTRAST_LOG, false>(val, tid, ep, meta, coef, o, step, valid); break;
-            case ACIDS_CONTRAST_LOG10: epilogue_cols<T, ACIDS_CONTRAST_LOG10, false>(val, tid, ep, meta, coef, o, step, valid); break;
-            default: epilogue_cols<T, ACIDS_CONTRAST_NONE, false>(val, tid, ep, meta, coef, o, step, valid); break;
+            case ACIDS_CONTRAST_LOG1P: ACIDS_EPI(ACIDS_CONTRAST_LOG1P, false); break;
+            case ACIDS_CONTRAST_LOG: ACIDS_EPI(ACIDS_CONTRAST_LOG, false); break;
+            case ACIDS_CONTRAST_LOG10: ACIDS_EPI(ACIDS_CONTRAST_LOG10, false); break;
+            default: ACIDS_EPI(ACIDS_CONTRAST_NONE, false); break;
         }
     }
+#undef ACIDS_EPI
 }
 
 // stage the banded matrix in shared memory (all threads of the CTA); returns the pointers to use

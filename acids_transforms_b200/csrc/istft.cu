@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
-    float* ring = reinterpret_cast<float*>(reinterpret_cast<cf*>(smem_raw) + (size_t)G * P::SMEM_CF);
+    constexpr size_t kExch = ((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15;     // keep the ring 16-byte aligned
+    float* ring = reinterpret_cast<float*>(smem_raw + kExch);
     float* g2 = ring + (size_t)p.ring * N;           // window^2, for the envelope at the clip edges
     float2* swin = reinterpret_cast<float2*>(g2 + N);  // synthesis window pairs with irfft's 1/N folded in
     float* inv_env = reinterpret_cast<float*>(swin + M);   // 1 / sum_i g^2[r + i hop]: the interior envelope
@@ -166,23 +167,64 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
             // whole hop segments; segment q gets frames [max(0, q - ov + 1), min(nT - 1, q)]
             const int ov = N / hop;
             const int q0 = (int)(emitted / hop), q1 = (int)(hi / hop);
-            for (int q = q0; q < q1; ++q) {
-                const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
-                const bool interior = (t_hi - t_lo + 1) == ov;
-                const int64_t nbase = (int64_t)q * hop - p.trim;
-                for (int r = threadIdx.x; r < hop; r += THREADS) {
-                    float acc = 0.f;
-                    for (int tt = t_lo; tt <= t_hi; ++tt) acc += ring[(size_t)(tt % p.ring) * N + r + (q - tt) * hop];
-                    float y;
-                    if (interior) {
-                        y = acc * inv_env[r];
-                    } else {
-                        float env = 0.f;
-                        for (int tt = t_lo; tt <= t_hi; ++tt) env += g2[r + (q - tt) * hop];
-                        y = acc / env;
+            if ((hop & 3) == 0) {
+                // four consecutive samples per thread: 16-byte shared loads and one 16-byte streaming store
+                const int h4 = hop >> 2;
+                const int items = (q1 - q0) * h4;
+                for (int it = threadIdx.x; it < items; it += THREADS) {
+                    const int dq = it / h4;
+                    const int r = (it - dq * h4) << 2;
+                    const int q = q0 + dq;
+                    const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
+                    int slot = t_lo % p.ring;
+                    int off = r + (q - t_lo) * hop;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int tt = t_lo; tt <= t_hi; ++tt) {        // ascending frame order, like torch.istft's col2im
+                        const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + off);
+                        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                        off -= hop;
+                        slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                     }
-                    const int64_t n = nbase + r;
-                    if (n >= 0 && n < p.out_len) stg_stream1(outc + n, y);
+                    float4 y;
+                    if (t_hi - t_lo + 1 == ov) {
+                        const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
+                        y = make_float4(acc.x * e.x, acc.y * e.y, acc.z * e.z, acc.w * e.w);
+                    } else {
+                        float4 env = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int o2 = r + (q - t_lo) * hop;
+                        for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
+                            const float4 w = *reinterpret_cast<const float4*>(g2 + o2);
+                            env.x += w.x; env.y += w.y; env.z += w.z; env.w += w.w;
+                        }
+                        y = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
+                    }
+                    const int64_t n = (int64_t)q * hop + r - p.trim;
+                    if (n >= 0 && n + 3 < p.out_len) {
+                        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outc + n), "f"(y.x), "f"(y.y),
+                                     "f"(y.z), "f"(y.w) : "memory");
+                    } else {
+                        const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (n + j >= 0 && n + j < p.out_len) stg_stream1(outc + n + j, yy[j]);
+                    }
+                }
+            } else {
+                for (int q = q0; q < q1; ++q) {
+                    const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
+                    const int slot0 = t_lo % p.ring;
+                    for (int r = threadIdx.x; r < hop; r += THREADS) {
+                        float acc = 0.f, env = 0.f;
+                        int slot = slot0, off = r + (q - t_lo) * hop;
+                        for (int tt = t_lo; tt <= t_hi; ++tt) {
+                            acc += ring[slot * N + off];
+                            env += g2[off];
+                            off -= hop;
+                            slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                        }
+                        const int64_t n = (int64_t)q * hop + r - p.trim;
+                        if (n >= 0 && n < p.out_len) stg_stream1(outc + n, acc / env);
+                    }
                 }
             }
         } else {
@@ -296,7 +338,7 @@ struct InvLaunch {
     static constexpr int G = InvCfg<P>::G;
     static size_t smem_ola(int ovc, int hop) {
         // exchange buffers | frame ring | window^2 | window pairs | interior inverse envelope
-        return (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float) +
+        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float) +
                (size_t)P::M * sizeof(float2) + (size_t)hop * sizeof(float);
     }
     static int ola(InvParams p, cudaStream_t st) {

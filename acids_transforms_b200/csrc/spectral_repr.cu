@@ -21,25 +21,30 @@ struct MagParams {
 };
 
 __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
+    // 8 rows per CTA iteration: each warp stages |X| of one row, then the CTA projects the 8 rows together
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* val = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.n_bins;
+    const int stride = (p.n_bins + 3) & ~3;
+    float* val = reinterpret_cast<float*>(smem_raw);
     EpiParams ep = p.ep;
     load_norm(p.offset_ptr, p.scale_ptr, ep);
     const int32_t* bmeta;
     const float* bcoef;
-    stage_band(ep, smem_raw + (size_t)8 * p.n_bins * sizeof(float), bmeta, bcoef);
+    stage_band(ep, smem_raw + (size_t)8 * stride * sizeof(float), bmeta, bcoef);
     __syncthreads();
-    const int64_t wpg = (int64_t)gridDim.x * 8;
-    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < p.rows; r += wpg) {
-        const float2* __restrict__ row = p.X + r * p.n_bins;
-        __syncwarp();
-        for (int k = lane; k < p.n_bins; k += 32) {
-            const float2 a = ldg_stream2(row + k);
-            val[k] = fast_sqrt(a.x * a.x + a.y * a.y);
+    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < p.rows; r0 += (int64_t)gridDim.x * 8) {
+        const int64_t r = r0 + warp;
+        if (r < p.rows) {
+            const float2* __restrict__ row = p.X + r * p.n_bins;
+            for (int k = lane; k < p.n_bins; k += 32) {
+                const float2 a = ldg_stream2(row + k);
+                val[warp * stride + k] = fast_sqrt(a.x * a.x + a.y * a.y);
+            }
         }
-        __syncwarp();
-        epilogue_row<32>(val, lane, ep, bmeta, bcoef, p.out + r * p.out_row_stride, 1, true);
+        __syncthreads();
+        const int n_valid = (int)min((int64_t)8, p.rows - r0);
+        epilogue_rows<256, 8>(val, stride, threadIdx.x, ep, bmeta, bcoef, p.out + r0 * p.out_row_stride, 1, p.out_row_stride, n_valid);
+        __syncthreads();
     }
 }
 
@@ -79,8 +84,10 @@ __global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
         __syncwarp();
         float* __restrict__ out = p.out + r * (int64_t)p.n_out;
         for (int m = lane; m < p.n_out; m += 32) {
-            const float a = p.meta ? band_column(val, p.meta, p.coef, (p.n_out + 31) >> 5, m) : val[m];
-            stg_stream1(out + m, a);
+            float a[1];
+            if (p.meta) band_column<1>(val, 0, p.meta, p.coef, (p.n_out + 31) >> 5, m, a);
+            else a[0] = val[m];
+            stg_stream1(out + m, a[0]);
         }
     }
 }
@@ -277,7 +284,7 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, 24 * 1024);
     if (rc) return rc;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
-    const size_t smem = (size_t)8 * n_bins * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
+    const size_t smem = (size_t)8 * ((n_bins + 3) & ~3) * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
     static size_t reserved = 48 * 1024;
     if (smem > reserved) {
         ACIDS_REQUIRE(cudaFuncSetAttribute(mag_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,

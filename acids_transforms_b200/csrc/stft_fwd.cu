@@ -192,9 +192,15 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                 }
             }
             if (tid == 0) val[M / 2] = pow_value(ex.x, ex.y, pmode, p.power);
-            gsync();
-            float* out_row = p.out + b * p.out_clip_stride + t * p.out_row_stride;
-            epilogue_row<T>(val, tid, ep, bmeta, bcoef, out_row, p.out_col_stride, valid);
+            // the G rows of this unit are projected together by the whole CTA: per-column band metadata and
+            // coefficients are fetched once for G frames
+            __syncthreads();
+            const int64_t t0 = uc * G;
+            const int n_valid = (int)min((int64_t)G, p.n_frames - t0);
+            float* out_row0 = p.out + b * p.out_clip_stride + t0 * p.out_row_stride;
+            epilogue_rows<THREADS, G>(reinterpret_cast<const float*>(smem_raw), 2 * P::SMEM_CF, threadIdx.x, ep, bmeta, bcoef,
+                                      out_row0, p.out_col_stride, p.out_row_stride, n_valid);
+            __syncthreads();
         }
     }
 }
