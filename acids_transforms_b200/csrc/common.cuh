@@ -189,16 +189,14 @@ __device__ __forceinline__ void epilogue_cols(const float* __restrict__ val, int
     }
 }
 
-// NF rows at once: `val` holds the non-negative inputs (|X| or |X|^p) of NF rows in shared memory; NT threads
-// produce columns tid, tid+NT, ... of every row: banded projection -> contrast -> normalise -> streaming store.
-// Per-column work (band metadata, coefficients, dispatch) is paid once for the NF rows; the (uniform) contrast
-// mode and band presence are dispatched once per call.
+// G rows: `val` holds the non-negative inputs (|X| or |X|^p) of G rows in shared memory; NT threads produce
+// columns tid, tid+NT, ... of every row: banded projection -> contrast -> normalise -> streaming store.
+// Rows are taken in chunks of at most 4: per-column work (band metadata, coefficients, dispatch) is paid once per
+// chunk; the (uniform) contrast mode and band presence are dispatched once per chunk, not once per column.
 template <int NT, int NF>
-__device__ __forceinline__ void epilogue_rows(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
-                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                              float* __restrict__ out_row0, int64_t col_stride, int64_t row_stride, int n_valid) {
-    float* o = out_row0 + (int64_t)(tid - ep.drop_first) * col_stride;
-    const int64_t cs = (int64_t)NT * col_stride;
+__device__ __forceinline__ void epilogue_chunk(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
+                                               const int32_t* __restrict__ meta, const float* __restrict__ coef,
+                                               float* __restrict__ o, int64_t cs, int64_t row_stride, int n_valid) {
 #define ACIDS_EPI(C, B) epilogue_cols<NT, NF, C, B>(val, val_stride, tid, ep, meta, coef, o, cs, row_stride, n_valid)
     if (meta != nullptr) {
         switch (ep.contrast) {
@@ -216,6 +214,19 @@ __device__ __forceinline__ void epilogue_rows(const float* __restrict__ val, int
         }
     }
 #undef ACIDS_EPI
+}
+
+template <int NT, int G>
+__device__ __forceinline__ void epilogue_rows(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
+                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
+                                              float* __restrict__ out_row0, int64_t col_stride, int64_t row_stride, int n_valid) {
+    constexpr int NF = G < 4 ? G : 4;
+    static_assert(G % NF == 0, "rows per CTA must be a multiple of the row chunk");
+    float* o = out_row0 + (int64_t)(tid - ep.drop_first) * col_stride;
+    const int64_t cs = (int64_t)NT * col_stride;
+    for (int g0 = 0; g0 < G && g0 < n_valid; g0 += NF)
+        epilogue_chunk<NT, NF>(val + (size_t)g0 * val_stride, val_stride, tid, ep, meta, coef, o + g0 * row_stride, cs, row_stride,
+                               n_valid - g0);
 }
 
 // stage the banded matrix in shared memory (all threads of the CTA); returns the pointers to use

@@ -36,9 +36,30 @@ struct ACIDS_ALIGN8 cf {
 };
 
 ACIDS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+#if defined(__CUDA_ARCH__)
+// Blackwell packed FP32 (CUDA 12.9 float2 builtins -> FADD2 / FMUL2 / FFMA2): a complex value is one aligned
+// register pair, so a complex add / sub is ONE instruction and a complex multiply TWO
+// (FMUL2 a, w.x ; FFMA2 swap(a) * (-w.y, +w.y) + .) — ptxas folds the swap, the per-half sign and the scalar
+// broadcast into operand modifiers (.LO_HI, .NP, .F32).  The FP32 pipe still retires 128 results / clk / SM;
+// what is saved are issue slots (tools/micro/f32x2.cu).
+__device__ __forceinline__ cf operator+(cf a, cf b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return mk(r.x, r.y);
+}
+__device__ __forceinline__ cf operator-(cf a, cf b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    return mk(r.x, r.y);
+}
+__device__ __forceinline__ cf cmul(cf a, cf b) {
+    const float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.x));
+    const float2 r = __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), t);
+    return mk(r.x, r.y);
+}
+#else
 ACIDS_HD cf operator+(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
 ACIDS_HD cf operator-(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
 ACIDS_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+#endif
 ACIDS_HD cf cconj(cf a) { return mk(a.x, -a.y); }
 ACIDS_HD cf mul_pi(cf a) { return mk(-a.y, a.x); }   // a * (+i)
 ACIDS_HD cf mul_mi(cf a) { return mk(a.y, -a.x); }   // a * (-i)
@@ -61,7 +82,7 @@ ACIDS_HD cf mul_root(cf a) {
                         (t == 7) ? 0.980785280f : (t == 9) ? 0.980785280f : (t == 10) ? 0.923879533f :
                         (t == 11) ? 0.831469612f : (t == 12) ? 0.707106781f : (t == 13) ? 0.555570233f :
                         (t == 14) ? 0.382683432f : 0.195090322f;
-    return INV ? mk(a.x * c - a.y * s, a.y * c + a.x * s) : mk(a.x * c + a.y * s, a.y * c - a.x * s);
+    return cmul(a, mk(c, INV ? s : -s));
 }
 
 // In-place radix-R DFT of a[0..R), natural-order output.  b[q] = sum_r a[r] e^{-+2 pi i r q / R}.
@@ -353,8 +374,8 @@ struct FrameFFT {
                         Bv = csel(sp, vb[3 * R / 2 - 1 - s], Bv);
                     }
                 }
-                cf E = mk(A.x + Bv.x, A.y - Bv.y);       // A + conj(B)
-                cf O = mk(A.y + Bv.y, Bv.x - A.x);       // -i (A - conj(B))
+                cf E = A + cconj(Bv);                     // A + conj(B)
+                cf O = mul_mi(A) + mk(Bv.y, Bv.x);        // -i (A - conj(B)) = (A.y + B.y, B.x - A.x)
                 cf Pm = cmul(O, wk[c * R + s]);
                 cf x1 = E + Pm, x2 = cconj(E - Pm);
                 if (c == 0 && s == 0) {
@@ -383,8 +404,8 @@ struct FrameFFT {
                     A.y = sp ? 0.f : A.y;
                     Bx.y = sp ? 0.f : Bx.y;
                 }
-                cf E2 = mk(A.x + Bx.x, A.y - Bx.y);          // A + conj(Bx)
-                cf P2 = mk(A.x - Bx.x, A.y + Bx.y);          // A - conj(Bx)
+                cf E2 = A + cconj(Bx);                        // A + conj(Bx)
+                cf P2 = A - cconj(Bx);                        // A - conj(Bx)
                 cf O2 = cmul(P2, wk[c * R + s]);             // conj(W^k) P2
                 cf iO = mul_pi(O2);
                 za[s] = E2 + iO;

@@ -32,10 +32,13 @@ struct FwdParams {
 };
 
 // launch shape per plan: small frame groups run 128-thread CTAs at 4 CTAs / SM (<= 128 registers)
+#ifndef ACIDS_FWD_MINB_SMALL
+#define ACIDS_FWD_MINB_SMALL 4
+#endif
 template <class P>
 struct FwdCfg {
     static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
-    static constexpr int MINB = P::T <= 32 ? 4 : (P::T <= 256 ? 2 : 1);
+    static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 256 ? 2 : 1);
     static constexpr int G = THREADS / P::T;
 };
 
@@ -82,35 +85,29 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
     const int64_t upc = (p.n_frames + G - 1) / G;        // units per clip
     const int64_t total = p.B * upc;
     const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+    // |X| rows of the current unit (MODE_REAL): their own region, so that the next unit's FFT never waits for
+    // the slowest epilogue thread of this one
+    constexpr int VSTR = (P::F + 3) & ~3;
+    float* vrows = reinterpret_cast<float*>(smem_raw + (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)M * sizeof(float2) +
+                                            (size_t)p.ep.band_bytes_meta + p.ep.band_bytes_coef);
 
-    int64_t b = u0 / upc;                   // clip and unit-in-clip advance incrementally: no division per frame
-    int64_t uc = u0 - b * upc;
-    for (int64_t u = u0; u < u1; ++u, ++uc) {
-        if (uc == upc) {
-            uc = 0;
-            ++b;
-        }
-        const int64_t t = uc * G + g;
+    // raw (un-windowed) samples of frame (b, t) in pass-0 operand order; edge frames reflect (torch.stft
+    // center=True, pad_mode="reflect")
+    auto fetch = [&](cf* v, int64_t b, int64_t t) {
         const bool valid = t < p.n_frames;
         const int64_t s0 = t * p.hop - p.pad;
         const float* __restrict__ xb = p.x + b * p.ldx;
-
-        // ---- load + window (pass-0 operand order) ----
-        cf v[V];
         if (valid && p.vec_ok && s0 >= 0 && s0 + N <= p.L) {
 #pragma unroll
             for (int b0 = 0; b0 < B0; ++b0) {
                 const float2* __restrict__ src = reinterpret_cast<const float2*>(xb + s0) + (tid + T * b0);
-                const float2* __restrict__ wv = swin + (tid + T * b0);
 #pragma unroll
                 for (int r = 0; r < R0; ++r) {
                     const float2 a = __ldg(src + r * NB0);
-                    const float2 w = wv[r * NB0];
-                    v[b0 * R0 + r] = mk(a.x * w.x, a.y * w.y);
+                    v[b0 * R0 + r] = mk(a.x, a.y);
                 }
             }
         } else if (valid) {
-            // edge frame: reflect padding (torch.stft center=True, pad_mode="reflect")
 #pragma unroll
             for (int b0 = 0; b0 < B0; ++b0)
 #pragma unroll
@@ -125,11 +122,36 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                         i = i < 0 ? 0 : (i >= p.L ? p.L - 1 : i);
                         e[h] = __ldg(xb + i);
                     }
-                    v[b0 * R0 + r] = mk(e[0] * swin[n].x, e[1] * swin[n].y);
+                    v[b0 * R0 + r] = mk(e[0], e[1]);
                 }
         } else {
 #pragma unroll
             for (int i = 0; i < V; ++i) v[i] = mk(0.f, 0.f);
+        }
+    };
+
+    int64_t b = u0 / upc;                   // clip and unit-in-clip advance incrementally: no division per frame
+    int64_t uc = u0 - b * upc;
+    cf v[V];
+    if (u0 < u1) fetch(v, b, uc * G + g);
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t t = uc * G + g;
+        const bool valid = t < p.n_frames;
+        const int64_t cur_b = b, cur_uc = uc;
+        if (++uc == upc) {
+            uc = 0;
+            ++b;
+        }
+
+        // ---- window (pass-0 operand order) ----
+#pragma unroll
+        for (int b0 = 0; b0 < B0; ++b0) {
+            const float2* __restrict__ wv = swin + (tid + T * b0);
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const float2 w = wv[r * NB0];
+                v[b0 * R0 + r] = mk(v[b0 * R0 + r].x * w.x, v[b0 * R0 + r].y * w.y);
+            }
         }
 
         // ---- passes ----
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
 
         if (MODE == MODE_COMPLEX) {
             if (valid) {
-                float2* __restrict__ row = reinterpret_cast<float2*>(p.out) + (b * p.n_frames + t) * (int64_t)P::F;
+                float2* __restrict__ row = reinterpret_cast<float2*>(p.out) + (cur_b * p.n_frames + t) * (int64_t)P::F;
 #pragma unroll
                 for (int c = 0; c < PR::PC; ++c) {
                     // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
@@ -176,9 +198,10 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                 }
                 if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
+            if (u + 1 < u1) fetch(v, b, uc * G + g);
         } else {
-            float* __restrict__ val = reinterpret_cast<float*>(s);
-            gsync();   // every thread has finished reading s for the last pass
+            float* __restrict__ val = vrows + g * VSTR;
+            __syncthreads();   // every thread is past the previous unit's epilogue: the rows may be overwritten
 #pragma unroll
             for (int c = 0; c < PR::PC; ++c) {
                 float* lo = val + PR::klo(tid, c);
@@ -192,15 +215,15 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                 }
             }
             if (tid == 0) val[M / 2] = pow_value(ex.x, ex.y, pmode, p.power);
+            // v, o1, o2 are dead: start fetching the next frame's samples, they land during the epilogue
+            if (u + 1 < u1) fetch(v, b, uc * G + g);
             // the G rows of this unit are projected together by the whole CTA: per-column band metadata and
-            // coefficients are fetched once for G frames
+            // coefficients are fetched once per row chunk
             __syncthreads();
-            const int64_t t0 = uc * G;
+            const int64_t t0 = cur_uc * G;
             const int n_valid = (int)min((int64_t)G, p.n_frames - t0);
-            float* out_row0 = p.out + b * p.out_clip_stride + t0 * p.out_row_stride;
-            epilogue_rows<THREADS, G>(reinterpret_cast<const float*>(smem_raw), 2 * P::SMEM_CF, threadIdx.x, ep, bmeta, bcoef,
-                                      out_row0, p.out_col_stride, p.out_row_stride, n_valid);
-            __syncthreads();
+            float* out_row0 = p.out + cur_b * p.out_clip_stride + t0 * p.out_row_stride;
+            epilogue_rows<THREADS, G>(vrows, VSTR, threadIdx.x, ep, bmeta, bcoef, out_row0, p.out_col_stride, p.out_row_stride, n_valid);
         }
     }
 }
@@ -212,7 +235,8 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     constexpr int THREADS = FwdCfg<P>::THREADS;
     constexpr int G = FwdCfg<P>::G;
     const size_t band_bytes = (MODE == MODE_REAL) ? (size_t)p.ep.band_bytes_meta + p.ep.band_bytes_coef : 0;
-    const size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)P::M * sizeof(float2) + band_bytes;
+    const size_t rows_bytes = (MODE == MODE_REAL) ? (size_t)G * ((P::F + 3) & ~3) * sizeof(float) : 0;
+    const size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)P::M * sizeof(float2) + band_bytes + rows_bytes;
     auto kern = stft_fwd_kernel<P, MODE>;
     static size_t reserved = 0;
     static int ctas_per_sm = 0;
