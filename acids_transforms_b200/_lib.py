@@ -7,7 +7,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacids_b200.so")
+LIB_PATH = os.environ.get("ACIDS_B200_LIB") or os.path.join(_HERE, "libacids_b200.so")   # override: tuning builds only
 ABI_VERSION = 1
 
 ACIDS_OK, ACIDS_EINVAL, ACIDS_ENOTSUP, ACIDS_ECUDA, ACIDS_EWORKSPACE = 0, -1, -2, -3, -4

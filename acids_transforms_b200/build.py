@@ -13,9 +13,11 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libacids_b200.so")
+LIB = os.environ.get("ACIDS_B200_LIB") or os.path.join(PKG, "libacids_b200.so")
 SOURCES = ["capi.cu", "stft_fwd.cu", "istft.cu", "spectral_repr.cu", "pointwise.cu"]
-HEADERS = ["common.cuh", "fft_core.cuh", "plans.cuh", os.path.join(ROOT, "include", "acids_b200.h")]
+# the fused forward kernels: one translation unit per FFT plan (stft_fwd_plan.cu -DACIDS_FWD_PLAN_N=n), built in parallel
+FWD_PLANS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
+HEADERS = ["common.cuh", "fft_core.cuh", "plans.cuh", "stft_fwd_kernel.cuh", os.path.join(ROOT, "include", "acids_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -39,15 +41,21 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
-    for src in SOURCES:
+    objs = []
+    units = [(src, src.replace(".cu", ".o"), []) for src in SOURCES]
+    units += [("stft_fwd_plan.cu", "stft_fwd_plan_%d.o" % n, ["-DACIDS_FWD_PLAN_N=%d" % n]) for n in FWD_PLANS]
+    extra = os.environ.get("ACIDS_NVCC_EXTRA", "").split()      # e.g. -DACIDS_FWD_MINB_SMALL=3 for tuning experiments
+    for src, obj, defs in units:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, obj)
+        objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append((s, o))
+            jobs.append((s, o, defs + extra))
+    jobs.sort(key=lambda j: -os.path.getsize(j[0]) if "plan" not in j[1] else -10**9)   # longest (per-plan) units first
 
     def compile_one(job):
-        s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        s, o, defs = job
+        cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (s, r.stdout, r.stderr))
@@ -58,7 +66,6 @@ def build(force=False, verbose=False):
             logs = list(ex.map(compile_one, jobs))
         if verbose:
             print("\n".join(logs))
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)

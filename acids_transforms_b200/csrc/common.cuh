@@ -71,10 +71,8 @@ struct EpiParams {
     int n_cols;              // output columns before drop_first
     int contrast;
     float eps;
-    float inv_scale;         // 1 / scale                 (filled on the device from the Normalize buffers)
-    float neg_off_scaled;    // -offset / scale
     int drop_first;
-    int band_bytes_meta;     // bytes of meta / coef to stage in shared memory (0: read through L1)
+    int band_bytes_meta;     // bytes of meta / coef to stage in shared memory (0: read from global memory)
     int band_bytes_coef;
 };
 
@@ -122,12 +120,40 @@ __device__ __forceinline__ float contrast_gain(int contrast) {
     return 1.0f;
 }
 
+// ---- the row-tile epilogue --------------------------------------------------------------------------------------
+// `val` (shared memory) holds the non-negative inputs (|X| or |X|^p) of NF consecutive rows, val_stride floats
+// apart.  NT threads produce columns tid, tid + NT, ... of every row:
+//     banded projection -> contrast -> normalise -> streaming store.
+// Everything that is uniform over the launch is a template parameter (contrast, where the band lives, output
+// orientation), so the column loop is branch free apart from the warp-uniform tap-count dispatch; per-column work
+// (band metadata, coefficients, dispatch) is paid once for the NF rows.
+enum { BAND_NONE = 0, BAND_SMEM = 1, BAND_GLOBAL = 2 };
+
+struct EpiArgs {
+    const int32_t* meta;     // banded matrix in the address space named by the BAND template parameter
+    const float* coef;
+    int n_cols;              // output columns before drop_first
+    int drop_first;
+    float gain;              // contrast_gain / scale
+    float bias;              // -offset / scale
+    float eps;
+};
+
+template <int BAND>
+__device__ __forceinline__ float band_ld(const float* p) {
+    return BAND == BAND_GLOBAL ? __ldg(p) : *p;
+}
+template <int BAND>
+__device__ __forceinline__ int band_ldi(const int32_t* p) {
+    return BAND == BAND_GLOBAL ? __ldg(p) : *p;
+}
+
 // K taps of one column for NF rows: the K coefficients are loaded once and reused for every row
-template <int K, int NF>
+template <int K, int NF, int BAND>
 __device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride, const float* __restrict__ c, float (&a)[NF]) {
     float w[K > 0 ? K : 1];
 #pragma unroll
-    for (int u = 0; u < K; ++u) w[u] = c[u << 5];
+    for (int u = 0; u < K; ++u) w[u] = band_ld<BAND>(c + (u << 5));
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float acc = 0.f;
@@ -138,117 +164,92 @@ __device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride
 }
 
 // Banded projection of column m for NF rows (rows are val_stride floats apart).  The tap count is uniform over
-// a group of 32 columns, so the switch does not diverge inside a warp and every case is branch-free.
-template <int NF>
+// a group of 32 columns, so the switch does not diverge inside a warp and every case is straight-line code.
+template <int NF, int BAND>
 __device__ __forceinline__ void band_column(const float* __restrict__ val, int val_stride, const int32_t* __restrict__ meta,
                                             const float* __restrict__ coef, int n_groups, int m, float (&a)[NF]) {
-    const int2 gi = *reinterpret_cast<const int2*>(meta + 2 * (m >> 5));      // (cnt, base)
-    const float* __restrict__ v = val + meta[2 * n_groups + m];
-    const float* __restrict__ c = coef + (gi.y << 5) + (m & 31);
-    switch (gi.x) {
-        case 0: taps<0, NF>(v, val_stride, c, a); break;
-        case 1: taps<1, NF>(v, val_stride, c, a); break;
-        case 2: taps<2, NF>(v, val_stride, c, a); break;
-        case 3: taps<3, NF>(v, val_stride, c, a); break;
-        case 4: taps<4, NF>(v, val_stride, c, a); break;
-        case 5: taps<5, NF>(v, val_stride, c, a); break;
-        case 6: taps<6, NF>(v, val_stride, c, a); break;
-        case 7: taps<7, NF>(v, val_stride, c, a); break;
-        case 8: taps<8, NF>(v, val_stride, c, a); break;
+    const int cnt = band_ldi<BAND>(meta + 2 * (m >> 5));
+    const int base = band_ldi<BAND>(meta + 2 * (m >> 5) + 1);
+    const float* __restrict__ v = val + band_ldi<BAND>(meta + 2 * n_groups + m);
+    const float* __restrict__ c = coef + (base << 5) + (m & 31);
+    switch (cnt) {
+        case 0: taps<0, NF, BAND>(v, val_stride, c, a); break;
+        case 1: taps<1, NF, BAND>(v, val_stride, c, a); break;
+        case 2: taps<2, NF, BAND>(v, val_stride, c, a); break;
+        case 3: taps<3, NF, BAND>(v, val_stride, c, a); break;
+        case 4: taps<4, NF, BAND>(v, val_stride, c, a); break;
+        case 5: taps<5, NF, BAND>(v, val_stride, c, a); break;
+        case 6: taps<6, NF, BAND>(v, val_stride, c, a); break;
+        case 7: taps<7, NF, BAND>(v, val_stride, c, a); break;
+        case 8: taps<8, NF, BAND>(v, val_stride, c, a); break;
         default:
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float acc = 0.f;
-                for (int u = 0; u < gi.x; ++u) acc = fmaf(v[f * val_stride + u], c[u << 5], acc);
+                for (int u = 0; u < cnt; ++u) acc = fmaf(v[f * val_stride + u], band_ld<BAND>(c + (u << 5)), acc);
                 a[f] = acc;
             }
     }
 }
 
-template <int NT, int NF, int CONTRAST, bool BAND>
-__device__ __forceinline__ void epilogue_cols(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
-                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                              float* __restrict__ o, int64_t col_step, int64_t row_step, int n_valid) {
-    // o points at this thread's first column of row 0 (already shifted by drop_first); consecutive columns of a
-    // thread are NT apart (col_step floats), consecutive rows row_step floats
+template <int NT, int NF, int CONTRAST, int BAND, bool TRANSPOSED>
+__device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int val_stride, int tid, const EpiArgs& ep,
+                                              float* __restrict__ out0, int row_step, int col_step, int n_valid) {
+    // out0: element (row 0, column drop_first) of the tile; rows are row_step floats apart, columns col_step
+    // (TRANSPOSED: rows are adjacent, row_step is ignored; otherwise columns are adjacent, col_step is ignored)
     const int n_groups = (ep.n_cols + 31) >> 5;
-    const float gain = ep.inv_scale * contrast_gain(CONTRAST);
-    for (int m = tid; m < ep.n_cols; m += NT, o += col_step) {
+    for (int m = tid; m < ep.n_cols; m += NT) {
         float a[NF];
-        if (BAND) {
-            band_column<NF>(val, val_stride, meta, coef, n_groups, m, a);
+        if (BAND != BAND_NONE) {
+            band_column<NF, BAND>(val, val_stride, ep.meta, ep.coef, n_groups, m, a);
         } else {
 #pragma unroll
             for (int f = 0; f < NF; ++f) a[f] = val[f * val_stride + m];
         }
         if (m >= ep.drop_first) {
+            float* __restrict__ o = out0 + (TRANSPOSED ? (m - ep.drop_first) * col_step : (m - ep.drop_first));
 #pragma unroll
             for (int f = 0; f < NF; ++f)
-                if (f < n_valid) stg_stream1(o + f * row_step, fmaf(contrast_core<CONTRAST>(a[f], ep.eps), gain, ep.neg_off_scaled));
+                if (f < n_valid)
+                    stg_stream1(o + (TRANSPOSED ? f : f * row_step), fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
         }
     }
 }
 
-// G rows: `val` holds the non-negative inputs (|X| or |X|^p) of G rows in shared memory; NT threads produce
-// columns tid, tid+NT, ... of every row: banded projection -> contrast -> normalise -> streaming store.
-// Rows are taken in chunks of at most 4: per-column work (band metadata, coefficients, dispatch) is paid once per
-// chunk; the (uniform) contrast mode and band presence are dispatched once per chunk, not once per column.
-template <int NT, int NF>
-__device__ __forceinline__ void epilogue_chunk(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
-                                               const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                               float* __restrict__ o, int64_t cs, int64_t row_stride, int n_valid) {
-#define ACIDS_EPI(C, B) epilogue_cols<NT, NF, C, B>(val, val_stride, tid, ep, meta, coef, o, cs, row_stride, n_valid)
-    if (meta != nullptr) {
-        switch (ep.contrast) {
-            case ACIDS_CONTRAST_LOG1P: ACIDS_EPI(ACIDS_CONTRAST_LOG1P, true); break;
-            case ACIDS_CONTRAST_LOG: ACIDS_EPI(ACIDS_CONTRAST_LOG, true); break;
-            case ACIDS_CONTRAST_LOG10: ACIDS_EPI(ACIDS_CONTRAST_LOG10, true); break;
-            default: ACIDS_EPI(ACIDS_CONTRAST_NONE, true); break;
-        }
-    } else {
-        switch (ep.contrast) {
-            case ACIDS_CONTRAST_LOG1P: ACIDS_EPI(ACIDS_CONTRAST_LOG1P, false); break;
-            case ACIDS_CONTRAST_LOG: ACIDS_EPI(ACIDS_CONTRAST_LOG, false); break;
-            case ACIDS_CONTRAST_LOG10: ACIDS_EPI(ACIDS_CONTRAST_LOG10, false); break;
-            default: ACIDS_EPI(ACIDS_CONTRAST_NONE, false); break;
-        }
-    }
-#undef ACIDS_EPI
-}
-
-template <int NT, int G>
-__device__ __forceinline__ void epilogue_rows(const float* __restrict__ val, int val_stride, int tid, const EpiParams& ep,
-                                              const int32_t* __restrict__ meta, const float* __restrict__ coef,
-                                              float* __restrict__ out_row0, int64_t col_stride, int64_t row_stride, int n_valid) {
-    constexpr int NF = G < 4 ? G : 4;
-    static_assert(G % NF == 0, "rows per CTA must be a multiple of the row chunk");
-    float* o = out_row0 + (int64_t)(tid - ep.drop_first) * col_stride;
-    const int64_t cs = (int64_t)NT * col_stride;
-    for (int g0 = 0; g0 < G && g0 < n_valid; g0 += NF)
-        epilogue_chunk<NT, NF>(val + (size_t)g0 * val_stride, val_stride, tid, ep, meta, coef, o + g0 * row_stride, cs, row_stride,
-                               n_valid - g0);
-}
-
-// stage the banded matrix in shared memory (all threads of the CTA); returns the pointers to use
-__device__ __forceinline__ void stage_band(const EpiParams& ep, unsigned char* smem_band, const int32_t*& meta,
-                                           const float*& coef) {
-    meta = ep.meta;
-    coef = ep.coef;
-    if (ep.meta != nullptr && ep.band_bytes_meta > 0) {
-        int32_t* sm = reinterpret_cast<int32_t*>(smem_band);
-        float* sc = reinterpret_cast<float*>(smem_band + ep.band_bytes_meta);
-        for (int i = threadIdx.x; i < ep.band_bytes_meta / 4; i += blockDim.x) sm[i] = __ldg(ep.meta + i);
-        for (int i = threadIdx.x; i < ep.band_bytes_coef / 4; i += blockDim.x) sc[i] = __ldg(ep.coef + i);
-        meta = sm;
-        coef = sc;
+// runtime contrast -> compile-time contrast (one dispatch per launch-uniform value; call sites that already know
+// the contrast at compile time call epilogue_tile directly)
+template <int NT, int NF, int BAND, bool TRANSPOSED>
+__device__ __forceinline__ void epilogue_tile_rt(int contrast, const float* __restrict__ val, int val_stride, int tid,
+                                                 const EpiArgs& ep, float* __restrict__ out0, int row_step, int col_step, int n_valid) {
+    switch (contrast) {
+        case ACIDS_CONTRAST_LOG1P: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG1P, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
+        case ACIDS_CONTRAST_LOG: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
+        case ACIDS_CONTRAST_LOG10: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG10, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
+        default: epilogue_tile<NT, NF, ACIDS_CONTRAST_NONE, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
     }
 }
 
-__device__ __forceinline__ void load_norm(const float* offset, const float* scale, EpiParams& ep) {
-    // (x - offset) / scale as one FFMA: x * (1/scale) + (-offset/scale)   (norm.py:40-41)
+// stage the banded matrix in shared memory (all threads of the CTA; caller synchronises)
+__device__ __forceinline__ void stage_band(const EpiParams& ep, int32_t* smeta, float* scoef) {
+    for (int i = threadIdx.x; i < ep.band_bytes_meta / 4; i += blockDim.x) smeta[i] = __ldg(ep.meta + i);
+    for (int i = threadIdx.x; i < ep.band_bytes_coef / 4; i += blockDim.x) scoef[i] = __ldg(ep.coef + i);
+}
+
+__device__ __forceinline__ EpiArgs make_epi_args(const EpiParams& ep, const int32_t* meta, const float* coef, const float* offset,
+                                                 const float* scale) {
+    // (x - offset) / scale as one FFMA: x * (1/scale) + (-offset/scale)   (norm.py:40-41); the constant factor of
+    // the lg2-based contrast is folded into the same multiply
+    EpiArgs a;
+    a.meta = meta;
+    a.coef = coef;
+    a.n_cols = ep.n_cols;
+    a.drop_first = ep.drop_first;
     const float off = offset ? __ldg(offset) : 0.f;
-    ep.inv_scale = scale ? 1.0f / __ldg(scale) : 1.0f;
-    ep.neg_off_scaled = -off * ep.inv_scale;
+    const float inv = scale ? 1.0f / __ldg(scale) : 1.0f;
+    a.gain = inv * contrast_gain(ep.contrast);
+    a.bias = -off * inv;
+    a.eps = ep.eps;
+    return a;
 }
 
 // bytes of shared memory the banded matrix needs, or 0 when it should stay in global memory

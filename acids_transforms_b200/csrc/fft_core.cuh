@@ -35,6 +35,12 @@ struct ACIDS_ALIGN8 cf {
     float x, y;
 };
 
+#if defined(__CUDACC__)
+struct __align__(16) cf2 { cf a, b; };     // two adjacent complex slots: one 128-bit access
+#else
+struct alignas(16) cf2 { cf a, b; };
+#endif
+
 ACIDS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
 #if defined(__CUDA_ARCH__)
 // Blackwell packed FP32 (CUDA 12.9 float2 builtins -> FADD2 / FMUL2 / FFMA2): a complex value is one aligned
@@ -55,7 +61,12 @@ __device__ __forceinline__ cf cmul(cf a, cf b) {
     const float2 r = __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), t);
     return mk(r.x, r.y);
 }
+__device__ __forceinline__ cf cmul2(cf a, cf w) {      // element-wise (a.x w.x, a.y w.y): one FMUL2
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(w.x, w.y));
+    return mk(r.x, r.y);
+}
 #else
+ACIDS_HD cf cmul2(cf a, cf w) { return mk(a.x * w.x, a.y * w.y); }
 ACIDS_HD cf operator+(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
 ACIDS_HD cf operator-(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
 ACIDS_HD cf cmul(cf a, cf b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -158,17 +169,19 @@ ACIDS_HD cf unit(int num, int den) {
     return mk(c, s);
 }
 
-// Shared-memory index swizzle for the exchange buffers (pad one slot every 2^PADLOG slots).
+// Shared-memory index swizzle for the exchange buffers: TWO pad slots (16 bytes) every 2^PADLOG slots, so that
+// pairs of slots stay 16-byte aligned (128-bit stores of the first pass) and a run of 64 slots is displaced by
+// half a bank row (the strided stores of the middle passes of the 8x8x8 plan become conflict free).
 // swz(base + c) == swz(base) + swz(c) whenever (base mod 2^PADLOG) + (c mod 2^PADLOG) < 2^PADLOG, which
 // holds for every (pass, butterfly, slot) of every plan (checked exhaustively by tests/emu/emu_fft.cpp):
 // each access is one per-thread base plus a compile-time immediate.
 template <int PADLOG>
 ACIDS_HD int swz(int i) {
-    return i + (i >> PADLOG);
+    return i + 2 * (i >> PADLOG);
 }
 template <int PADLOG>
 ACIDS_HD constexpr int swzc(int c) {
-    return c + (c >> PADLOG);
+    return c + 2 * (c >> PADLOG);
 }
 #if !defined(__CUDA_ARCH__) && defined(ACIDS_EMU_CHECK)
 #define ACIDS_EMU_ASSERT(cond) do { if (!(cond)) { printf("emu assert failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); abort(); } } while (0)
@@ -189,7 +202,7 @@ struct Plan {
     static constexpr int V = M / T_;
     static constexpr int NP = (R3_ > 1) ? 4 : ((R2_ > 1) ? 3 : 2);
     static constexpr int PADLOG = 4;
-    static constexpr int SMEM_CF = M + (M >> PADLOG) + 1;   // exchange buffer, complex slots
+    static constexpr int SMEM_CF = M + 2 * (M >> PADLOG) + 2;   // exchange buffer, complex slots (even: 16-byte rows)
     static_assert(R0_ * R1_ * R2_ * R3_ == M, "radices must multiply to N/2");
     static_assert(M % T_ == 0, "T must divide N/2");
     static constexpr int radix(int p) { return p == 0 ? R0_ : (p == 1 ? R1_ : (p == 2 ? R2_ : R3_)); }
@@ -255,15 +268,24 @@ struct FrameFFT {
     template <int PASS>
     static constexpr bool tw_is_shared() { return PASS != PAIRED && P::tw_shared(PASS); }
 
+    // butterfly that slot b of this thread computes in pass PASS.  Paired pass: mirrored couples (see above).
+    // First pass of the forward transform: bpt(0) CONSECUTIVE butterflies, so that a thread's operands of one
+    // radix slot are adjacent in memory (128-bit global / window loads) and its outputs one contiguous run
+    // (128-bit exchange stores).  Elsewhere: strided by T (consecutive lanes touch consecutive slots).
+    template <int PASS>
+    ACIDS_HD int bfly(int b) const {
+        if (PASS == PAIRED) return (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
+        if (PASS == 0) return tid * P::bpt(0) + b;
+        return tid + P::T * b;
+    }
+
     template <int PASS>
     ACIDS_HD void init_pass() {
         constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = tw_is_shared<PASS>() ? 1 : P::bpt(PASS);
         if (PASS > 0) {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
-                int j;
-                if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
-                else j = tid + P::T * b;
+                int j = bfly<PASS>(b);
                 int k = j % NS;
 #pragma unroll
                 for (int r = 1; r < R; ++r) {
@@ -293,18 +315,13 @@ struct FrameFFT {
     template <int PASS>
     ACIDS_HD int in_index(int b, int r) const {
         constexpr int NB = P::nb(PASS);
-        int j;
-        if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
-        else j = tid + P::T * b;
-        return j + r * NB;
+        return bfly<PASS>(b) + r * NB;
     }
     // element that v[b*R + q] holds AFTER the butterfly of pass PASS
     template <int PASS>
     ACIDS_HD int out_index(int b, int q) const {
         constexpr int R = P::radix(PASS), NS = P::ns(PASS);
-        int j;
-        if (PASS == PAIRED) j = (b & 1) ? PR::jb(tid, b >> 1) : PR::ja(tid, b >> 1);
-        else j = tid + P::T * b;
+        int j = bfly<PASS>(b);
         int k = j % NS;
         return (j - k) * R + k + q * NS;
     }
@@ -329,10 +346,24 @@ struct FrameFFT {
 #pragma unroll
         for (int b = 0; b < B; ++b) {
             cf* sb = s + swz<P::PADLOG>(out_index<PASS>(b, 0));
+            if (NS == 1 && R % 2 == 0) {
+                // the R outputs of a first-pass butterfly are one contiguous, 16-byte aligned run: 128-bit stores
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q)) == swz<P::PADLOG>(out_index<PASS>(b, 0)) + swzc<P::PADLOG>(q * NS));
-                sb[swzc<P::PADLOG>(q * NS)] = v[b * R + q];
+                for (int q = 0; q < R; q += 2) {
+                    ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q)) == swz<P::PADLOG>(out_index<PASS>(b, 0)) + swzc<P::PADLOG>(q));
+                    ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q + 1)) == swz<P::PADLOG>(out_index<PASS>(b, q)) + 1);
+                    ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q)) % 2 == 0);
+                    cf2 w;
+                    w.a = v[b * R + q];
+                    w.b = v[b * R + q + 1];
+                    *reinterpret_cast<cf2*>(sb + swzc<P::PADLOG>(q)) = w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    ACIDS_EMU_ASSERT(swz<P::PADLOG>(out_index<PASS>(b, q)) == swz<P::PADLOG>(out_index<PASS>(b, 0)) + swzc<P::PADLOG>(q * NS));
+                    sb[swzc<P::PADLOG>(q * NS)] = v[b * R + q];
+                }
             }
         }
     }

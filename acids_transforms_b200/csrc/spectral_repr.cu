@@ -20,17 +20,18 @@ struct MagParams {
     int64_t out_row_stride;
 };
 
+template <int BAND>
 __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
-    // 8 rows per CTA iteration: each warp stages |X| of one row, then the CTA projects the 8 rows together
+    // 8 rows per CTA iteration: each warp stages |X| of one row, then the CTA projects the rows together (tiles of 4)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = (p.n_bins + 3) & ~3;
     float* val = reinterpret_cast<float*>(smem_raw);
-    EpiParams ep = p.ep;
-    load_norm(p.offset_ptr, p.scale_ptr, ep);
-    const int32_t* bmeta;
-    const float* bcoef;
-    stage_band(ep, smem_raw + (size_t)8 * stride * sizeof(float), bmeta, bcoef);
+    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)8 * stride * sizeof(float));
+    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)8 * stride * sizeof(float) + p.ep.band_bytes_meta);
+    if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
+    const EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef,
+                                     p.offset_ptr, p.scale_ptr);
     __syncthreads();
     for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < p.rows; r0 += (int64_t)gridDim.x * 8) {
         const int64_t r = r0 + warp;
@@ -43,7 +44,11 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
         }
         __syncthreads();
         const int n_valid = (int)min((int64_t)8, p.rows - r0);
-        epilogue_rows<256, 8>(val, stride, threadIdx.x, ep, bmeta, bcoef, p.out + r0 * p.out_row_stride, 1, p.out_row_stride, n_valid);
+        const int rs = (int)p.out_row_stride;
+#pragma unroll 1
+        for (int g0 = 0; g0 < 8 && g0 < n_valid; g0 += 4)
+            epilogue_tile_rt<256, 4, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
+                                                  p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
         __syncthreads();
     }
 }
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
         float* __restrict__ out = p.out + r * (int64_t)p.n_out;
         for (int m = lane; m < p.n_out; m += 32) {
             float a[1];
-            if (p.meta) band_column<1>(val, 0, p.meta, p.coef, (p.n_out + 31) >> 5, m, a);
+            if (p.meta) band_column<1, BAND_GLOBAL>(val, 0, p.meta, p.coef, (p.n_out + 31) >> 5, m, a);
             else a[0] = val[m];
             stg_stream1(out + m, a[0]);
         }
@@ -285,16 +290,13 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     if (rc) return rc;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
     const size_t smem = (size_t)8 * ((n_bins + 3) & ~3) * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
-    static size_t reserved = 48 * 1024;
-    if (smem > reserved) {
-        ACIDS_REQUIRE(cudaFuncSetAttribute(mag_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
-                      ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
-        reserved = smem;
-    }
+    auto kern = !band.meta ? mag_epilogue_kernel<BAND_NONE> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM> : mag_epilogue_kernel<BAND_GLOBAL>);
+    ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
+                  ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
     int64_t grid = (rows + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
-    mag_epilogue_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("mag_epilogue");
     return ACIDS_OK;
 }

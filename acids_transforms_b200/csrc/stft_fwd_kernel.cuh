@@ -1,0 +1,323 @@
+// stft_fwd_kernel.cuh — the fused forward kernel template, its launch logic and the per-plan entry points.
+// stft_fwd_plan.cu instantiates it once per FFT plan (one translation unit each, built in parallel);
+// stft_fwd.cu holds the C ABI and dispatches on n_fft.
+#pragma once
+#include "common.cuh"
+#include "plans.cuh"
+
+namespace acids {
+
+enum { MODE_COMPLEX = 0, MODE_REAL = 1 };
+enum { VAR_COMPLEX = 0, VAR_MAG_NOBAND, VAR_MAG_SMEM, VAR_MAG_GLOBAL, VAR_MEL_POWER_SMEM, VAR_MEL_POWER_GLOBAL, VAR_MEL_ANY_SMEM,
+       VAR_MEL_ANY_GLOBAL };
+
+struct FwdParams {
+    const float* x;
+    int64_t B, L, ldx;
+    int hop, pad;
+    int64_t n_frames;
+    const float* window;
+    float* out;
+    int64_t out_clip_stride, out_row_stride, out_col_stride;   // MODE_REAL, in floats
+    EpiParams ep;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    float power;     // MODE_REAL: value = |X|^power (1 -> magnitude, 2 -> power spectrum)
+    int vec_ok;      // clip rows and frame starts are aligned for the first pass's vector loads (bit 0: 8 B, bit 1: 16 B)
+    int band_smem_bytes;   // shared memory reserved for the banded matrix (16-byte multiple; 0: read it from global)
+};
+
+// launch shape per plan: small frame groups run 128-thread CTAs at 4 CTAs / SM (<= 128 registers)
+#ifndef ACIDS_FWD_MINB_SMALL
+#define ACIDS_FWD_MINB_SMALL 4
+#endif
+template <class P>
+struct FwdCfg {
+    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
+    static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 256 ? 2 : 1);
+    static constexpr int G = THREADS / P::T;
+    static constexpr int NF = G < 4 ? G : 4;                    // rows per epilogue tile
+    static constexpr int VSTR = (P::F + 3) & ~3;                // |X| row stride in shared memory (floats)
+    static constexpr int VW = (P::bpt(0) % 2 == 0) ? 4 : 2;     // floats per vector load of the first pass
+    static_assert(G % NF == 0, "rows per CTA must be a multiple of the row tile");
+    static constexpr size_t exch_bytes() { return (size_t)G * P::SMEM_CF * sizeof(cf); }
+    static constexpr size_t win_bytes() { return (size_t)P::M * sizeof(float2); }
+};
+
+static inline size_t round16(size_t n) { return (n + 15) & ~(size_t)15; }
+
+// |X|^power from the squared magnitude; PMODE: 1 -> magnitude, 2 -> power spectrum, 0 -> general exponent
+template <int PMODE>
+__device__ __forceinline__ float pow_value(cf a, float power) {
+    const float p2 = fmaf(a.x, a.x, a.y * a.y);
+    if (PMODE == 1) return fast_sqrt(p2);
+    if (PMODE == 2) return p2;
+    return powf(fast_sqrt(p2), power);
+}
+
+// CSEL: contrast known at compile time (ACIDS_CONTRAST_*) or -1 (dispatched once per row tile)
+template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
+__global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_kernel(const FwdParams p) {
+    using C = FwdCfg<P>;
+    constexpr int THREADS = C::THREADS;
+    constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW;
+    constexpr int R0 = P::radix(0), B0 = P::bpt(0), NB0 = P::nb(0);
+    using FFT = FrameFFT<P, false>;
+    using PR = typename FFT::PR;
+    constexpr int RP = PR::R, NBP = PR::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = threadIdx.x / T, tid = threadIdx.x % T;
+    cf* const s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
+    auto gsync = [&]() { group_sync<T, THREADS>(g); };
+
+    // ---- frame-invariant state: twiddles in registers; the analysis window as (w[2n], w[2n+1]) / 2 pairs in shared
+    //      memory (1/2 = the factor of the even/odd split); the banded matrix; the normalisation constants ----
+    FFT fft;
+    fft.init(tid);
+    float2* const swin = reinterpret_cast<float2*>(smem_raw + C::exch_bytes());
+    for (int n = threadIdx.x; n < M; n += THREADS)
+        swin[n] = make_float2(0.5f * __ldg(p.window + 2 * n), 0.5f * __ldg(p.window + 2 * n + 1));
+    EpiArgs ea{};
+    float* vrows = nullptr;
+    if (MODE == MODE_REAL) {
+        unsigned char* bandmem = smem_raw + C::exch_bytes() + C::win_bytes();
+        int32_t* smeta = reinterpret_cast<int32_t*>(bandmem);
+        float* scoef = reinterpret_cast<float*>(bandmem + p.ep.band_bytes_meta);
+        if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
+        ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef, p.offset_ptr,
+                           p.scale_ptr);
+        // |X| rows of a unit, double buffered: the next unit's FFT never waits for the slowest epilogue thread
+        vrows = reinterpret_cast<float*>(bandmem + (BAND == BAND_SMEM ? p.band_smem_bytes : 0));
+    }
+    __syncthreads();
+
+    const int64_t upc = (p.n_frames + G - 1) / G;        // units per clip
+    const int64_t total = p.B * upc;
+    const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+
+    // Raw (un-windowed) samples of frame (b, t) in first-pass operand order.  Interior, aligned frames: vector
+    // loads straight into registers.  Edge frames (torch.stft center=True, pad_mode="reflect") and unaligned
+    // inputs: the group stages the frame in its exchange buffer with scalar loads, then reads its operands.
+    auto fetch = [&](cf* v, int64_t b, int64_t t) {
+        const bool valid = t < p.n_frames;
+        const int64_t s0 = t * p.hop - p.pad;
+        const float* __restrict__ xb = p.x + b * p.ldx;
+        const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0 >= 0 && s0 + N <= p.L;
+        bool stage = valid && !fast;
+        if (T < 32) stage = __any_sync(0xffffffffu, stage);     // frame groups sharing a warp take the same path
+        if (!stage) {
+            if (valid) {
+#pragma unroll
+                for (int r = 0; r < R0; ++r) {
+                    // this thread's B0 butterflies are consecutive: B0 adjacent complex operands per radix slot
+                    const float* __restrict__ src = xb + s0 + 2 * (tid * B0 + r * NB0);
+                    if (VW == 4) {
+#pragma unroll
+                        for (int b0 = 0; b0 < B0; b0 += 2) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
+                            v[b0 * R0 + r] = mk(a.x, a.y);
+                            v[(b0 + 1) * R0 + r] = mk(a.z, a.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int b0 = 0; b0 < B0; ++b0) {
+                            const float2 a = __ldg(reinterpret_cast<const float2*>(src) + b0);
+                            v[b0 * R0 + r] = mk(a.x, a.y);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i) v[i] = mk(0.f, 0.f);
+            }
+        } else {
+            float* sf = reinterpret_cast<float*>(s);
+            gsync();   // the group is done reading the exchange buffer
+            for (int i = tid; i < N; i += T) {
+                int64_t k = s0 + i;
+                if (k < 0) k = -k;
+                if (k >= p.L) k = 2 * (p.L - 1) - k;
+                k = k < 0 ? 0 : (k >= p.L ? p.L - 1 : k);
+                sf[i] = valid ? __ldg(xb + k) : 0.f;
+            }
+            gsync();
+#pragma unroll
+            for (int b0 = 0; b0 < B0; ++b0)
+#pragma unroll
+                for (int r = 0; r < R0; ++r) v[b0 * R0 + r] = *reinterpret_cast<const cf*>(sf + 2 * fft.template in_index<0>(b0, r));
+        }
+    };
+
+    int64_t b = u0 / upc;                   // clip and unit-in-clip advance incrementally: no division per frame
+    int64_t uc = u0 - b * upc;
+    int buf = 0;
+    cf v[V];
+    if (u0 < u1) fetch(v, b, uc * G + g);
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t t = uc * G + g;
+        const bool valid = t < p.n_frames;
+        const int64_t cur_b = b, cur_uc = uc;
+        if (++uc == upc) {
+            uc = 0;
+            ++b;
+        }
+
+        // ---- window (first-pass operand order, same adjacency as the loads) ----
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+            const float2* __restrict__ wv = swin + (tid * B0 + r * NB0);
+            if (VW == 4) {
+#pragma unroll
+                for (int b0 = 0; b0 < B0; b0 += 2) {
+                    const float4 w = *reinterpret_cast<const float4*>(wv + b0);
+                    v[b0 * R0 + r] = cmul2(v[b0 * R0 + r], mk(w.x, w.y));
+                    v[(b0 + 1) * R0 + r] = cmul2(v[(b0 + 1) * R0 + r], mk(w.z, w.w));
+                }
+            } else {
+#pragma unroll
+                for (int b0 = 0; b0 < B0; ++b0) {
+                    const float2 w = wv[b0];
+                    v[b0 * R0 + r] = cmul2(v[b0 * R0 + r], mk(w.x, w.y));
+                }
+            }
+        }
+
+        // ---- passes ----
+        fft.template butterflies<0>(v);
+        gsync();   // the previous frame's readers of s are done
+        fft.template store<0>(v, s);
+        gsync();
+        fft.template load<1>(v, s);
+        fft.template butterflies<1>(v);
+        if constexpr (P::NP > 2) {
+            gsync();
+            fft.template store<1>(v, s);
+            gsync();
+            fft.template load<2>(v, s);
+            fft.template butterflies<2>(v);
+        }
+        if constexpr (P::NP > 3) {
+            gsync();
+            fft.template store<2>(v, s);
+            gsync();
+            fft.template load<3>(v, s);
+            fft.template butterflies<3>(v);
+        }
+
+        // ---- untangle in registers ----
+        cf o1[V / 2], o2[V / 2], ex;
+        fft.untangle_fwd(v, o1, o2, ex);
+
+        if (MODE == MODE_COMPLEX) {
+            if (valid) {
+                float2* __restrict__ row = reinterpret_cast<float2*>(p.out) + (cur_b * p.n_frames + t) * (int64_t)P::F;
+#pragma unroll
+                for (int c = 0; c < PR::PC; ++c) {
+                    // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
+                    float2* lo = row + PR::klo(tid, c);
+                    float2* hi = row + PR::khi(tid, c);
+                    float2* mlo = row + (M - PR::klo(tid, c));
+                    float2* mhi = row + (M - PR::khi(tid, c));
+#pragma unroll
+                    for (int q = 0; q < RP; ++q) {
+                        stg_stream2((q < RP / 2 ? lo : hi) + q * NBP, o1[c * RP + q].x, o1[c * RP + q].y);
+                        stg_stream2((q < RP / 2 ? mlo : mhi) - q * NBP, o2[c * RP + q].x, o2[c * RP + q].y);
+                    }
+                }
+                if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
+            }
+            if (u + 1 < u1) fetch(v, b, uc * G + g);
+        } else {
+            float* __restrict__ vbuf = vrows + buf * (G * VSTR);
+            float* __restrict__ val = vbuf + g * VSTR;
+#pragma unroll
+            for (int c = 0; c < PR::PC; ++c) {
+                float* lo = val + PR::klo(tid, c);
+                float* hi = val + PR::khi(tid, c);
+                float* mlo = val + (M - PR::klo(tid, c));
+                float* mhi = val + (M - PR::khi(tid, c));
+#pragma unroll
+                for (int q = 0; q < RP; ++q) {
+                    (q < RP / 2 ? lo : hi)[q * NBP] = pow_value<PMODE>(o1[c * RP + q], p.power);
+                    (q < RP / 2 ? mlo : mhi)[-q * NBP] = pow_value<PMODE>(o2[c * RP + q], p.power);
+                }
+            }
+            if (tid == 0) val[M / 2] = pow_value<PMODE>(ex, p.power);
+            // v, o1, o2 are dead: start fetching the next frame's samples, they land during the epilogue
+            if (u + 1 < u1) fetch(v, b, uc * G + g);
+            // One barrier per unit: the rows are complete.  (Writers of this buffer two units from now have passed
+            // the next barrier, i.e. every thread has left this epilogue.)
+            __syncthreads();
+            const int64_t t0 = cur_uc * G;
+            const int n_valid = (int)min((int64_t)G, p.n_frames - t0);
+            float* out0 = p.out + cur_b * p.out_clip_stride + (TRANSPOSED ? t0 : t0 * p.out_row_stride);
+            const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
+#pragma unroll 1
+            for (int g0 = 0; g0 < G; g0 += NF) {
+                if (g0 >= n_valid) break;
+                float* o = out0 + (TRANSPOSED ? g0 : g0 * rs);
+                if (CSEL >= 0)
+                    epilogue_tile<THREADS, NF, (CSEL >= 0 ? CSEL : 0), BAND, TRANSPOSED>(vbuf + g0 * VSTR, VSTR, threadIdx.x, ea, o, rs, cs, n_valid - g0);
+                else
+                    epilogue_tile_rt<THREADS, NF, BAND, TRANSPOSED>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea, o, rs, cs, n_valid - g0);
+            }
+            buf ^= 1;
+        }
+    }
+}
+
+static const size_t kBandSmemBudget = 24 * 1024;
+
+template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
+static int launch_fwd(FwdParams p, cudaStream_t st) {
+    using C = FwdCfg<P>;
+    constexpr int THREADS = C::THREADS;
+    constexpr int G = C::G;
+    size_t smem = C::exch_bytes() + C::win_bytes();
+    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (size_t)2 * G * C::VSTR * sizeof(float);
+    auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
+    static size_t reserved = 0;
+    static int ctas_per_sm = 0;
+    if (smem > reserved || ctas_per_sm == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("stft_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+            return ACIDS_ECUDA;
+        }
+        reserved = smem;
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem);
+        ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    const int64_t total = p.B * ((p.n_frames + G - 1) / G);
+    if (total == 0) return ACIDS_OK;
+    int64_t grid = (int64_t)num_sms() * ctas_per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
+    ACIDS_CHECK_LAUNCH("stft_fwd");
+    return ACIDS_OK;
+}
+
+template <class P>
+static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
+    switch (variant) {
+        case VAR_COMPLEX: return launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
+        case VAR_MAG_NOBAND: return launch_fwd<P, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
+        case VAR_MAG_SMEM: return launch_fwd<P, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
+        case VAR_MAG_GLOBAL: return launch_fwd<P, MODE_REAL, 1, -1, BAND_GLOBAL, false>(p, st);
+        case VAR_MEL_POWER_SMEM: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
+        case VAR_MEL_POWER_GLOBAL: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
+        case VAR_MEL_ANY_SMEM: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
+        case VAR_MEL_ANY_GLOBAL: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
+    }
+    set_error("stft_fwd: unknown kernel variant %d", variant);
+    return ACIDS_EINVAL;
+}
+
+
+// one definition per plan, each in its own translation unit (stft_fwd_plan.cu with -DACIDS_FWD_PLAN_N=<n_fft>)
+#define ACIDS_DECLARE_FWD_PLAN(n) int launch_fwd_plan_##n(int variant, const FwdParams& p, cudaStream_t st)
+ACIDS_DECLARE_FWD_PLAN(32); ACIDS_DECLARE_FWD_PLAN(64); ACIDS_DECLARE_FWD_PLAN(128); ACIDS_DECLARE_FWD_PLAN(256);
+ACIDS_DECLARE_FWD_PLAN(512); ACIDS_DECLARE_FWD_PLAN(1024); ACIDS_DECLARE_FWD_PLAN(2048); ACIDS_DECLARE_FWD_PLAN(4096);
+ACIDS_DECLARE_FWD_PLAN(8192); ACIDS_DECLARE_FWD_PLAN(16384);
+
+}  // namespace acids

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 #include "../../acids_transforms_b200/csrc/fft_core.cuh"
 #include "../../acids_transforms_b200/csrc/plans.cuh"
 
@@ -122,6 +123,79 @@ static double check_inv(const char* name) {
     return ei;
 }
 
+// ---- shared-memory bank model: wavefronts a warp needs for each exchange access of a plan ----------------------
+// 8-byte accesses are served per half warp (16 lanes, 16 bank pairs), 16-byte accesses per quarter warp
+// (8 lanes, 8 bank quads); lanes that hit the same word are merged.  Prints actual / ideal wavefronts per frame.
+static int wavefronts(const std::vector<long>& byte_addr, int width) {
+    const int lanes_per = width == 16 ? 8 : 16, units = 128 / width;
+    int total = 0;
+    for (size_t l0 = 0; l0 < byte_addr.size(); l0 += lanes_per) {
+        std::vector<std::vector<long>> bank(units);
+        for (size_t l = l0; l < l0 + lanes_per && l < byte_addr.size(); ++l) {
+            long u = byte_addr[l] / width;
+            auto& bk = bank[u % units];
+            bool seen = false;
+            for (long w : bk) seen |= (w == u);
+            if (!seen) bk.push_back(u);
+        }
+        size_t deg = 1;
+        for (auto& bk : bank) deg = std::max(deg, bk.size());
+        total += (int)deg;
+    }
+    return total;
+}
+
+template <class P, bool INV, int PASS>
+static void pass_conflicts(std::vector<FrameFFT<P, INV>>& th, long& actual, long& ideal) {
+    if constexpr (PASS < P::NP) {
+        constexpr int R = P::radix(PASS), B = P::bpt(PASS), NS = P::ns(PASS);
+        const int lanes = 32, groups = P::T >= 32 ? 1 : 32 / P::T, warps = P::T >= 32 ? P::T / 32 : 1;
+        auto slot_addr = [&](int lane_global, int idx) {   // byte address of slot idx for that lane's frame group
+            int g = P::T >= 32 ? 0 : lane_global / P::T;
+            return ((long)g * P::SMEM_CF + swz<P::PADLOG>(idx)) * 8L;
+        };
+        for (int w = 0; w < warps; ++w) {
+            if (PASS < P::NP - 1) {   // store<PASS>
+                const bool vec = (NS == 1 && R % 2 == 0);
+                for (int b = 0; b < B; ++b)
+                    for (int q = 0; q < R; q += vec ? 2 : 1) {
+                        std::vector<long> a;
+                        for (int l = 0; l < lanes; ++l) {
+                            int t = P::T >= 32 ? w * 32 + l : l % P::T;
+                            a.push_back(slot_addr(l, th[t].template out_index<PASS>(b, q)));
+                        }
+                        actual += wavefronts(a, vec ? 16 : 8);
+                        ideal += vec ? 4 : 2;
+                    }
+            }
+            if (PASS > 0) {           // load<PASS>
+                for (int b = 0; b < B; ++b)
+                    for (int r = 0; r < R; ++r) {
+                        std::vector<long> a;
+                        for (int l = 0; l < lanes; ++l) {
+                            int t = P::T >= 32 ? w * 32 + l : l % P::T;
+                            a.push_back(slot_addr(l, th[t].template in_index<PASS>(b, r)));
+                        }
+                        actual += wavefronts(a, 8);
+                        ideal += 2;
+                    }
+            }
+        }
+        (void)groups;
+        pass_conflicts<P, INV, PASS + 1>(th, actual, ideal);
+    }
+}
+
+template <class P, bool INV>
+static void report_conflicts(const char* name) {
+    std::vector<FrameFFT<P, INV>> th(P::T);
+    for (int t = 0; t < P::T; ++t) th[t].init(t);
+    long actual = 0, ideal = 0;
+    pass_conflicts<P, INV, 0>(th, actual, ideal);
+    printf("%-10s %s exchange wavefronts per warp-frame-set: %ld (ideal %ld, x%.2f)\n", name, INV ? "inv" : "fwd", actual, ideal,
+           (double)actual / ideal);
+}
+
 #define CHECKF(PL) worst = fmax(worst, check_fwd<PL>(#PL))
 #define CHECKI(PL) worst = fmax(worst, check_inv<PL>(#PL))
 
@@ -129,6 +203,10 @@ int main() {
     double worst = 0;
     ACIDS_FOR_EACH_FWD_PLAN(CHECKF);
     ACIDS_FOR_EACH_INV_PLAN(CHECKI);
+#define CONFF(PL) report_conflicts<PL, false>(#PL)
+#define CONFI(PL) report_conflicts<PL, true>(#PL)
+    ACIDS_FOR_EACH_FWD_PLAN(CONFF);
+    ACIDS_FOR_EACH_INV_PLAN(CONFI);
     if (!(worst < 5e-6)) { printf("FAIL worst %.3e\n", worst); return 1; }
     printf("OK worst %.3e\n", worst);
     return 0;
