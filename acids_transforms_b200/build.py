@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
+OBJ = os.environ.get("ACIDS_B200_OBJ") or os.path.join(PKG, "build")
 LIB = os.environ.get("ACIDS_B200_LIB") or os.path.join(PKG, "libacids_b200.so")
 SOURCES = ["capi.cu", "stft_fwd.cu", "istft.cu", "spectral_repr.cu", "pointwise.cu"]
 # the fused forward kernels: one translation unit per FFT plan (stft_fwd_plan.cu -DACIDS_FWD_PLAN_N=n), built in parallel

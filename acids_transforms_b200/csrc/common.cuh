@@ -122,38 +122,32 @@ __device__ __forceinline__ float contrast_gain(int contrast) {
 
 // ---- the row-tile epilogue --------------------------------------------------------------------------------------
 // `val` (shared memory) holds the non-negative inputs (|X| or |X|^p) of NF consecutive rows, val_stride floats
-// apart.  NT threads produce columns tid, tid + NT, ... of every row:
+// apart.  NT threads produce output columns tid, tid + NT, ... of every row:
 //     banded projection -> contrast -> normalise -> streaming store.
 // Everything that is uniform over the launch is a template parameter (contrast, where the band lives, output
-// orientation), so the column loop is branch free apart from the warp-uniform tap-count dispatch; per-column work
-// (band metadata, coefficients, dispatch) is paid once for the NF rows.
+// orientation, whether all NF rows exist), so the column loop is branch free apart from the warp-uniform
+// tap-count dispatch; per-column work (band metadata, coefficients, dispatch) is paid once for the NF rows.
 enum { BAND_NONE = 0, BAND_SMEM = 1, BAND_GLOBAL = 2 };
 
+// BAND_SMEM: the kernel re-packs the group-ELL metadata into ONE 8-byte record per column when it stages the band:
+//   x = first input row of the column's window, y = (taps << 16) | index of its first coefficient
 struct EpiArgs {
-    const int32_t* meta;     // banded matrix in the address space named by the BAND template parameter
-    const float* coef;
-    int n_cols;              // output columns before drop_first
+    const int32_t* meta;     // BAND_GLOBAL: group-ELL metadata in global memory; BAND_SMEM: int2 records in shared memory
+    const float* coef;       // coefficients, same address space
+    int n_out;               // output columns (= n_cols - drop_first)
+    int n_groups;            // ceil(n_cols / 32)
     int drop_first;
     float gain;              // contrast_gain / scale
     float bias;              // -offset / scale
     float eps;
 };
 
-template <int BAND>
-__device__ __forceinline__ float band_ld(const float* p) {
-    return BAND == BAND_GLOBAL ? __ldg(p) : *p;
-}
-template <int BAND>
-__device__ __forceinline__ int band_ldi(const int32_t* p) {
-    return BAND == BAND_GLOBAL ? __ldg(p) : *p;
-}
-
 // K taps of one column for NF rows: the K coefficients are loaded once and reused for every row
 template <int K, int NF, int BAND>
 __device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride, const float* __restrict__ c, float (&a)[NF]) {
     float w[K > 0 ? K : 1];
 #pragma unroll
-    for (int u = 0; u < K; ++u) w[u] = band_ld<BAND>(c + (u << 5));
+    for (int u = 0; u < K; ++u) w[u] = BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float acc = 0.f;
@@ -168,10 +162,20 @@ __device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride
 template <int NF, int BAND>
 __device__ __forceinline__ void band_column(const float* __restrict__ val, int val_stride, const int32_t* __restrict__ meta,
                                             const float* __restrict__ coef, int n_groups, int m, float (&a)[NF]) {
-    const int cnt = band_ldi<BAND>(meta + 2 * (m >> 5));
-    const int base = band_ldi<BAND>(meta + 2 * (m >> 5) + 1);
-    const float* __restrict__ v = val + band_ldi<BAND>(meta + 2 * n_groups + m);
-    const float* __restrict__ c = coef + (base << 5) + (m & 31);
+    int cnt;
+    const float* __restrict__ v;
+    const float* __restrict__ c;
+    if (BAND == BAND_SMEM) {
+        const int2 rec = reinterpret_cast<const int2*>(meta)[m];
+        cnt = (int)((unsigned)rec.y >> 16);
+        v = val + rec.x;
+        c = coef + (rec.y & 0xffff);
+    } else {
+        cnt = __ldg(meta + 2 * (m >> 5));
+        const int base = __ldg(meta + 2 * (m >> 5) + 1);
+        v = val + __ldg(meta + 2 * n_groups + m);
+        c = coef + (base << 5) + (m & 31);
+    }
     switch (cnt) {
         case 0: taps<0, NF, BAND>(v, val_stride, c, a); break;
         case 1: taps<1, NF, BAND>(v, val_stride, c, a); break;
@@ -186,52 +190,68 @@ __device__ __forceinline__ void band_column(const float* __restrict__ val, int v
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float acc = 0.f;
-                for (int u = 0; u < cnt; ++u) acc = fmaf(v[f * val_stride + u], band_ld<BAND>(c + (u << 5)), acc);
+                for (int u = 0; u < cnt; ++u) acc = fmaf(v[f * val_stride + u], BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5], acc);
                 a[f] = acc;
             }
     }
 }
 
-template <int NT, int NF, int CONTRAST, int BAND, bool TRANSPOSED>
+// FULL: all NF rows exist (no row predicates); otherwise rows f >= n_valid are skipped
+template <int NT, int NF, int CONTRAST, int BAND, bool TRANSPOSED, bool FULL>
 __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int val_stride, int tid, const EpiArgs& ep,
                                               float* __restrict__ out0, int row_step, int col_step, int n_valid) {
-    // out0: element (row 0, column drop_first) of the tile; rows are row_step floats apart, columns col_step
+    // out0: element (row 0, first output column) of the tile; rows are row_step floats apart, columns col_step
     // (TRANSPOSED: rows are adjacent, row_step is ignored; otherwise columns are adjacent, col_step is ignored)
-    const int n_groups = (ep.n_cols + 31) >> 5;
-    for (int m = tid; m < ep.n_cols; m += NT) {
+    float* orow[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) orow[f] = out0 + (TRANSPOSED ? f : f * row_step);
+    for (int mo = tid; mo < ep.n_out; mo += NT) {
+        const int m = mo + ep.drop_first;
         float a[NF];
         if (BAND != BAND_NONE) {
-            band_column<NF, BAND>(val, val_stride, ep.meta, ep.coef, n_groups, m, a);
+            band_column<NF, BAND>(val, val_stride, ep.meta, ep.coef, ep.n_groups, m, a);
         } else {
 #pragma unroll
             for (int f = 0; f < NF; ++f) a[f] = val[f * val_stride + m];
         }
-        if (m >= ep.drop_first) {
-            float* __restrict__ o = out0 + (TRANSPOSED ? (m - ep.drop_first) * col_step : (m - ep.drop_first));
+        const int off = TRANSPOSED ? mo * col_step : mo;
 #pragma unroll
-            for (int f = 0; f < NF; ++f)
-                if (f < n_valid)
-                    stg_stream1(o + (TRANSPOSED ? f : f * row_step), fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
+        for (int f = 0; f < NF; ++f)
+            if (FULL || f < n_valid) stg_stream1(orow[f] + off, fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
+    }
+}
+
+// runtime contrast / row count -> compile-time (one dispatch per tile; call sites that know the contrast at compile
+// time pass it as CSEL >= 0 and pay no dispatch)
+template <int NT, int NF, int CSEL, int BAND, bool TRANSPOSED>
+__device__ __forceinline__ void epilogue_dispatch(int contrast, const float* __restrict__ val, int val_stride, int tid,
+                                                  const EpiArgs& ep, float* __restrict__ out0, int row_step, int col_step, int n_valid) {
+#define ACIDS_TILE(C)                                                                                                   \
+    do {                                                                                                                \
+        if (n_valid >= NF) epilogue_tile<NT, NF, C, BAND, TRANSPOSED, true>(val, val_stride, tid, ep, out0, row_step, col_step, NF); \
+        else epilogue_tile<NT, NF, C, BAND, TRANSPOSED, false>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid);       \
+    } while (0)
+    if (CSEL >= 0) {
+        ACIDS_TILE((CSEL >= 0 ? CSEL : 0));
+    } else {
+        switch (contrast) {
+            case ACIDS_CONTRAST_LOG1P: ACIDS_TILE(ACIDS_CONTRAST_LOG1P); break;
+            case ACIDS_CONTRAST_LOG: ACIDS_TILE(ACIDS_CONTRAST_LOG); break;
+            case ACIDS_CONTRAST_LOG10: ACIDS_TILE(ACIDS_CONTRAST_LOG10); break;
+            default: ACIDS_TILE(ACIDS_CONTRAST_NONE); break;
         }
     }
+#undef ACIDS_TILE
 }
 
-// runtime contrast -> compile-time contrast (one dispatch per launch-uniform value; call sites that already know
-// the contrast at compile time call epilogue_tile directly)
-template <int NT, int NF, int BAND, bool TRANSPOSED>
-__device__ __forceinline__ void epilogue_tile_rt(int contrast, const float* __restrict__ val, int val_stride, int tid,
-                                                 const EpiArgs& ep, float* __restrict__ out0, int row_step, int col_step, int n_valid) {
-    switch (contrast) {
-        case ACIDS_CONTRAST_LOG1P: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG1P, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
-        case ACIDS_CONTRAST_LOG: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
-        case ACIDS_CONTRAST_LOG10: epilogue_tile<NT, NF, ACIDS_CONTRAST_LOG10, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
-        default: epilogue_tile<NT, NF, ACIDS_CONTRAST_NONE, BAND, TRANSPOSED>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid); break;
+// stage the banded matrix in shared memory (all threads of the CTA; caller synchronises): one int2 record per
+// column (see EpiArgs) + the coefficients
+__device__ __forceinline__ void stage_band(const EpiParams& ep, int32_t* srec, float* scoef) {
+    const int n_groups = (ep.n_cols + 31) >> 5;
+    for (int m = threadIdx.x; m < ep.n_cols; m += blockDim.x) {
+        const int cnt = __ldg(ep.meta + 2 * (m >> 5)), base = __ldg(ep.meta + 2 * (m >> 5) + 1);
+        reinterpret_cast<int2*>(srec)[m] = make_int2(__ldg(ep.meta + 2 * n_groups + m), (cnt << 16) | ((base << 5) + (m & 31)));
     }
-}
-
-// stage the banded matrix in shared memory (all threads of the CTA; caller synchronises)
-__device__ __forceinline__ void stage_band(const EpiParams& ep, int32_t* smeta, float* scoef) {
-    for (int i = threadIdx.x; i < ep.band_bytes_meta / 4; i += blockDim.x) smeta[i] = __ldg(ep.meta + i);
     for (int i = threadIdx.x; i < ep.band_bytes_coef / 4; i += blockDim.x) scoef[i] = __ldg(ep.coef + i);
 }
 
@@ -242,7 +262,8 @@ __device__ __forceinline__ EpiArgs make_epi_args(const EpiParams& ep, const int3
     EpiArgs a;
     a.meta = meta;
     a.coef = coef;
-    a.n_cols = ep.n_cols;
+    a.n_out = ep.n_cols - ep.drop_first;
+    a.n_groups = (ep.n_cols + 31) >> 5;
     a.drop_first = ep.drop_first;
     const float off = offset ? __ldg(offset) : 0.f;
     const float inv = scale ? 1.0f / __ldg(scale) : 1.0f;
@@ -253,12 +274,13 @@ __device__ __forceinline__ EpiArgs make_epi_args(const EpiParams& ep, const int3
 }
 
 // bytes of shared memory the banded matrix needs, or 0 when it should stay in global memory
-static inline void band_smem_plan(const acids_band& band, int64_t coef_floats, int64_t meta_ints, size_t budget, EpiParams& ep) {
+static inline void band_smem_plan(const acids_band& band, int64_t coef_floats, size_t budget, EpiParams& ep) {
     ep.band_bytes_meta = ep.band_bytes_coef = 0;
     if (!band.meta) return;
-    const size_t need = (size_t)(meta_ints + coef_floats) * 4;
-    if (need <= budget) {
-        ep.band_bytes_meta = (int)(meta_ints * 4);
+    // in shared memory: one 8-byte record per column + the coefficients (indexable with 16 bits, see EpiArgs)
+    const size_t need = (size_t)band.n_out * 8 + (size_t)coef_floats * 4;
+    if (need <= budget && coef_floats < 65536 && band.n_out < 65536) {
+        ep.band_bytes_meta = band.n_out * 8;
         ep.band_bytes_coef = (int)(coef_floats * 4);
     }
 }

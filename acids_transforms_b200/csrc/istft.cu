@@ -11,6 +11,7 @@
 // HBM traffic per frame: (n_fft/2+1)*8 B in, hop*4 B out.
 #include "common.cuh"
 #include "plans.cuh"
+#include <type_traits>
 
 namespace acids {
 
@@ -29,15 +30,12 @@ struct InvParams {
     int ring;               // G + ovc - 1 slots
 };
 
-// Spectrum row -> N windowed time samples, left in v[] in the natural order of the last pass.
-template <class P, int THREADS>
-__device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, const cf* __restrict__ row, bool valid,
-                                              cf* v, cf* s, int g) {
-    constexpr int M = P::M, T = P::T, V = P::V;
+// One spectrum row into registers, in the operand order of the paired first pass (bins k and M - k together).
+template <class P>
+__device__ __forceinline__ void load_spectrum(const FrameFFT<P, true>& fft, const cf* __restrict__ row, bool valid, cf* i1, cf* i2, cf& ex) {
+    constexpr int M = P::M, V = P::V;
     using PR = typename FrameFFT<P, true>::PR;
     constexpr int RP = PR::R, NBP = PR::NB;
-    auto gsync = [&]() { group_sync<T, THREADS>(g); };
-    cf i1[V / 2], i2[V / 2], ex;
     if (valid) {
         const float2* __restrict__ r2 = reinterpret_cast<const float2*>(row);
 #pragma unroll
@@ -62,6 +60,13 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
         for (int i = 0; i < V / 2; ++i) i1[i] = i2[i] = mk(0.f, 0.f);
         ex = mk(0.f, 0.f);
     }
+}
+
+// Spectrum row (already in registers) -> N time samples, left in v[] in the natural order of the last pass.
+template <class P, int THREADS>
+__device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, const cf* i1, const cf* i2, cf ex, cf* v, cf* s, int g) {
+    constexpr int T = P::T;
+    auto gsync = [&]() { group_sync<T, THREADS>(g); };
     fft.pretangle_inv(i1, i2, ex, v);
     fft.template butterflies<0>(v);
     gsync();
@@ -89,7 +94,7 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
 template <class P>
 struct InvCfg {
     static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
-    static constexpr int MINB = P::T <= 32 ? 3 : (P::T <= 256 ? 2 : 1);
+    static constexpr int MINB = P::T <= 32 ? 4 : (P::T <= 256 ? 2 : 1);
     static constexpr int G = THREADS / P::T;
 };
 
@@ -104,33 +109,47 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
     constexpr size_t kExch = ((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15;     // keep the ring 16-byte aligned
     float* ring = reinterpret_cast<float*>(smem_raw + kExch);
-    float* g2 = ring + (size_t)p.ring * N;           // window^2, for the envelope at the clip edges
-    float2* swin = reinterpret_cast<float2*>(g2 + N);  // synthesis window pairs with irfft's 1/N folded in
+    float2* swin = reinterpret_cast<float2*>(ring + (size_t)p.ring * N);   // synthesis window pairs with irfft's 1/N folded in
     float* inv_env = reinterpret_cast<float*>(swin + M);   // 1 / sum_i g^2[r + i hop]: the interior envelope
+    // window^2 for the envelope (N is a power of two: scaling by N undoes the folded 1/N exactly)
+    const float* swf = reinterpret_cast<const float*>(swin);
+    auto g2 = [&](int i) { const float w = swf[i] * (float)N; return w * w; };
 
     FFT fft;
     fft.init(tid);
     const int hop = p.hop;
-    for (int i = threadIdx.x; i < N; i += THREADS) {
-        const float w = __ldg(p.window + i);
-        g2[i] = w * w;
-    }
     for (int n = threadIdx.x; n < M; n += THREADS)
         swin[n] = make_float2(__ldg(p.window + 2 * n) * (1.0f / N), __ldg(p.window + 2 * n + 1) * (1.0f / N));
     __syncthreads();
     const bool aligned = (N % hop) == 0;             // integer overlap: every hop segment sees the same frames
+    const int ov = N / hop;                          // (aligned) frames per hop segment
+    const int h4 = hop >> 2;
+    const unsigned h4_magic = h4 > 0 ? (unsigned)(0xffffffffu / (unsigned)h4) + 1u : 0u;
+    const int out_len = (int)p.out_len;
+    // ring slot arithmetic without modulo: arguments stay within (-ring, 2 ring)
+    auto wrap = [&](int sl) { return sl < 0 ? sl + p.ring : (sl >= p.ring ? sl - p.ring : sl); };
     if (aligned)
         for (int r = threadIdx.x; r < hop; r += THREADS) {
             float e = 0.f;
-            for (int i = N / hop - 1; i >= 0; --i) e += g2[r + i * hop];     // ascending frame order, like col2im
+            for (int i = ov - 1; i >= 0; --i) e += g2(r + i * hop);     // ascending frame order, like col2im
             inv_env[r] = 1.0f / e;
         }
 
-    const int64_t clip = blockIdx.x / p.chunks_per_clip;
-    const int ch = blockIdx.x % p.chunks_per_clip;
+    // Persistent grid: CTA c owns a contiguous run of units (G frames of one clip) of the whole batch, i.e. a sequence
+    // of segments (clip, [ta, tb)).  Only a segment that starts inside a clip recomputes halo frames, and there is at
+    // most one such segment per CTA.
     const int nT = p.n_frames;
-    const int ta = ch * p.chunk_frames;
-    const int tb = min(nT, ta + p.chunk_frames);
+    const int upc = (nT + G - 1) / G;
+    const int64_t total_units = p.B * upc;
+    int64_t u0 = total_units * blockIdx.x / gridDim.x;
+    const int64_t u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+    int64_t clip = u0 / upc;
+    int ua = (int)(u0 - clip * upc);
+    for (; u0 < u1; ++clip, ua = 0) {
+    const int ub = (int)min((int64_t)upc, ua + (u1 - u0));
+    u0 += ub - ua;
+    const int ta = ua * G;
+    const int tb = min(nT, ub * G);
     // padded-sample span owned by this CTA
     const int64_t own_lo = (int64_t)ta * hop;
     const int64_t own_hi = (tb == nT) ? (int64_t)(nT - 1) * hop + N : (int64_t)tb * hop;
@@ -138,15 +157,20 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     int64_t emitted = own_lo;
     const cf* __restrict__ Xc = p.X + clip * (int64_t)nT * P::F;
     float* __restrict__ outc = p.out + clip * p.out_len;
-    __syncthreads();
 
+    // slot of frame tr in the ring (frames take consecutive slots, a segment starts at slot 0); hop segments emitted
+    int base_slot = 0;
+    int q_next = ta;
+    const int q_own_hi = (tb == nT) ? nT - 1 + ov : tb;
+    cf i1[V / 2], i2[V / 2], ex;
+    load_spectrum<P>(fft, Xc + (int64_t)(t_start + g) * P::F, t_start + g < tb, i1, i2, ex);
     for (int tr = t_start; tr < tb; tr += G) {
         const int t = tr + g;
         const bool valid = t < tb;
         cf v[V];
-        inverse_frame<P, THREADS>(fft, Xc + (int64_t)t * P::F, valid, v, s, g);
+        inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
         if (valid) {
-            float2* slot = reinterpret_cast<float2*>(ring + (size_t)(t % p.ring) * N);
+            float2* slot = reinterpret_cast<float2*>(ring + (size_t)wrap(base_slot + g) * N);
 #pragma unroll
             for (int b = 0; b < BL; ++b) {
                 // last-pass outputs sit at n = (tid + T b) + q * Ns: one base, compile-time offsets
@@ -155,70 +179,92 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
 #pragma unroll
                 for (int q = 0; q < RL; ++q) {
                     const float2 w = wv[q * NSL];
-                    dst[q * NSL] = make_float2(v[b * RL + q].x * w.x, v[b * RL + q].y * w.y);
+                    const cf y = cmul2(v[b * RL + q], mk(w.x, w.y));
+                    dst[q * NSL] = make_float2(y.x, y.y);
                 }
             }
         }
+        // the next round's spectrum rows land while this round is gathered
+        if (tr + G < tb) load_spectrum<P>(fft, Xc + (int64_t)(t + G) * P::F, t + G < tb, i1, i2, ex);
         __syncthreads();
         // gather every sample that no later frame can touch
         const int t_done = min(tr + G, tb) - 1;
         const int64_t hi = (t_done == nT - 1) ? own_hi : min(own_hi, (int64_t)(t_done + 1) * hop);
         if (aligned) {
-            // whole hop segments; segment q gets frames [max(0, q - ov + 1), min(nT - 1, q)]
-            const int ov = N / hop;
-            const int q0 = (int)(emitted / hop), q1 = (int)(hi / hop);
+            // whole hop segments; segment q gets frames [max(0, q - ov + 1), min(nT - 1, q)].  All bookkeeping is
+            // incremental (q_next, base_slot): no division or modulo per sample.
+            const int q0 = q_next;
+            const int q1 = (t_done == nT - 1) ? nT - 1 + ov : min(q_own_hi, t_done + 1);
+            if (q1 > q_next) q_next = q1;
             if ((hop & 3) == 0) {
                 // four consecutive samples per thread: 16-byte shared loads and one 16-byte streaming store
-                const int h4 = hop >> 2;
                 const int items = (q1 - q0) * h4;
                 for (int it = threadIdx.x; it < items; it += THREADS) {
-                    const int dq = it / h4;
+                    const int dq = (int)__umulhi((unsigned)it, h4_magic);      // it / h4, exact for it < 2^16
                     const int r = (it - dq * h4) << 2;
                     const int q = q0 + dq;
                     const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
-                    int slot = t_lo % p.ring;
-                    int off = r + (q - t_lo) * hop;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int tt = t_lo; tt <= t_hi; ++tt) {        // ascending frame order, like torch.istft's col2im
-                        const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + off);
-                        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-                        off -= hop;
-                        slot = (slot + 1 == p.ring) ? 0 : slot + 1;
-                    }
+                    int slot = wrap(base_slot + (t_lo - tr));
+                    const float* src = ring + r + (q - t_lo) * hop;
                     float4 y;
                     if (t_hi - t_lo + 1 == ov) {
+                        // interior: ov frames, ascending frame order like torch.istft's col2im; loads issued together
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        auto run = [&](auto ovc_) {
+                            constexpr int OV = decltype(ovc_)::value;
+                            float4 f[OV];
+#pragma unroll
+                            for (int i = 0; i < OV; ++i) {
+                                f[i] = *reinterpret_cast<const float4*>(src + slot * N - i * hop);
+                                slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                            }
+#pragma unroll
+                            for (int i = 0; i < OV; ++i) { acc.x += f[i].x; acc.y += f[i].y; acc.z += f[i].z; acc.w += f[i].w; }
+                        };
+                        if (ov == 4) run(std::integral_constant<int, 4>{});
+                        else if (ov == 2) run(std::integral_constant<int, 2>{});
+                        else if (ov == 8) run(std::integral_constant<int, 8>{});
+                        else
+                            for (int i = 0; i < ov; ++i) {
+                                const float4 f = *reinterpret_cast<const float4*>(src + slot * N - i * hop);
+                                acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                                slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                            }
                         const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
                         y = make_float4(acc.x * e.x, acc.y * e.y, acc.z * e.z, acc.w * e.w);
                     } else {
-                        float4 env = make_float4(0.f, 0.f, 0.f, 0.f);
+                        // clip edges: fewer frames, exact envelope
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = make_float4(0.f, 0.f, 0.f, 0.f);
                         int o2 = r + (q - t_lo) * hop;
                         for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
-                            const float4 w = *reinterpret_cast<const float4*>(g2 + o2);
-                            env.x += w.x; env.y += w.y; env.z += w.z; env.w += w.w;
+                            const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + o2);
+                            acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                            env.x += g2(o2); env.y += g2(o2 + 1); env.z += g2(o2 + 2); env.w += g2(o2 + 3);
+                            slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                         }
                         y = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
                     }
-                    const int64_t n = (int64_t)q * hop + r - p.trim;
-                    if (n >= 0 && n + 3 < p.out_len) {
+                    const int n = q * hop + r - p.trim;
+                    if (n >= 0 && n + 3 < out_len) {
                         asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outc + n), "f"(y.x), "f"(y.y),
                                      "f"(y.z), "f"(y.w) : "memory");
                     } else {
                         const float yy[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (n + j >= 0 && n + j < p.out_len) stg_stream1(outc + n + j, yy[j]);
+                            if (n + j >= 0 && n + j < out_len) stg_stream1(outc + n + j, yy[j]);
                     }
                 }
             } else {
                 for (int q = q0; q < q1; ++q) {
                     const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
-                    const int slot0 = t_lo % p.ring;
+                    const int slot0 = wrap(base_slot + (t_lo - tr));
                     for (int r = threadIdx.x; r < hop; r += THREADS) {
                         float acc = 0.f, env = 0.f;
                         int slot = slot0, off = r + (q - t_lo) * hop;
                         for (int tt = t_lo; tt <= t_hi; ++tt) {
                             acc += ring[slot * N + off];
-                            env += g2[off];
+                            env += g2(off);
                             off -= hop;
                             slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                         }
@@ -235,15 +281,17 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                 float acc = 0.f, env = 0.f;
                 for (int tt = t_lo; tt <= t_hi; ++tt) {
                     const int m = (int)(np - (int64_t)tt * hop);
-                    acc += ring[(size_t)(tt % p.ring) * N + m];
-                    env += g2[m];
+                    acc += ring[(size_t)wrap(base_slot + (tt - tr)) * N + m];
+                    env += g2(m);
                 }
                 const int64_t n = np - p.trim;
                 if (n >= 0 && n < p.out_len) stg_stream1(outc + n, acc / env);
             }
         }
         if (hi > emitted) emitted = hi;
+        base_slot = wrap(base_slot + G);
         __syncthreads();
+    }
     }
 }
 
@@ -275,7 +323,11 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) irfft_fra
         const int64_t r = u * G + g;
         const bool valid = r < p.rows;
         cf v[V];
-        inverse_frame<P, THREADS>(fft, p.X + r * (int64_t)P::F, valid, v, s, g);
+        {
+            cf i1[V / 2], i2[V / 2], ex;
+            load_spectrum<P>(fft, p.X + r * (int64_t)P::F, valid, i1, i2, ex);
+            inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
+        }
         if (valid) {
 #pragma unroll
             for (int b = 0; b < BL; ++b) {
@@ -337,8 +389,8 @@ struct InvLaunch {
     static constexpr int THREADS = InvCfg<P>::THREADS;
     static constexpr int G = InvCfg<P>::G;
     static size_t smem_ola(int ovc, int hop) {
-        // exchange buffers | frame ring | window^2 | window pairs | interior inverse envelope
-        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(G + ovc - 1) * P::N * sizeof(float) + (size_t)P::N * sizeof(float) +
+        // exchange buffers | frame ring | window pairs | interior inverse envelope
+        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(G + ovc - 1) * P::N * sizeof(float) +
                (size_t)P::M * sizeof(float2) + (size_t)hop * sizeof(float);
     }
     static int ola(InvParams p, cudaStream_t st) {
@@ -353,20 +405,22 @@ struct InvLaunch {
             reserved = smem;
         }
         p.ring = G + p.ovc - 1;
-        // chunking: enough CTAs for ~8 waves, chunks no shorter than 8 overlaps, multiples of G
-        int64_t want = 8LL * 2 * num_sms();
-        int cpc = (int)((want + p.B - 1) / (p.B > 0 ? p.B : 1));
-        int max_cpc = p.n_frames / (8 * p.ovc);
-        if (max_cpc < 1) max_cpc = 1;
-        if (cpc > max_cpc) cpc = max_cpc;
-        if (cpc < 1) cpc = 1;
-        int cf_ = (p.n_frames + cpc - 1) / cpc;
-        cf_ = ((cf_ + G - 1) / G) * G;
-        p.chunk_frames = cf_;
-        p.chunks_per_clip = (p.n_frames + cf_ - 1) / cf_;
-        const int64_t grid = p.B * p.chunks_per_clip;
-        if (grid == 0) return ACIDS_OK;
-        ACIDS_REQUIRE(grid < (1LL << 31), ACIDS_EINVAL, "istft_ola: grid too large");
+        static int ctas_per_sm = 0;
+        static size_t occ_smem = 0;
+        if (ctas_per_sm == 0 || occ_smem != smem) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem);
+            ctas_per_sm = nb > 0 ? nb : 1;
+            occ_smem = smem;
+        }
+        // persistent grid over a contiguous partition of all (clip, unit) pairs; a CTA's run should be long compared
+        // with the ovc - 1 halo frames it recomputes at its start
+        const int64_t total_units = p.B * (((int64_t)p.n_frames + G - 1) / G);
+        if (total_units == 0) return ACIDS_OK;
+        int64_t grid = (int64_t)num_sms() * ctas_per_sm;
+        const int64_t min_units = 4 * ((p.ovc + G - 1) / G) + 1;
+        if (grid > total_units / min_units) grid = total_units / min_units;
+        if (grid < 1) grid = 1;
         kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
         ACIDS_CHECK_LAUNCH("istft_ola");
         return ACIDS_OK;
@@ -461,6 +515,7 @@ extern "C" ACIDS_API int acids_istft_ola(const float* X, int64_t B, int64_t n_fr
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t out_len = (int64_t)hop * (n_frames - 1);
+    ACIDS_REQUIRE(out_len + 2 * (int64_t)n_fft < ((int64_t)1 << 31), ACIDS_ENOTSUP, "istft_ola: clips of 2^31 samples or more are not supported");
     if (fits) {
         InvParams p{};
         p.X = reinterpret_cast<const cf*>(X); p.B = B; p.n_frames = (int)n_frames; p.hop = hop; p.window = window;

@@ -13,7 +13,11 @@ using Fwd64    = Plan<64,    2, 4, 8>;
 using Fwd128   = Plan<128,   4, 8, 8>;
 using Fwd256   = Plan<256,   8, 4, 4, 8>;
 using Fwd512   = Plan<512,  16, 4, 8, 8>;
+#if defined(ACIDS_FWD1024_T16)
+using Fwd1024  = Plan<1024, 16, 32, 16>;      // experiment: one exchange, 32 values per thread
+#else
 using Fwd1024  = Plan<1024, 32, 8, 8, 8>;
+#endif
 using Fwd2048  = Plan<2048, 64, 16, 8, 8>;
 using Fwd4096  = Plan<4096, 128, 16, 16, 8>;
 using Fwd8192  = Plan<8192, 256, 8, 8, 8, 8>;

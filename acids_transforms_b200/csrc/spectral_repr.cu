@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
         const int rs = (int)p.out_row_stride;
 #pragma unroll 1
         for (int g0 = 0; g0 < 8 && g0 < n_valid; g0 += 4)
-            epilogue_tile_rt<256, 4, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
-                                                  p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
+            epilogue_dispatch<256, 4, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
+                                                       p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
         __syncthreads();
     }
 }

@@ -34,6 +34,7 @@ static int dispatch_fwd(int variant, int n_fft, const FwdParams& p, cudaStream_t
 static int fill_common(FwdParams& p, const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
                        int n_fft, int hop, int center, int64_t n_frames) {
     ACIDS_REQUIRE(x && window, ACIDS_EINVAL, "stft: NULL input or window");
+    ACIDS_REQUIRE(L < ((int64_t)1 << 31) - 2 * n_fft, ACIDS_ENOTSUP, "stft: clips of 2^31 samples or more are not supported (L=%lld)", (long long)L);
     ACIDS_REQUIRE(B >= 0 && L > 0 && ldx >= L && hop > 0 && n_frames >= 0, ACIDS_EINVAL,
                   "stft: bad sizes B=%lld L=%lld ldx=%lld hop=%d frames=%lld", (long long)B, (long long)L,
                   (long long)ldx, hop, (long long)n_frames);
@@ -60,8 +61,7 @@ int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, floa
     ep.meta = band.meta; ep.coef = band.coef;
     ep.n_cols = band.meta ? band.n_out : n_bins;
     ep.contrast = contrast; ep.eps = eps; ep.drop_first = drop_first;
-    const int64_t meta_ints = band.meta ? (int64_t)band.n_out + 2 * (((int64_t)band.n_out + 31) / 32) : 0;
-    band_smem_plan(band, band.coef_len, meta_ints, smem_budget, ep);
+    band_smem_plan(band, band.coef_len, smem_budget, ep);
     return ACIDS_OK;
 }
 
@@ -85,6 +85,7 @@ extern "C" ACIDS_API int acids_stft_fwd(const float* x, int64_t B, int64_t L, in
     int rc = fill_common(p, x, B, L, ldx, window, n_fft, hop, center, n_frames);
     if (rc) return rc;
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "stft_fwd: NULL output");
+    ACIDS_REQUIRE(n_frames * (n_fft / 2 + 1) < ((int64_t)1 << 30), ACIDS_ENOTSUP, "stft_fwd: more than 2^30 bins per clip");
     p.out = out;
     return dispatch_fwd(VAR_COMPLEX, n_fft, p, static_cast<cudaStream_t>(stream));
 }
@@ -99,6 +100,8 @@ extern "C" ACIDS_API int acids_stft_mag_fwd(const float* x, int64_t B, int64_t L
     rc = fill_epilogue(p.ep, band, n_fft / 2 + 1, contrast, eps, drop_first, kBandSmemBudget);
     if (rc) return rc;
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "stft_mag_fwd: NULL output");
+    ACIDS_REQUIRE(out_row_stride >= 0 && (n_frames + 4) * out_row_stride < ((int64_t)1 << 31), ACIDS_ENOTSUP,
+                  "stft_mag_fwd: more than 2^31 output elements per clip");
     p.offset_ptr = offset; p.scale_ptr = scale;
     p.out = out; p.out_clip_stride = out_clip_stride; p.out_row_stride = out_row_stride; p.out_col_stride = 1;
     p.power = 1.0f;
@@ -116,6 +119,7 @@ extern "C" ACIDS_API int acids_melspec_fwd(const float* x, int64_t B, int64_t L,
     rc = fill_epilogue(p.ep, mel, n_fft / 2 + 1, ACIDS_CONTRAST_NONE, 0.f, 0, kBandSmemBudget);
     if (rc) return rc;
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "melspec_fwd: NULL output");
+    ACIDS_REQUIRE((int64_t)mel.n_out * n_frames < ((int64_t)1 << 31), ACIDS_ENOTSUP, "melspec_fwd: more than 2^31 output elements per clip");
     p.offset_ptr = offset; p.scale_ptr = scale;
     // frequency-major output [B, n_mels, n_frames] like torchaudio (mel.py:70)
     p.out = out; p.out_clip_stride = (int64_t)mel.n_out * n_frames; p.out_row_stride = 1; p.out_col_stride = n_frames;

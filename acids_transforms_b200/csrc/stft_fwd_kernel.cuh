@@ -91,18 +91,19 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
     }
     __syncthreads();
 
-    const int64_t upc = (p.n_frames + G - 1) / G;        // units per clip
+    const int n_frames = (int)p.n_frames;
+    const int upc = (n_frames + G - 1) / G;              // units per clip
     const int64_t total = p.B * upc;
     const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int L = (int)p.L;                              // < 2^31 - 2 n_fft (checked by the host)
 
     // Raw (un-windowed) samples of frame (b, t) in first-pass operand order.  Interior, aligned frames: vector
     // loads straight into registers.  Edge frames (torch.stft center=True, pad_mode="reflect") and unaligned
     // inputs: the group stages the frame in its exchange buffer with scalar loads, then reads its operands.
-    auto fetch = [&](cf* v, int64_t b, int64_t t) {
-        const bool valid = t < p.n_frames;
-        const int64_t s0 = t * p.hop - p.pad;
-        const float* __restrict__ xb = p.x + b * p.ldx;
-        const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0 >= 0 && s0 + N <= p.L;
+    auto fetch = [&](cf* v, const float* __restrict__ xb, int t) {
+        const bool valid = t < n_frames;
+        const int s0 = t * p.hop - p.pad;
+        const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0 >= 0 && s0 + N <= L;
         bool stage = valid && !fast;
         if (T < 32) stage = __any_sync(0xffffffffu, stage);     // frame groups sharing a warp take the same path
         if (!stage) {
@@ -134,10 +135,10 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
             float* sf = reinterpret_cast<float*>(s);
             gsync();   // the group is done reading the exchange buffer
             for (int i = tid; i < N; i += T) {
-                int64_t k = s0 + i;
+                int k = s0 + i;
                 if (k < 0) k = -k;
-                if (k >= p.L) k = 2 * (p.L - 1) - k;
-                k = k < 0 ? 0 : (k >= p.L ? p.L - 1 : k);
+                if (k >= L) k = 2 * (L - 1) - k;
+                k = k < 0 ? 0 : (k >= L ? L - 1 : k);
                 sf[i] = valid ? __ldg(xb + k) : 0.f;
             }
             gsync();
@@ -148,18 +149,24 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
         }
     };
 
-    int64_t b = u0 / upc;                   // clip and unit-in-clip advance incrementally: no division per frame
-    int64_t uc = u0 - b * upc;
+    // clip and unit-in-clip advance incrementally: no division, no 64-bit multiply per frame
+    int64_t b = u0 / upc;
+    int uc = (int)(u0 - b * upc);
+    const float* __restrict__ xclip = p.x + b * p.ldx;                // clip of the NEXT unit (the one being fetched)
+    float* __restrict__ oclip = MODE == MODE_COMPLEX ? p.out + b * ((int64_t)n_frames * P::F * 2) : p.out + b * p.out_clip_stride;
+    const int64_t oclip_step = MODE == MODE_COMPLEX ? (int64_t)n_frames * P::F * 2 : p.out_clip_stride;
     int buf = 0;
     cf v[V];
-    if (u0 < u1) fetch(v, b, uc * G + g);
+    if (u0 < u1) fetch(v, xclip, uc * G + g);
     for (int64_t u = u0; u < u1; ++u) {
-        const int64_t t = uc * G + g;
-        const bool valid = t < p.n_frames;
-        const int64_t cur_b = b, cur_uc = uc;
+        const int t = uc * G + g;
+        const bool valid = t < n_frames;
+        const int cur_uc = uc;
+        float* __restrict__ const cur_out = oclip;
         if (++uc == upc) {
             uc = 0;
-            ++b;
+            xclip += p.ldx;
+            oclip += oclip_step;
         }
 
         // ---- window (first-pass operand order, same adjacency as the loads) ----
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
 
         if (MODE == MODE_COMPLEX) {
             if (valid) {
-                float2* __restrict__ row = reinterpret_cast<float2*>(p.out) + (cur_b * p.n_frames + t) * (int64_t)P::F;
+                float2* __restrict__ row = reinterpret_cast<float2*>(cur_out) + t * P::F;
 #pragma unroll
                 for (int c = 0; c < PR::PC; ++c) {
                     // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                 }
                 if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
-            if (u + 1 < u1) fetch(v, b, uc * G + g);
+            if (u + 1 < u1) fetch(v, xclip, uc * G + g);
         } else {
             float* __restrict__ vbuf = vrows + buf * (G * VSTR);
             float* __restrict__ val = vbuf + g * VSTR;
@@ -244,22 +251,19 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
             }
             if (tid == 0) val[M / 2] = pow_value<PMODE>(ex, p.power);
             // v, o1, o2 are dead: start fetching the next frame's samples, they land during the epilogue
-            if (u + 1 < u1) fetch(v, b, uc * G + g);
+            if (u + 1 < u1) fetch(v, xclip, uc * G + g);
             // One barrier per unit: the rows are complete.  (Writers of this buffer two units from now have passed
             // the next barrier, i.e. every thread has left this epilogue.)
             __syncthreads();
-            const int64_t t0 = cur_uc * G;
-            const int n_valid = (int)min((int64_t)G, p.n_frames - t0);
-            float* out0 = p.out + cur_b * p.out_clip_stride + (TRANSPOSED ? t0 : t0 * p.out_row_stride);
+            const int t0 = cur_uc * G;
+            const int n_valid = min(G, n_frames - t0);
             const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
+            float* out0 = cur_out + (TRANSPOSED ? t0 : t0 * rs);
 #pragma unroll 1
             for (int g0 = 0; g0 < G; g0 += NF) {
                 if (g0 >= n_valid) break;
-                float* o = out0 + (TRANSPOSED ? g0 : g0 * rs);
-                if (CSEL >= 0)
-                    epilogue_tile<THREADS, NF, (CSEL >= 0 ? CSEL : 0), BAND, TRANSPOSED>(vbuf + g0 * VSTR, VSTR, threadIdx.x, ea, o, rs, cs, n_valid - g0);
-                else
-                    epilogue_tile_rt<THREADS, NF, BAND, TRANSPOSED>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea, o, rs, cs, n_valid - g0);
+                epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
+                                                                       out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
             }
             buf ^= 1;
         }

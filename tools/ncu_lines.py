@@ -34,6 +34,6 @@ for kk in [k for k in seen if pat in k]:
     items = [(k, v) for k, v in out.items() if k[0] == kk]
     tot, tots = sum(v[0] for _, v in items), sum(v[1] for _, v in items)
     print(kk[:110], "| inst/unit %.1f | samples %d" % (tot / units, tots))
-    for k, v in sorted(items, key=lambda x: -x[1][0])[:40]:
+    for k, v in sorted(items, key=lambda x: -x[1][0])[:int(__import__("os").environ.get("TOP", "40"))]:
         print("%8.1f inst  %5.1f%% samples  %-16s:%-4d %s" % (v[0] / units, 100.0 * v[1] / max(tots, 1), k[1], k[2], k[3]))
     break
