@@ -90,11 +90,14 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
     }
 }
 
+#ifndef ACIDS_INV_MINB_SMALL
+#define ACIDS_INV_MINB_SMALL 3   // 168 registers: at 4 CTAs / SM (128 registers) the prefetched spectrum spills and costs 30 %
+#endif
 // launch shape per plan (see FwdCfg): small frame groups run 128-thread CTAs
 template <class P>
 struct InvCfg {
     static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
-    static constexpr int MINB = P::T <= 32 ? 4 : (P::T <= 256 ? 2 : 1);
+    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL : (P::T <= 256 ? 2 : 1);
     static constexpr int G = THREADS / P::T;
 };
 
