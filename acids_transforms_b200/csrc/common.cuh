@@ -51,9 +51,15 @@ __device__ __forceinline__ float2 ldg_stream2(const float2* p) {
     return r;
 }
 __device__ __forceinline__ void stg_stream2(float2* p, float x, float y) {
+#ifdef ACIDS_DEBUG_NOSTORE      // tuning experiment only: keep the value alive, skip the store unless it is NaN-tagged
+    if (x != 123456.789f) return;
+#endif
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
 }
 __device__ __forceinline__ void stg_stream1(float* p, float x) {
+#ifdef ACIDS_DEBUG_NOSTORE
+    if (x != 123456.789f) return;
+#endif
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(x) : "memory");
 }
 

@@ -35,6 +35,9 @@ template <class P>
 struct FwdCfg {
     static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
     static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 256 ? 2 : 1);
+    // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
+    // second register set; that needs ~160 registers -> one CTA less per SM for the small plans
+    static constexpr int MINB_COMPLEX = P::T <= 32 ? 3 : MINB;
     static constexpr int G = THREADS / P::T;
     static constexpr int NF = G < 4 ? G : 4;                    // rows per epilogue tile
     static constexpr int VSTR = (P::F + 3) & ~3;                // |X| row stride in shared memory (floats)
@@ -57,7 +60,8 @@ __device__ __forceinline__ float pow_value(cf a, float power) {
 
 // CSEL: contrast known at compile time (ACIDS_CONTRAST_*) or -1 (dispatched once per row tile)
 template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
-__global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? FwdCfg<P>::MINB_COMPLEX : FwdCfg<P>::MINB)
+    stft_fwd_kernel(const FwdParams p) {
     using C = FwdCfg<P>;
     constexpr int THREADS = C::THREADS;
     constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW;
@@ -102,7 +106,12 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
     // inputs: the group stages the frame in its exchange buffer with scalar loads, then reads its operands.
     auto fetch = [&](cf* v, const float* __restrict__ xb, int t) {
         const bool valid = t < n_frames;
+#ifdef ACIDS_DEBUG_NOLOAD       // tuning experiment only: every frame reads the same (cached) samples
+        const int s0 = N;
+        xb = p.x;
+#else
         const int s0 = t * p.hop - p.pad;
+#endif
         const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0 >= 0 && s0 + N <= L;
         bool stage = valid && !fast;
         if (T < 32) stage = __any_sync(0xffffffffu, stage);     // frame groups sharing a warp take the same path
@@ -189,6 +198,11 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
             }
         }
 
+        cf nv[MODE == MODE_COMPLEX ? V : 1];
+        if (MODE == MODE_COMPLEX) {
+            if (u + 1 < u1) fetch(nv, xclip, uc * G + g);       // lands during this frame's FFT
+        }
+
         // ---- passes ----
         fft.template butterflies<0>(v);
         gsync();   // the previous frame's readers of s are done
@@ -233,7 +247,8 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, FwdCfg<P>::MINB) stft_fwd_
                 }
                 if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
-            if (u + 1 < u1) fetch(v, xclip, uc * G + g);
+#pragma unroll
+            for (int i = 0; i < V; ++i) v[i] = nv[MODE == MODE_COMPLEX ? i : 0];
         } else {
             float* __restrict__ vbuf = vrows + buf * (G * VSTR);
             float* __restrict__ val = vbuf + g * VSTR;

@@ -75,7 +75,7 @@ with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
 # the bench kernels are the LARGEST launch of each name
 tj = {}
 for n, v in traffic.items():
-    key = "stft_fwd_kernel<Fwd1024,MODE_REAL>" if ("stft_fwd_kernel" in n and n.rstrip().endswith("1>(FwdParams)")) else \
+    key = "stft_fwd_kernel<Fwd1024,MODE_REAL>" if ("stft_fwd_kernel" in n and ">, 1, " in n) else \
           "istft_ola_kernel<Inv1024>" if "istft_ola_kernel" in n else n
     tj[key] = max(tj.get(key, 0), max(v))
 json.dump(tj, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
