@@ -118,7 +118,10 @@ struct PhaseParams {
 
 __device__ __forceinline__ float unwrap_correction(float d) {
     // utils/misc.py:19-24: ddmod = (d + pi) % 2pi - pi (python remainder); +pi when it lands on -pi going up
-    float r = fmodf(d + ACIDS_PI_F, ACIDS_2PI_F);
+    // d is a difference of two principal values, so x = d + pi lies in [-pi, 3 pi]: the float remainder (exact, like
+    // fmodf) reduces to one conditional subtraction (exact by Sterbenz' lemma), then python's sign fix-up
+    const float x = d + ACIDS_PI_F;
+    float r = x >= ACIDS_2PI_F ? x - ACIDS_2PI_F : x;
     if (r < 0.f) r += ACIDS_2PI_F;
     float dd = r - ACIDS_PI_F;
     if (dd == -ACIDS_PI_F && d > 0.f) dd = ACIDS_PI_F;
@@ -132,7 +135,13 @@ __device__ __forceinline__ float if_weight(int t, int T) {
     return (1.5f * N) / (N * N - 1.f) * (1.f - a * a);
 }
 
+// One thread per (clip, bin) column walks the frames.  The arctangents and unwrap corrections of KB consecutive
+// frames only depend on the raw spectrum: they are loaded and evaluated as a block (memory- and instruction-level
+// parallelism); only the running sum and the differences run serially, in torch.cumsum's order.
+// MODE / METHOD / WEIGHTED are compile-time: no branching per element.
+template <int MODE, int METHOD, bool WEIGHTED>
 __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
+    constexpr int KB = 8;
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= p.B * p.n_bins) return;
     const int64_t b = col / p.n_bins;
@@ -144,46 +153,70 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
     const float inv = p.scale_ptr ? 1.0f / __ldg(p.scale_ptr) : 1.0f;
     const int T = p.n_frames;
     auto emit = [&](int t, float v) {
-        if (p.weighted) v *= if_weight(t, T);
+        if (WEIGHTED) v *= if_weight(t, T);
         if (write) stg_stream1(out + (int64_t)t * p.out_row_stride, (v - off) * inv);
     };
     float prev_raw = 0.f, cum = 0.f;
     float u1 = 0.f, u2 = 0.f;   // unwrapped phase at t-1, t-2
-#pragma unroll 4
-    for (int t = 0; t < T; ++t) {
-        const float2 a = ldg_stream2(X + (int64_t)t * p.n_bins);
-        const float raw = atan2f(a.y, a.x);
-        if (p.mode == ACIDS_PHASE_RAW) {
-            emit(t, raw);
-            continue;
+    for (int t0 = 0; t0 < T; t0 += KB) {
+        float2 a[KB];
+        float rawv[KB], corr[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) a[k] = (t0 + k < T) ? ldg_stream2(X + (int64_t)(t0 + k) * p.n_bins) : make_float2(1.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) rawv[k] = atan2f(a[k].y, a[k].x);
+        if (MODE != ACIDS_PHASE_RAW) {
+#pragma unroll
+            for (int k = 0; k < KB; ++k) corr[k] = unwrap_correction(rawv[k] - (k == 0 ? prev_raw : rawv[k - 1]));
+            prev_raw = rawv[KB - 1];
         }
-        if (t > 0) cum += unwrap_correction(raw - prev_raw);
-        const float un = t > 0 ? raw + cum : raw;
-        prev_raw = raw;
-        if (p.mode == ACIDS_PHASE_UNWRAP) {
-            emit(t, un);
-        } else if (p.method == ACIDS_IF_FORWARD) {
-            // row 0 = phi_0, row t = (phi_t - phi_{t-1}) / 2; rows [:-1] then divided by pi
-            float v = t == 0 ? un : (un - u1) / 2.f;
-            if (t < T - 1) v = v / ACIDS_PI_F;
-            emit(t, v);
-        } else if (p.method == ACIDS_IF_BACKWARD) {
-            // row t = (phi_t - phi_{t+1}) / 2 for t < T-1, row T-1 = phi_{T-1}; rows [1:] divided by -pi
-            if (t > 0) {
-                float v = (u1 - un) / 2.f;
-                if (t - 1 >= 1) v = v / (-ACIDS_PI_F);
-                emit(t - 1, v);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int t = t0 + k;
+            if (t >= T) break;
+            const float raw = rawv[k];
+            if (MODE == ACIDS_PHASE_RAW) {
+                emit(t, raw);
+                continue;
             }
-            if (t == T - 1) emit(t, t >= 1 ? un / (-ACIDS_PI_F) : un);
-        } else {
-            // central: row 0 = phi_0, row t = (phi_{t+1} - phi_{t-1}) / 4 / (2 pi), row T-1 = phi_{T-1}
-            if (t == 0) emit(0, un);
-            if (t >= 2) emit(t - 1, (un - u2) / 4.f / ACIDS_2PI_F);
-            if (t == T - 1 && t > 0) emit(t, un);
+            if (t > 0) cum += corr[k];
+            const float un = t > 0 ? raw + cum : raw;
+            if (MODE == ACIDS_PHASE_UNWRAP) {
+                emit(t, un);
+            } else if (METHOD == ACIDS_IF_FORWARD) {
+                // row 0 = phi_0, row t = (phi_t - phi_{t-1}) / 2; rows [:-1] then divided by pi
+                float v = t == 0 ? un : (un - u1) / 2.f;
+                if (t < T - 1) v = v / ACIDS_PI_F;
+                emit(t, v);
+            } else if (METHOD == ACIDS_IF_BACKWARD) {
+                // row t = (phi_t - phi_{t+1}) / 2 for t < T-1, row T-1 = phi_{T-1}; rows [1:] divided by -pi
+                if (t > 0) {
+                    float v = (u1 - un) / 2.f;
+                    if (t - 1 >= 1) v = v / (-ACIDS_PI_F);
+                    emit(t - 1, v);
+                }
+                if (t == T - 1) emit(t, t >= 1 ? un / (-ACIDS_PI_F) : un);
+            } else {
+                // central: row 0 = phi_0, row t = (phi_{t+1} - phi_{t-1}) / 4 / (2 pi), row T-1 = phi_{T-1}
+                if (t == 0) emit(0, un);
+                if (t >= 2) emit(t - 1, (un - u2) / 4.f / ACIDS_2PI_F);
+                if (t == T - 1 && t > 0) emit(t, un);
+            }
+            u2 = u1;
+            u1 = un;
         }
-        u2 = u1;
-        u1 = un;
     }
+}
+
+typedef void (*PhaseFwdKernel)(const PhaseParams);
+static PhaseFwdKernel pick_phase_kernel(int mode, int method, int weighted) {
+    if (mode == ACIDS_PHASE_RAW) return phase_fwd_kernel<ACIDS_PHASE_RAW, 0, false>;
+    if (mode == ACIDS_PHASE_UNWRAP) return phase_fwd_kernel<ACIDS_PHASE_UNWRAP, 0, false>;
+#define ACIDS_IFK(M) (weighted ? phase_fwd_kernel<ACIDS_PHASE_IF, M, true> : phase_fwd_kernel<ACIDS_PHASE_IF, M, false>)
+    if (method == ACIDS_IF_FORWARD) return ACIDS_IFK(ACIDS_IF_FORWARD);
+    if (method == ACIDS_IF_BACKWARD) return ACIDS_IFK(ACIDS_IF_BACKWARD);
+    return ACIDS_IFK(ACIDS_IF_CENTRAL);
+#undef ACIDS_IFK
 }
 
 struct PhaseInvParams {
@@ -346,7 +379,7 @@ extern "C" ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_fr
     p.offset_ptr = offset; p.scale_ptr = scale; p.drop_first = drop_first; p.out = out;
     p.out_clip_stride = out_clip_stride; p.out_row_stride = out_row_stride;
     const int64_t cols = B * n_bins;
-    phase_fwd_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    pick_phase_kernel(mode, if_method, p.weighted)<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("phase_fwd");
     return ACIDS_OK;
 }

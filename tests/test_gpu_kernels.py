@@ -84,9 +84,11 @@ def test_dgt_golden(ops, name):
 @pytest.mark.parametrize("n_fft,hop,L,B", [(32, 8, 100, 3), (64, 16, 333, 2), (128, 32, 1000, 3), (256, 128, 2049, 2),
                                            (512, 512, 4096, 2), (1024, 256, 20000, 5), (2048, 512, 30001, 3),
                                            (4096, 1024, 40000, 2), (8192, 2048, 50000, 2), (16384, 4096, 70000, 1),
-                                           (1024, 100, 5000, 2), (1024, 128, 9000, 2), (512, 127, 3000, 2), (256, 85, 2001, 3)])
+                                           (1024, 100, 5000, 2), (1024, 128, 9000, 2), (512, 127, 3000, 2), (256, 85, 2001, 3),
+                                           (1024, 256, 20002, 3), (512, 128, 10002, 3), (1024, 256, 176400, 2)])
 def test_stft_istft_oracle(ops, n_fft, hop, L, B):
-    """All supported n_fft (32..16384), odd lengths (scalar load path), odd hops, hop == n_fft."""
+    """All supported n_fft (32..16384), odd lengths and rows that are only 8-byte aligned (staged load path), odd
+    hops, hop == n_fft, and a full 4 s clip (the persistent inverse starts segments inside a clip: halo frames)."""
     x = synth(B, L, n_fft + hop)
     w = O.periodic_window("hann", n_fft)
     Xo = O.stft(x, n_fft, hop, w)
@@ -184,8 +186,10 @@ def test_fused_chain_golden(ops, name, window):
     assert_parity(host(y2), g["y"], REL, name + " unfused")
 
 
-@pytest.mark.parametrize("n_fft,hop", [(512, 128), (2048, 512), (4096, 1024)])
+@pytest.mark.parametrize("n_fft,hop", [(128, 32), (512, 128), (2048, 512), (4096, 1024), (8192, 2048)])
 def test_fused_magnitude_oracle(ops, n_fft, hop):
+    """Small plans (many frames per CTA, several row tiles per unit) up to a bank that does not fit in shared memory
+    (n_fft = 8192: banded matrix read from global memory)."""
     x = synth(3, 6 * n_fft + 17, n_fft)
     w = O.periodic_window("hann", n_fft)
     fwd, _ = O.magnitude_banks(44100, n_fft)

@@ -23,7 +23,8 @@ def timeit(fn, iters=20, warm=3):
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    nums = [a for a in sys.argv[1:] if a.isdigit()]
+    B = int(nums[0]) if nums else 1024
     L, n, h = 176400, 1024, 256
     T, F = 1 + L // h, n // 2 + 1
     x = 0.5 * (2 * torch.rand((B, L), device="cuda") - 1)
@@ -64,6 +65,38 @@ def main():
     if B <= 1024:
         ms = timeit(eager, iters=5)
         res["torch_eager_cuda_chain"] = dict(ms=ms)
+    if "--all" in sys.argv:
+        del X, out
+        torch.cuda.empty_cache()
+        # cfg 3: MFCC = MelSpectrogram(n_fft=2048, hop=512, 128 mels) on 10 s clips (batch reduced to fit the probe)
+        B3, L3, n3, h3 = 512, 441000, 2048, 512
+        T3 = 1 + L3 // h3
+        x3 = 0.5 * (2 * torch.rand((B3, L3), device="cuda") - 1)
+        import torchaudio
+        fb = torchaudio.functional.melscale_fbanks(n3 // 2 + 1, 0.0, 22050.0, 128, 44100)
+        mel = ops.BandedMatrix(fb)
+        hw3 = torch.hann_window(n3).cuda()
+        ms = timeit(lambda: ops.melspec_fwd(x3, hw3, n3, h3, mel, 2.0), iters=10)
+        byt = B3 * (4 * L3 + 4 * 128 * T3)
+        res["cfg3_melspec_2048_128"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK, audio_s_per_s=B3 * 10 / (ms / 1e3))
+        del x3
+        torch.cuda.empty_cache()
+        # cfg 4: stereo clips, STFT(4096, 1024) -> complex; ISTFT back; Phase/IF on the spectrum
+        B4, n4, h4 = 1024, 4096, 1024
+        x4 = 0.5 * (2 * torch.rand((B4, L), device="cuda") - 1)
+        hw4 = torch.hann_window(n4).cuda()
+        T4, F4 = 1 + L // h4, n4 // 2 + 1
+        X4 = ops.stft_fwd(x4, hw4, n4, h4)
+        ms = timeit(lambda: ops.stft_fwd(x4, hw4, n4, h4), iters=10)
+        byt = B4 * (4 * L + 8 * T4 * F4)
+        res["cfg4_stft_4096"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        ms = timeit(lambda: ops.istft_ola(X4, hw4, n4, h4, check_envelope=False), iters=10)
+        byt = B4 * (8 * T4 * F4 + 4 * h4 * (T4 - 1))
+        res["cfg4_istft_4096"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        o4 = torch.empty((B4, T4, F4), device="cuda")
+        ms = timeit(lambda: ops.phase_fwd(X4, 2, "forward", False, 0.0, 1.0, out=o4), iters=10)
+        byt = B4 * 12 * T4 * F4
+        res["cfg4_if_4096"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
     for k, v in res.items():
         print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
 
