@@ -3,9 +3,10 @@ canonical dual as synthesis window (acids_transforms/transforms/dgt.py:24-123, :
 
 The analysis / complex-inverse path is the same pair of kernels as STFT.  Phase-gradient heap
 integration (PGHI, dgt.py:156-236, :338-466) is a sequential priority-queue flood fill that
-SURVEY.md §8 places out of the hot path (row N4, last): it is not implemented in this round and
-inverting a *magnitude* with inversion_mode="pghi" raises NotImplementedError; the other phaseless
-modes (griffin_lim, random, keep_input, sinebank) run on the new kernels.
+SURVEY.md §8 keeps off the GPU hot path (row N4): the phase is reconstructed on the host
+(transforms/pghi.py, numpy + heapq), recombined with the magnitude and inverted by the CUDA kernels.
+Like the reference's, it is eager-only (the reference scripts a TorchScript heap; here scripted modules
+support every other inversion mode and raise for "pghi").
 """
 import math
 from typing import Dict, List, Optional, Union
@@ -16,6 +17,7 @@ from .stft import STFT, RealtimeSTFT, MAX_NFFT, realtime_sinebank
 from .base import AudioTransform
 from ..utils.misc import frame
 from .. import _torch_ops  # noqa: F401
+from . import pghi as _pghi
 
 __all__ = ["DGT", "RealtimeDGT"]
 
@@ -70,15 +72,29 @@ class DGT(STFT):
     def invert_without_phase(self, x: torch.Tensor, inversion_mode: Optional[str] = None) -> torch.Tensor:
         mode = self.inversion_mode if inversion_mode is None else inversion_mode
         if mode == "pghi":
-            raise NotImplementedError("PGHI phase reconstruction (dgt.py:156-236) is outside this round's hot-path scope; "
-                                      "use inversion_mode='griffin_lim', 'random' or 'keep_input'")
+            return self._pghi_istft(x)
         return self._phaseless(x, mode)
+
+    @torch.jit.unused
+    def pghi(self, mag: torch.Tensor, tolerance: float = 1.e-4) -> torch.Tensor:
+        """Phase of one [T, F] magnitude by heap integration (dgt.py:156-162), computed on the host."""
+        return _pghi.pghi(mag, float(self.gamma), self._n_fft, self._hop, float(tolerance), float(self.eps))
+
+    @torch.jit.unused
+    def _pghi_istft(self, x: torch.Tensor) -> torch.Tensor:
+        # dgt.py:136-143: one flood fill per clip, then mag * exp(i phase) -> ISTFT with the dual window
+        tol = float(self.tolerance)
+        if x.dim() == 3:
+            phase = torch.stack([self.pghi(x[n], tol) for n in range(x.size(0))])
+        else:
+            phase = self.pghi(x, tol)
+        return self._istft(torch.ops.acids_b200.polar_to_complex(x.contiguous(), phase.to(x.device)))
 
     def test_inversion(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         outs = {}
         x_dgt = self.forward(x)
         outs["direct"] = self.invert(x_dgt)
-        for mode in ["griffin_lim", "keep_input", "random", "sinebank"]:
+        for mode in ["griffin_lim", "keep_input", "random", "sinebank", "pghi"]:
             outs[mode] = self.invert(x_dgt.abs(), inversion_mode=mode)
         return outs
 
@@ -135,22 +151,51 @@ class RealtimeDGT(DGT):
             return torch.ops.acids_b200.irfft_frames(x, self.inv_window, self._n_fft)       # dgt.py:297-302
         return self.invert_without_phase(x, inversion_mode)
 
+    def _gamma_value(self, n_fft: int) -> float:
+        # dgt.py:373-374: the real-time class overrides gamma with lambda itself (not 2 pi lambda^2)
+        return math.sqrt(-float(n_fft) ** 2 / (8 * math.log(0.01)))
+
     def invert_without_phase(self, x: torch.Tensor, inversion_mode: Optional[str] = None) -> torch.Tensor:
+        """dgt.py:304-327: every mode but "sinebank" also refreshes the two-frame PGHI history."""
         mode = self.inversion_mode if inversion_mode is None else inversion_mode
-        if mode == "pghi":
-            raise NotImplementedError("real-time PGHI (dgt.py:338-466) is outside this round's hot-path scope")
+        if list(x.shape[:-2]) != self._batch:
+            self.reset(list(x.shape[:-2]))
         if mode == "keep_input":
             phase = self._get_phase_buffer(x)
             if phase.size(0) == 0 or phase.shape != x.shape:
                 phase = 2 * math.pi * torch.rand_like(x)
+        elif mode == "pghi":
+            phase = self._rt_pghi(x)
         elif mode == "random":
             phase = 2 * math.pi * torch.rand_like(x)
         elif mode == "sinebank":
             return self._rt_sinebank(x) * self.inv_window[:self._n_fft].to(x.device)
         else:
             raise ValueError("inversion mode %s not valid." % mode)
-        z = torch.ops.acids_b200.polar_to_complex(x, phase.to(x.device))
+        phase = phase.to(x.device)
+        self._update_hgi_buffers(x, phase)
+        z = torch.ops.acids_b200.polar_to_complex(x.contiguous(), phase.contiguous())
         return torch.ops.acids_b200.irfft_frames(z, self.inv_window, self._n_fft)
+
+    @torch.jit.unused
+    def _rt_pghi(self, x: torch.Tensor) -> torch.Tensor:
+        # dgt.py:338-357: the new frames are appended to the two remembered frames, one flood fill per clip
+        n_bins = x.size(-1)
+        flat = x.reshape(-1, x.size(-2), n_bins)
+        hist_mag = self.hgi_mag_buffer.reshape(-1, 2, n_bins)
+        hist_phase = self.hgi_phase_buffer.reshape(-1, n_bins)
+        ph = _pghi.rt_pghi(flat, hist_mag, hist_phase, float(self.gamma), self._n_fft, self._hop, float(self.tolerance),
+                           float(self.eps))
+        return ph.reshape(x.shape)
+
+    def _update_hgi_buffers(self, mag: torch.Tensor, phase: torch.Tensor) -> None:
+        # dgt.py:329-336, on (|x|, angle(x)) of x = mag * exp(i phase): the angle is the phase wrapped to (-pi, pi]
+        if mag.size(-2) > 1:
+            self.hgi_mag_buffer = mag[..., -2:, :].abs()
+        else:
+            self.hgi_mag_buffer = torch.stack([self.hgi_mag_buffer[..., 1, :].to(mag.device), mag[..., -1, :].abs()], -2)
+        last = phase[..., -1, :]
+        self.hgi_phase_buffer = torch.atan2(torch.sin(last), torch.cos(last))
 
     def _rt_sinebank(self, x_fft: torch.Tensor) -> torch.Tensor:
         y, self.random_phase, self.time_index = realtime_sinebank(x_fft, self.random_phase, self.time_index, self._n_fft,
@@ -166,7 +211,7 @@ class RealtimeDGT(DGT):
         self.reset(list(x.shape[:-1]))
         chunk = self._n_fft * 4
         outs = {}
-        for mode in ["direct", "random", "keep_input", "sinebank"]:
+        for mode in ["direct", "random", "keep_input", "sinebank", "pghi"]:
             oadd = OverlapAdd(self._n_fft, self._hop)
             pieces = []
             for part in x.split(chunk, -1):

@@ -111,7 +111,10 @@ class STFT(AudioTransform):
         self.inv_window.zero_()
         self.window[:n_fft] = self._get_window().to(self.window.device)
         self.inv_window[:n_fft] = self._get_dual_window().to(self.window.device)
-        self.gamma.fill_(pghi_gamma(n_fft))
+        self.gamma.fill_(self._gamma_value(n_fft))
+
+    def _gamma_value(self, n_fft: int) -> float:
+        return pghi_gamma(n_fft)
 
     def _get_window(self) -> torch.Tensor:
         return make_window(self.window_name, self._n_fft)

@@ -280,6 +280,16 @@ def main():
          mag_offset=ch[2].magnitude.norm.offset, mag_scale=ch[2].magnitude.norm.scale,
          ph_offset=ch[2].phase.norm.offset, ph_scale=ch[2].phase.norm.scale)
 
+    # ---- PGHI (DGT default inversion mode; dgt.py:156-236): phase of a small magnitude ----------
+    # sinusoid + weak noise so that most bins survive the tolerance and the flood fill has real work
+    g = torch.Generator().manual_seed(105)
+    n = torch.arange(1280, dtype=torch.float64)
+    x = (0.5 * torch.sin(2 * math.pi * 3000.0 * n / SR) + 0.25 * torch.sin(2 * math.pi * 9000.0 * n / SR)).float()[None]
+    x = x + 0.05 * (2 * torch.rand(x.shape, generator=g) - 1)
+    d = T.DGT(n_fft=128, hop_length=32)
+    mag = d(x)[0].abs()
+    save("pghi_128_32", x=x, mag=mag, phase=d.pghi(mag.clone(), 1e-2), gamma=d.gamma, eps=d.eps, y=d.invert(mag.clone()[None]))
+
 
 if __name__ == "__main__":
     main()

@@ -178,9 +178,19 @@ def test_phaseless_inversion(T):
     assert conv < 0.35, "griffin-lim spectral convergence %.3f" % conv
     ys = s2.invert(X.abs(), inversion_mode="sinebank")
     assert ys.shape[0] == 2 and bool(torch.isfinite(ys).all())
+    # PGHI (DGT's default inversion mode): host flood fill + CUDA ISTFT, against the reference's own output
+    g = load_golden("pghi_128_32")
+    d = T.DGT(n_fft=128, hop_length=32).cuda()
+    mag = cu(g["mag"])
+    ph = d.pghi(mag, 1e-2)
+    assert float((ph.cpu() - torch.from_numpy(g["phase"])).abs().max()) < 1e-3      # phases reach hundreds of radians
+    y = d.invert(mag[None])
+    assert_parity(host(y), g["y"], 2e-3, "pghi inverse")        # exp(i phase) of a phase known to ~1e-5 rad
     d = T.DGT().cuda()
-    with pytest.raises(NotImplementedError):
-        d.invert(d(x).abs())                                                # PGHI: out of scope this round
+    X = d(x)
+    yp = d.invert(X.abs())                                                  # default mode, default sizes
+    conv = float(((d(yp).abs() - X[:, :33].abs()).norm() / X.abs().norm()))
+    assert tuple(yp.shape) == (2, 8192) and conv < 0.6, "pghi spectral convergence %.3f" % conv
 
 
 def test_normalize_module(T):

@@ -231,3 +231,21 @@ def test_chains_script():
                T.MidSide() + T.STFT(n_fft=4096, hop_length=1024) + T.PolarIF(magnitude_args={"mode": "bipolar", "n_fft": 4096})):
         sc = torch.jit.script(ch)
         assert {"forward", "invert", "scale_data", "forward_with_time"} <= {m for m in dir(sc)}
+
+
+def test_pghi_matches_reference_golden():
+    """PGHI is host-side glue (transforms/pghi.py): pinned to the reference's DGT.pghi on a small magnitude."""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from acids_transforms_b200.transforms import pghi as P
+    g = load_golden("pghi_128_32")
+    ph = P.pghi(torch.from_numpy(g["mag"]), float(g["gamma"]), 128, 32, 1e-2, float(g["eps"]))
+    ref = torch.from_numpy(g["phase"])
+    assert ph.shape == ref.shape
+    assert float((ph - ref).abs().max()) < 1e-3 and float(((ph != 0) == (ref != 0)).float().mean()) == 1.0
+    # frame-by-frame variant: deterministic given the generator, finite, history rows dropped
+    rng = np.random.default_rng(0)
+    mag = torch.from_numpy(g["mag"])[None, :8]
+    out = P.rt_pghi(mag, torch.zeros(1, 2, 65), torch.zeros(1, 65), 12.0, 128, 32, 1e-2, float(g["eps"]), rng)
+    assert tuple(out.shape) == (1, 8, 65) and bool(torch.isfinite(out).all())
