@@ -182,24 +182,35 @@ __device__ __forceinline__ void band_column(const float* __restrict__ val, int v
         v = val + __ldg(meta + 2 * n_groups + m);
         c = coef + (base << 5) + (m & 31);
     }
-    switch (cnt) {
-        case 0: taps<0, NF, BAND>(v, val_stride, c, a); break;
-        case 1: taps<1, NF, BAND>(v, val_stride, c, a); break;
-        case 2: taps<2, NF, BAND>(v, val_stride, c, a); break;
-        case 3: taps<3, NF, BAND>(v, val_stride, c, a); break;
-        case 4: taps<4, NF, BAND>(v, val_stride, c, a); break;
-        case 5: taps<5, NF, BAND>(v, val_stride, c, a); break;
-        case 6: taps<6, NF, BAND>(v, val_stride, c, a); break;
-        case 7: taps<7, NF, BAND>(v, val_stride, c, a); break;
-        case 8: taps<8, NF, BAND>(v, val_stride, c, a); break;
-        default:
+    // warp-uniform dispatch on the tap count as a shallow compare tree (cheaper than a jump table: no constant-bank
+    // load feeding an indirect branch); the square mel banks use 0..7 taps, most columns 1..4
+#define ACIDS_TAPS(K) taps<K, NF, BAND>(v, val_stride, c, a)
+    if (cnt <= 4) {
+        if (cnt <= 2) {
+            if (cnt == 2) ACIDS_TAPS(2);
+            else if (cnt == 1) ACIDS_TAPS(1);
+            else ACIDS_TAPS(0);
+        } else {
+            if (cnt == 3) ACIDS_TAPS(3);
+            else ACIDS_TAPS(4);
+        }
+    } else if (cnt <= 8) {
+        if (cnt <= 6) {
+            if (cnt == 5) ACIDS_TAPS(5);
+            else ACIDS_TAPS(6);
+        } else {
+            if (cnt == 7) ACIDS_TAPS(7);
+            else ACIDS_TAPS(8);
+        }
+    } else {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                float acc = 0.f;
-                for (int u = 0; u < cnt; ++u) acc = fmaf(v[f * val_stride + u], BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5], acc);
-                a[f] = acc;
-            }
+        for (int f = 0; f < NF; ++f) {
+            float acc = 0.f;
+            for (int u = 0; u < cnt; ++u) acc = fmaf(v[f * val_stride + u], BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5], acc);
+            a[f] = acc;
+        }
     }
+#undef ACIDS_TAPS
 }
 
 // FULL: all NF rows exist (no row predicates); otherwise rows f >= n_valid are skipped

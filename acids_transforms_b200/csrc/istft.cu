@@ -126,8 +126,6 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     __syncthreads();
     const bool aligned = (N % hop) == 0;             // integer overlap: every hop segment sees the same frames
     const int ov = N / hop;                          // (aligned) frames per hop segment
-    const int h4 = hop >> 2;
-    const unsigned h4_magic = h4 > 0 ? (unsigned)(0xffffffffu / (unsigned)h4) + 1u : 0u;
     const int out_len = (int)p.out_len;
     // ring slot arithmetic without modulo: arguments stay within (-ring, 2 ring)
     auto wrap = [&](int sl) { return sl < 0 ? sl + p.ring : (sl >= p.ring ? sl - p.ring : sl); };
@@ -200,62 +198,91 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
             const int q1 = (t_done == nT - 1) ? nT - 1 + ov : min(q_own_hi, t_done + 1);
             if (q1 > q_next) q_next = q1;
             if ((hop & 3) == 0) {
-                // four consecutive samples per thread: 16-byte shared loads and one 16-byte streaming store
-                const int items = (q1 - q0) * h4;
-                for (int it = threadIdx.x; it < items; it += THREADS) {
-                    const int dq = (int)__umulhi((unsigned)it, h4_magic);      // it / h4, exact for it < 2^16
-                    const int r = (it - dq * h4) << 2;
-                    const int q = q0 + dq;
+                // One warp per hop segment: which frames overlap it, where they sit in the ring and whether it is an
+                // interior segment are warp-uniform and computed once; a lane then takes four consecutive samples at a
+                // time (16-byte shared loads, one 16-byte streaming store).
+                constexpr int NW = THREADS / 32;
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                // fewer segments than warps (large n_fft: few frames per round): split every segment into `parts` ranges
+                int lp = 0;                                              // log2(parts)
+                while (((q1 - q0) << (lp + 1)) <= NW && (hop & ((256 << lp) - 1)) == 0) ++lp;
+                const int span = hop >> lp;
+                for (int idx = warp; idx < ((q1 - q0) << lp); idx += NW) {
+                    const int q = q0 + (idx >> lp);
+                    const int part = idx & ((1 << lp) - 1);
+                    const int r_lo = part * span + (lane << 2), r_hi = part * span + span;
                     const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
-                    int slot = wrap(base_slot + (t_lo - tr));
-                    const float* src = ring + r + (q - t_lo) * hop;
-                    float4 y;
+                    const int slot0 = wrap(base_slot + (t_lo - tr));
+                    const int n0 = q * hop - p.trim;
                     if (t_hi - t_lo + 1 == ov) {
                         // interior: ov frames, ascending frame order like torch.istft's col2im; loads issued together
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                         auto run = [&](auto ovc_) {
                             constexpr int OV = decltype(ovc_)::value;
-                            float4 f[OV];
+                            int off[OV];
+                            int slot = slot0;
 #pragma unroll
                             for (int i = 0; i < OV; ++i) {
-                                f[i] = *reinterpret_cast<const float4*>(src + slot * N - i * hop);
+                                off[i] = slot * N + (OV - 1 - i) * hop;
                                 slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                             }
+                            for (int r = r_lo; r < r_hi; r += 128) {
+                                float4 f[OV];
 #pragma unroll
-                            for (int i = 0; i < OV; ++i) { acc.x += f[i].x; acc.y += f[i].y; acc.z += f[i].z; acc.w += f[i].w; }
+                                for (int i = 0; i < OV; ++i) f[i] = *reinterpret_cast<const float4*>(ring + off[i] + r);
+                                const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
+                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int i = 0; i < OV; ++i) { acc.x += f[i].x; acc.y += f[i].y; acc.z += f[i].z; acc.w += f[i].w; }
+                                const int n = n0 + r;
+                                if (n >= 0 && n + 3 < out_len) {
+                                    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outc + n), "f"(acc.x * e.x),
+                                                 "f"(acc.y * e.y), "f"(acc.z * e.z), "f"(acc.w * e.w) : "memory");
+                                } else {
+                                    const float yy[4] = {acc.x * e.x, acc.y * e.y, acc.z * e.z, acc.w * e.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (n + j >= 0 && n + j < out_len) stg_stream1(outc + n + j, yy[j]);
+                                }
+                            }
                         };
                         if (ov == 4) run(std::integral_constant<int, 4>{});
                         else if (ov == 2) run(std::integral_constant<int, 2>{});
                         else if (ov == 8) run(std::integral_constant<int, 8>{});
-                        else
-                            for (int i = 0; i < ov; ++i) {
-                                const float4 f = *reinterpret_cast<const float4*>(src + slot * N - i * hop);
-                                acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-                                slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                        else if (ov == 1) run(std::integral_constant<int, 1>{});
+                        else if (ov == 16) run(std::integral_constant<int, 16>{});
+                        else {
+                            for (int r = r_lo; r < r_hi; r += 128) {
+                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                                int slot = slot0;
+                                for (int i = 0; i < ov; ++i) {
+                                    const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + (ov - 1 - i) * hop + r);
+                                    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                                    slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                                }
+                                const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
+                                const float yy[4] = {acc.x * e.x, acc.y * e.y, acc.z * e.z, acc.w * e.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (n0 + r + j >= 0 && n0 + r + j < out_len) stg_stream1(outc + n0 + r + j, yy[j]);
                             }
-                        const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
-                        y = make_float4(acc.x * e.x, acc.y * e.y, acc.z * e.z, acc.w * e.w);
+                        }
                     } else {
                         // clip edges: fewer frames, exact envelope
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = make_float4(0.f, 0.f, 0.f, 0.f);
-                        int o2 = r + (q - t_lo) * hop;
-                        for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
-                            const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + o2);
-                            acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
-                            env.x += g2(o2); env.y += g2(o2 + 1); env.z += g2(o2 + 2); env.w += g2(o2 + 3);
-                            slot = (slot + 1 == p.ring) ? 0 : slot + 1;
-                        }
-                        y = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
-                    }
-                    const int n = q * hop + r - p.trim;
-                    if (n >= 0 && n + 3 < out_len) {
-                        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outc + n), "f"(y.x), "f"(y.y),
-                                     "f"(y.z), "f"(y.w) : "memory");
-                    } else {
-                        const float yy[4] = {y.x, y.y, y.z, y.w};
+                        for (int r = r_lo; r < r_hi; r += 128) {
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = make_float4(0.f, 0.f, 0.f, 0.f);
+                            int slot = slot0;
+                            int o2 = r + (q - t_lo) * hop;
+                            for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
+                                const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + o2);
+                                acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+                                env.x += g2(o2); env.y += g2(o2 + 1); env.z += g2(o2 + 2); env.w += g2(o2 + 3);
+                                slot = (slot + 1 == p.ring) ? 0 : slot + 1;
+                            }
+                            const float yy[4] = {acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (n + j >= 0 && n + j < out_len) stg_stream1(outc + n + j, yy[j]);
+                            for (int j = 0; j < 4; ++j)
+                                if (n0 + r + j >= 0 && n0 + r + j < out_len) stg_stream1(outc + n0 + r + j, yy[j]);
+                        }
                     }
                 }
             } else {
