@@ -208,10 +208,20 @@ __global__ void midside_kernel(const float* __restrict__ x, int64_t B, int64_t L
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) group_max_kernel(const float* __restrict__ mel, int64_t per_group,
                                                         float* __restrict__ gmax) {
-    // one block per group; max of the mel power (log10 is monotone, so the dB max follows from it)
-    const float* src = mel + (int64_t)blockIdx.x * per_group;
-    float m = -FLT_MAX;
-    for (int64_t i = threadIdx.x; i < per_group; i += blockDim.x) m = fmaxf(m, __ldg(src + i));
+    // grid = (chunks, groups): every CTA reduces a strided share of its group and merges with one atomic.  Only
+    // max(x, 0) matters (the dB conversion clamps at 1e-10 anyway), and for non-negative floats the integer order of
+    // the bit patterns is the float order: an integer atomicMax on a zero-initialised word is exact.
+    // (log10 is monotone, so the dB max follows from the max of the mel power.)
+    const float* src = mel + (int64_t)blockIdx.y * per_group;
+    float m = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (per_group & ~(int64_t)3) : 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int64_t i = n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_group; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, __ldg(src + i));
     __shared__ float sh[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(256) group_max_kernel(const float* __restrict_
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) m = fmaxf(m, sh[i]);
-        gmax[blockIdx.x] = m;
+        atomicMax(reinterpret_cast<int*>(gmax + blockIdx.y), __float_as_int(m));
     }
 }
 
@@ -259,6 +269,71 @@ __global__ void __launch_bounds__(256) mfcc_dct_kernel(const float* __restrict__
             float acc = 0.f;
             for (int m = 0; m < n_mels; ++m) acc = fmaf(db[m * 33 + tx], dm[m * n_mfcc + k], acc);
             if (t < n_frames) out[(b * n_mfcc + k) * n_frames + t] = acc;
+        }
+    }
+}
+
+// Register-tiled variant for n_mfcc <= 64: a CTA takes 64 frames; thread (lane, warp) owns frames lane and lane + 32
+// and the CPT consecutive coefficients warp * CPT ... : per mel band 2 conflict-free loads of the dB tile, CPT broadcast
+// loads of the DCT row and 2 CPT FMAs.  dB tile [n_mels][65], DCT matrix [n_mels][8 CPT] (zero padded) in shared memory.
+template <int CPT>
+__global__ void __launch_bounds__(256) mfcc_dct_tiled_kernel(const float* __restrict__ mel, int64_t B, int n_mels,
+                                                             int64_t n_frames, const float* __restrict__ dct, int n_mfcc,
+                                                             float top_db, const float* __restrict__ gmax,
+                                                             int64_t clips_per_group, float* __restrict__ out) {
+    extern __shared__ float smem[];
+    constexpr int KP = 8 * CPT;
+    float* db = smem;                         // [n_mels][65]
+    float* dm = smem + (size_t)n_mels * 65;   // [n_mels][KP]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < n_mels * KP; i += 256) {
+        const int m = i / KP, k = i - m * KP;
+        dm[i] = k < n_mfcc ? __ldg(dct + (size_t)m * n_mfcc + k) : 0.f;
+    }
+    const int64_t tiles_per_clip = (n_frames + 63) / 64;
+    for (int64_t tile = blockIdx.x; tile < B * tiles_per_clip; tile += gridDim.x) {
+        const int64_t b = tile / tiles_per_clip;
+        const int64_t t0 = (tile - b * tiles_per_clip) * 64;
+        float floor_db = -FLT_MAX;
+        if (top_db >= 0.f) {
+            const float gm = __ldg(gmax + b / clips_per_group);
+            floor_db = 10.0f * log10f(fmaxf(gm, 1e-10f)) - top_db;
+        }
+        __syncthreads();
+        const float* src = mel + b * (int64_t)n_mels * n_frames;
+        for (int i = threadIdx.x; i < n_mels * 64; i += 256) {
+            const int m = i >> 6, c = i & 63;
+            const int64_t t = t0 + c;
+            float v = 0.f;
+            if (t < n_frames) {
+                v = 10.0f * log10f(fmaxf(__ldg(src + (int64_t)m * n_frames + t), 1e-10f));   // functional.py:390-391 (db_multiplier = 0)
+                v = fmaxf(v, floor_db);
+            }
+            db[m * 65 + c] = v;
+        }
+        __syncthreads();
+        float a0[CPT], a1[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) a0[j] = a1[j] = 0.f;
+        const float* dr = dm + ty * CPT;
+#pragma unroll 4
+        for (int m = 0; m < n_mels; ++m) {
+            const float x0 = db[m * 65 + tx], x1 = db[m * 65 + tx + 32];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const float w = dr[m * KP + j];
+                a0[j] = fmaf(x0, w, a0[j]);
+                a1[j] = fmaf(x1, w, a1[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int k = ty * CPT + j;
+            if (k < n_mfcc) {
+                float* o = out + (b * n_mfcc + k) * n_frames + t0;
+                if (t0 + tx < n_frames) o[tx] = a0[j];
+                if (t0 + tx + 32 < n_frames) o[tx + 32] = a1[j];
+            }
         }
     }
 }
@@ -357,8 +432,45 @@ extern "C" ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels,
     if (B == 0) return ACIDS_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (top_db >= 0.f) {
-        group_max_kernel<<<(unsigned)(B / clips_per_group), 256, 0, st>>>(mel, clips_per_group * n_mels * n_frames, group_max);
+        const int64_t groups = B / clips_per_group, per_group = clips_per_group * n_mels * n_frames;
+        ACIDS_REQUIRE(groups < 65536, ACIDS_EINVAL, "mfcc_dct: more than 65535 top_db groups");
+        if (cudaMemsetAsync(group_max, 0, (size_t)groups * sizeof(float), st) != cudaSuccess) {
+            set_error("mfcc_dct: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return ACIDS_ECUDA;
+        }
+        // enough CTAs to stream the whole tensor at HBM speed, split over the groups
+        int64_t chunks = (per_group + 256 * 16 - 1) / (256 * 16);
+        const int64_t cap = ((int64_t)num_sms() * 8 + groups - 1) / groups;
+        if (chunks > cap) chunks = cap;
+        if (chunks < 1) chunks = 1;
+        group_max_kernel<<<dim3((unsigned)chunks, (unsigned)groups), 256, 0, st>>>(mel, per_group, group_max);
         ACIDS_CHECK_LAUNCH("mfcc group max");
+    }
+    const int64_t gsize = clips_per_group > 0 ? clips_per_group : 1;
+    if (n_mfcc <= 64) {
+        const int cpt = (n_mfcc + 7) / 8;
+        const size_t tsmem = ((size_t)n_mels * 65 + (size_t)n_mels * 8 * cpt) * sizeof(float);
+        if (tsmem <= 200 * 1024) {
+            void (*kern)(const float*, int64_t, int, int64_t, const float*, int, float, const float*, int64_t, float*) = nullptr;
+            switch (cpt) {
+                case 1: kern = mfcc_dct_tiled_kernel<1>; break;
+                case 2: kern = mfcc_dct_tiled_kernel<2>; break;
+                case 3: kern = mfcc_dct_tiled_kernel<3>; break;
+                case 4: kern = mfcc_dct_tiled_kernel<4>; break;
+                case 5: kern = mfcc_dct_tiled_kernel<5>; break;
+                case 6: kern = mfcc_dct_tiled_kernel<6>; break;
+                case 7: kern = mfcc_dct_tiled_kernel<7>; break;
+                default: kern = mfcc_dct_tiled_kernel<8>; break;
+            }
+            ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsmem > 48 * 1024 ? tsmem : 48 * 1024)) == cudaSuccess,
+                          ACIDS_ECUDA, "mfcc_dct: cannot reserve %zu B of shared memory", tsmem);
+            int64_t tgrid = B * ((n_frames + 63) / 64);
+            const int64_t tcap = (int64_t)num_sms() * (tsmem <= 56 * 1024 ? 4 : (tsmem <= 112 * 1024 ? 2 : 1));
+            if (tgrid > tcap) tgrid = tcap;
+            kern<<<(unsigned)tgrid, 256, tsmem, st>>>(mel, B, n_mels, n_frames, dct, n_mfcc, top_db, group_max, gsize, out);
+            ACIDS_CHECK_LAUNCH("mfcc_dct");
+            return ACIDS_OK;
+        }
     }
     const size_t smem = ((size_t)n_mels * 33 + (size_t)n_mels * n_mfcc) * sizeof(float);
     ACIDS_REQUIRE(smem <= 227 * 1024, ACIDS_ENOTSUP, "mfcc_dct: n_mels * (33 + n_mfcc) floats exceed shared memory");
