@@ -37,9 +37,14 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
         const int64_t r = r0 + warp;
         if (r < p.rows) {
             const float2* __restrict__ row = p.X + r * p.n_bins;
-            for (int k = lane; k < p.n_bins; k += 32) {
-                const float2 a = ldg_stream2(row + k);
-                val[warp * stride + k] = fast_sqrt(a.x * a.x + a.y * a.y);
+            // 8 independent loads in flight per lane before the first use (the row is streamed once)
+            for (int k0 = lane; k0 < p.n_bins; k0 += 32 * 8) {
+                float2 a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (k0 + 32 * j < p.n_bins) val[warp * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
             }
         }
         __syncthreads();
@@ -60,8 +65,7 @@ struct MagInvParams {
     int n_in;
     int64_t y_row_stride;
     int pad_last;
-    const int32_t* meta;
-    const float* coef;
+    EpiParams ep;            // the inverse band (ep.n_cols = n_out), contrast unused
     int n_out;
     int contrast;
     float eps;
@@ -70,30 +74,47 @@ struct MagInvParams {
     float* out;
 };
 
+// 8 rows per CTA iteration: each warp de-normalises and inverts the contrast of one row into shared memory, then the
+// CTA applies the banded inverse matrix to the rows together with the forward kernels' row-tile epilogue (tiles of 4,
+// identity contrast and normalisation): per-column metadata and coefficients are fetched once per 4 rows.
+template <int BAND>
 __global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_val = p.n_in + p.pad_last;
-    float* val = smem + (size_t)warp * n_val;
+    const int stride = (n_val + 3) & ~3;
+    float* val = reinterpret_cast<float*>(smem_raw);
+    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)8 * stride * sizeof(float));
+    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)8 * stride * sizeof(float) + p.ep.band_bytes_meta);
+    if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
+    EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef, nullptr, nullptr);
     const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
     const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
-    const int64_t wpg = (int64_t)gridDim.x * 8;
-    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < p.rows; r += wpg) {
-        const float* __restrict__ row = p.y + r * p.y_row_stride;
-        __syncwarp();
-        for (int k = lane; k < n_val; k += 32) {
-            // the zero pad is appended BEFORE the contrast inversion (spectral_repr.py:230-234)
-            const float a = k < p.n_in ? __ldg(row + k) * sc + off : 0.f;
-            val[k] = invert_contrast(a, p.contrast, p.eps);
+    __syncthreads();
+    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < p.rows; r0 += (int64_t)gridDim.x * 8) {
+        const int64_t r = r0 + warp;
+        if (r < p.rows) {
+            const float* __restrict__ row = p.y + r * p.y_row_stride;
+            // 8 independent loads in flight per lane before the first use
+            for (int k0 = lane; k0 < n_val; k0 += 32 * 8) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = (k0 + 32 * j < p.n_in) ? __ldg(row + k0 + 32 * j) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = k0 + 32 * j;
+                    // the zero pad is appended BEFORE the contrast inversion (spectral_repr.py:230-234)
+                    if (k < n_val) val[warp * stride + k] = invert_contrast(k < p.n_in ? a[j] * sc + off : 0.f, p.contrast, p.eps);
+                }
+            }
         }
-        __syncwarp();
-        float* __restrict__ out = p.out + r * (int64_t)p.n_out;
-        for (int m = lane; m < p.n_out; m += 32) {
-            float a[1];
-            if (p.meta) band_column<1, BAND_GLOBAL>(val, 0, p.meta, p.coef, (p.n_out + 31) >> 5, m, a);
-            else a[0] = val[m];
-            stg_stream1(out + m, a[0]);
-        }
+        __syncthreads();
+        const int n_valid = (int)min((int64_t)8, p.rows - r0);
+#pragma unroll 1
+        for (int g0 = 0; g0 < 8 && g0 < n_valid; g0 += 4)
+            epilogue_dispatch<256, 4, ACIDS_CONTRAST_NONE, BAND, false>(0, val + g0 * stride, stride, threadIdx.x, ea,
+                                                                        p.out + (r0 + g0) * (int64_t)p.n_out, p.n_out, 1, n_valid - g0);
+        __syncthreads();
     }
 }
 
@@ -345,20 +366,21 @@ extern "C" ACIDS_API int acids_mag_invert(const float* y, int64_t rows, int n_in
     if (rows == 0) return ACIDS_OK;
     MagInvParams p{};
     p.y = y; p.rows = rows; p.n_in = n_in; p.y_row_stride = y_row_stride; p.pad_last = pad_last;
-    p.meta = inverse_band.meta; p.coef = inverse_band.coef;
-    p.n_out = inverse_band.meta ? inverse_band.n_out : n_in + pad_last;
+    rc = fill_epilogue(p.ep, inverse_band, n_in + pad_last, ACIDS_CONTRAST_NONE, eps, 0, 48 * 1024);
+    if (rc) return rc;
+    p.n_out = p.ep.n_cols;
     p.contrast = contrast; p.eps = eps; p.offset_ptr = offset; p.scale_ptr = scale; p.out = out;
-    const size_t smem = (size_t)8 * (n_in + pad_last) * sizeof(float);
-    static size_t reserved = 48 * 1024;
-    if (smem > reserved) {
-        ACIDS_REQUIRE(cudaFuncSetAttribute(mag_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
-                      ACIDS_ECUDA, "mag_invert: cannot reserve %zu B of shared memory", smem);
-        reserved = smem;
-    }
+    const size_t rows_bytes = (size_t)8 * ((n_in + pad_last + 3) & ~3) * sizeof(float);
+    const size_t smem = rows_bytes + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
+    ACIDS_REQUIRE(smem <= 227 * 1024, ACIDS_ENOTSUP, "mag_invert: %d bins exceed shared memory", n_in);
+    auto kern = !inverse_band.meta ? mag_invert_kernel<BAND_NONE>
+                                   : (p.ep.band_bytes_meta > 0 ? mag_invert_kernel<BAND_SMEM> : mag_invert_kernel<BAND_GLOBAL>);
+    ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
+                  ACIDS_ECUDA, "mag_invert: cannot reserve %zu B of shared memory", smem);
     int64_t grid = (rows + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
-    mag_invert_kernel<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("mag_invert");
     return ACIDS_OK;
 }
