@@ -33,6 +33,7 @@ _SCHEMAS = {
                  "Tensor? mag_scale, int phase_mode, int method, bool weighted, Tensor? ph_offset, Tensor? ph_scale, "
                  "bool drop_first) -> Tensor",
     "polar_to_complex": "(Tensor mag, Tensor phase) -> Tensor",
+    "griffinlim_update": "(Tensor rebuilt, Tensor tprev, Tensor mag, float momentum) -> Tensor",
     "istft_ola": "(Tensor X, Tensor window, int n_fft, int hop) -> Tensor",
     "irfft_frames": "(Tensor X, Tensor window, int n_fft) -> Tensor",
     "ola_stream": "(Tensor frames, int hop, int keep, Tensor? carry_in, float gain) -> (Tensor, Tensor)",
@@ -107,6 +108,10 @@ def _polar_fwd(X, band_meta, band_coef, contrast: int, eps: float, mag_offset, m
 
 def _polar_to_complex(mag, phase):
     return ops.polar_to_complex(mag, phase)
+
+
+def _griffinlim_update(rebuilt, tprev, mag, momentum: float):
+    return ops.griffinlim_update(rebuilt, tprev, mag, momentum)
 
 
 def _istft_ola(X, window, n_fft: int, hop: int):

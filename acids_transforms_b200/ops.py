@@ -399,6 +399,28 @@ def polar_to_complex(mag, phase):
     return _ret(out, mag)
 
 
+def griffinlim_update(rebuilt, tprev, mag, momentum: float, out: Optional[torch.Tensor] = None):
+    """One fast-Griffin-Lim update: a = rebuilt - momentum/(1+momentum) * tprev; mag * a / (|a| + 1e-16).
+    complex64 in / out (torchaudio functional.py:336-350 as one kernel)."""
+    lib = _lib.load()
+    rd = _as_complex64(_dev(rebuilt)).resolve_conj().contiguous()
+    td = _as_complex64(_dev(tprev)).resolve_conj().contiguous()
+    md = _dev(mag).to(torch.float32).contiguous()
+    if rd.shape != td.shape or rd.shape != md.shape:
+        raise RuntimeError("griffinlim_update: rebuilt %s, tprev %s and mag %s must have the same shape" %
+                           (tuple(rd.shape), tuple(td.shape), tuple(md.shape)))
+    n = rd.numel()
+    if n & 1:        # odd bin count (n_fft/2+1 bins x odd frames x odd batch): process a padded flat copy
+        pad = lambda t: torch.cat([t.reshape(-1), t.new_zeros(1)])
+        return griffinlim_update(pad(rd), pad(td), pad(md), momentum)[:n].reshape(rd.shape)
+    if out is None:
+        out = torch.empty(rd.shape, dtype=torch.complex64, device=rd.device)
+    with torch.cuda.device(rd.device):
+        _run(out, lib.acids_griffinlim_update, _ptr(rd), _ptr(td), _ptr(md), ctypes.c_float(momentum), n, _ptr(out),
+             _stream(rd.device))
+    return _ret(out, rebuilt)
+
+
 # ------------------------------------------------------------------------------------------------
 # (4) inverse
 # ------------------------------------------------------------------------------------------------

@@ -202,19 +202,18 @@ class STFT(AudioTransform):
     def griffin_lim(self, mag: torch.Tensor, n_iter: int = 30, momentum: float = 0.99) -> torch.Tensor:
         """Fast Griffin-Lim (torchaudio griffinlim, functional.py:297-353, as called at stft.py:174-178:
         power 1, 30 iterations, momentum 0.99, random init) on the new ISTFT / STFT kernels."""
-        mom = momentum / (1 + momentum)
-        angles = torch.ops.acids_b200.polar_to_complex(torch.ones_like(mag), 2 * math.pi * torch.rand_like(mag))
-        tprev = torch.zeros_like(angles)
+        x = torch.ops.acids_b200.polar_to_complex(mag, 2 * math.pi * torch.rand_like(mag))     # mag * exp(i random phase)
+        tprev = torch.zeros_like(x)
         for _ in range(n_iter):
-            wave = self._istft(mag * angles)
+            wave = self._istft(x)
             rebuilt = torch.ops.acids_b200.stft_fwd(wave, self.inv_window, self._n_fft, self._hop, True)
             # the trimmed ISTFT output is one hop shorter than the frames it came from
             if rebuilt.size(-2) < mag.size(-2):
                 rebuilt = torch.nn.functional.pad(rebuilt, [0, 0, 0, mag.size(-2) - rebuilt.size(-2)])
-            angles = rebuilt - tprev * mom
-            angles = angles / (angles.abs() + 1e-16)
+            # angles = rebuilt - mom * tprev; x = mag * angles / (|angles| + 1e-16): one kernel
+            x = torch.ops.acids_b200.griffinlim_update(rebuilt, tprev, mag, momentum)
             tprev = rebuilt
-        return self._istft(mag * angles)
+        return self._istft(x)
 
     def get_sinebank_inversion(self, x_fft: torch.Tensor) -> torch.Tensor:
         """Additive resynthesis with one sinusoid per bin (stft.py:180-191); plain torch glue, off the hot path."""

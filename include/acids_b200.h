@@ -151,6 +151,13 @@ ACIDS_API int acids_phase_inv(const float* y, int64_t B, int64_t n_frames, int n
 /* SpectralRepresentation.invert tail, spectral_repr.py:452: out = mag * exp(i phase).          */
 ACIDS_API int acids_polar_to_complex(const float* mag, const float* phase, int64_t n, float* out, void* stream);
 
+/* One fast-Griffin-Lim update (STFT.griffin_lim, stft.py:174-178 -> torchaudio functional.py:336-350):
+ *   a = rebuilt - momentum / (1 + momentum) * tprev;   out = mag * a / (|a| + 1e-16)
+ * rebuilt, tprev, out: complex64 [n] (16-byte aligned), mag float32 [n], n even.  The caller keeps `rebuilt` as the
+ * next call's `tprev`.                                                                         */
+ACIDS_API int acids_griffinlim_update(const float* rebuilt, const float* tprev, const float* mag, float momentum,
+                            int64_t n, float* out, void* stream);
+
 /* ---- (4) inverse rFFT + synthesis window + overlap-add + envelope normalisation -------------
  * Replaces torch.istft at stft.py:126-127 / dgt.py:92 (centre=1: output trimmed by n_fft/2 on both
  * sides, length hop*(n_frames-1)), atomic-free: each CTA owns a span of output samples.

@@ -277,6 +277,19 @@ def test_polar_golden(ops):
 # ---------------------------------------------------------------------------------------------
 # MFCC (= MelSpectrogram) and the DCT variant
 # ---------------------------------------------------------------------------------------------
+def test_griffinlim_update(ops):
+    """The fused fast-Griffin-Lim update against the eager formula (torchaudio functional.py:336-350)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape in [(3, 33, 513), (1, 7, 17)]:          # even and odd bin counts
+        reb = torch.randn(shape, generator=g, device="cuda", dtype=torch.complex64)
+        tpr = torch.randn(shape, generator=g, device="cuda", dtype=torch.complex64)
+        mag = torch.rand(shape, generator=g, device="cuda")
+        a = reb - tpr * (0.99 / 1.99)
+        want = mag * (a / (a.abs() + 1e-16))
+        got = ops.griffinlim_update(reb, tpr, mag, 0.99)
+        assert_parity(host(torch.view_as_real(got)), host(torch.view_as_real(want)), 1e-5, "griffin-lim update %s" % (shape,))
+
+
 def test_mfcc_golden(ops):
     g = load_golden("mfcc")
     fb = dense(g["fb_rows"], g["fb_cols"], g["fb_vals"], g["fb_shape"])

@@ -45,6 +45,15 @@ def main():
     res["cfg4_forward_chain"] = dict(ms=ms, audio_s_per_s=B4 * 4 / (ms / 1e3), out_shape=list(y.shape))
     ms = timeit(lambda: ch.invert(y))
     res["cfg4_inverse_chain"] = dict(ms=ms, audio_s_per_s=B4 * 4 / (ms / 1e3))
+    del x4, y
+    torch.cuda.empty_cache()
+    # Griffin-Lim (the STFT default inversion mode): 30 iterations of ISTFT + STFT + one update kernel
+    Bg = 256
+    xg = 0.5 * (2 * torch.rand((Bg, 176400), device="cuda") - 1)
+    st = Tr.STFT(n_fft=1024, hop_length=256).cuda()
+    mag = st(xg).abs()
+    ms = timeit(lambda: st.invert(mag), iters=3, warm=1)
+    res["griffin_lim_256x4s"] = dict(ms=ms, audio_s_per_s=Bg * 4 / (ms / 1e3))
     for k, v in res.items():
         print(k, json.dumps(v))
 
