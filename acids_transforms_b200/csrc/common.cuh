@@ -13,6 +13,20 @@ void set_error(const char* fmt, ...);           // capi.cu (thread-local message
 int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, float eps, int drop_first, size_t smem_budget);  // stft_fwd.cu
 int num_sms();                                  // cached cudaDevAttrMultiProcessorCount
 
+// Function attributes (opt-in shared memory) and occupancy are per DEVICE: launch sites cache them per device ordinal
+// (one process may drive several GPUs).  Races between host threads are benign: the cached values are idempotent.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    size_t reserved = 0;     // dynamic shared memory the kernel has been opted in to
+    int ctas_per_sm = 0;     // occupancy at occ_smem bytes
+    size_t occ_smem = 0;
+};
+static inline PerDevice& per_device(PerDevice (&tab)[kMaxDevices]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    return tab[(d >= 0 && d < kMaxDevices) ? d : 0];
+}
+
 #define ACIDS_REQUIRE(cond, code, ...)   \
     do {                                 \
         if (!(cond)) {                   \

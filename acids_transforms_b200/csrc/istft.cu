@@ -426,7 +426,9 @@ struct InvLaunch {
     static int ola(InvParams p, cudaStream_t st) {
         auto kern = istft_ola_kernel<P>;
         const size_t smem = smem_ola(p.ovc, p.hop);
-        static size_t reserved = 0;
+        static PerDevice cache[kMaxDevices];
+        PerDevice& pd = per_device(cache);
+        size_t& reserved = pd.reserved;
         if (smem > reserved) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
                 set_error("istft_ola: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
@@ -435,8 +437,8 @@ struct InvLaunch {
             reserved = smem;
         }
         p.ring = G + p.ovc - 1;
-        static int ctas_per_sm = 0;
-        static size_t occ_smem = 0;
+        int& ctas_per_sm = pd.ctas_per_sm;
+        size_t& occ_smem = pd.occ_smem;
         if (ctas_per_sm == 0 || occ_smem != smem) {
             int nb = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem);
@@ -458,7 +460,8 @@ struct InvLaunch {
     static int frames(const InvFramesParams& p, cudaStream_t st) {
         auto kern = irfft_frames_kernel<P>;
         constexpr size_t smem = (size_t)G * P::SMEM_CF * sizeof(cf) + (size_t)P::M * sizeof(float2);
-        static int ctas_per_sm = 0;
+        static PerDevice cache[kMaxDevices];
+        int& ctas_per_sm = per_device(cache).ctas_per_sm;
         if (ctas_per_sm == 0) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
                 set_error("irfft_frames: cannot reserve shared memory");

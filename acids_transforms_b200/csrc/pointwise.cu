@@ -474,12 +474,9 @@ extern "C" ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels,
     }
     const size_t smem = ((size_t)n_mels * 33 + (size_t)n_mels * n_mfcc) * sizeof(float);
     ACIDS_REQUIRE(smem <= 227 * 1024, ACIDS_ENOTSUP, "mfcc_dct: n_mels * (33 + n_mfcc) floats exceed shared memory");
-    static size_t reserved = 48 * 1024;
-    if (smem > reserved) {
+    if (smem > 48 * 1024)
         ACIDS_REQUIRE(cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
                       ACIDS_ECUDA, "mfcc_dct: cannot reserve %zu B of shared memory", smem);
-        reserved = smem;
-    }
     const int64_t tiles = B * ((n_frames + 31) / 32);
     int64_t grid = tiles;
     const int64_t cap = (int64_t)num_sms() * 4;

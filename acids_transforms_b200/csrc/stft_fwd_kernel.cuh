@@ -185,7 +185,11 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
             if (VW == 4) {
 #pragma unroll
                 for (int b0 = 0; b0 < B0; b0 += 2) {
+#ifdef ACIDS_DEBUG_NOWINDOW     // tuning experiment only: what would the kernel cost if the window taps were free?
+                    const float4 w = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+#else
                     const float4 w = *reinterpret_cast<const float4*>(wv + b0);
+#endif
                     v[b0 * R0 + r] = cmul2(v[b0 * R0 + r], mk(w.x, w.y));
                     v[(b0 + 1) * R0 + r] = cmul2(v[(b0 + 1) * R0 + r], mk(w.z, w.w));
                 }
@@ -295,8 +299,10 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     size_t smem = C::exch_bytes() + C::win_bytes();
     if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (size_t)2 * G * C::VSTR * sizeof(float);
     auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
-    static size_t reserved = 0;
-    static int ctas_per_sm = 0;
+    static PerDevice cache[kMaxDevices];
+    PerDevice& pd = per_device(cache);
+    size_t& reserved = pd.reserved;
+    int& ctas_per_sm = pd.ctas_per_sm;
     if (smem > reserved || ctas_per_sm == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("stft_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));

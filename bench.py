@@ -59,48 +59,104 @@ def traffic_from_profiles(kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    In-process NVML (nvidia_ml_py) from a background thread, this rank's GPU only, every 100 ms.  A looping
+    `nvidia-smi` child re-enumerates every GPU of the box on each poll and holds driver locks long enough to stall
+    the many small CUDA API calls of the end-to-end pipeline (measured: 15 ms -> 20-55 ms per e2e step); it is only
+    the fallback when NVML cannot be loaded."""
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.idx = str(gpu_index)
         self.proc = None
+        self.thread = None
+        self.rows = []          # (sm_mhz, sm_max_mhz, power_w, [reasons])
+        self.how = None
+
+    def _nvml_loop(self, nv, handle, stop):
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        try:
+            sm_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            sm_max = None
+        while not stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.rows.append((sm, sm_max, pw, [n for b, n in bits if mask & b]))
+            except Exception:
+                pass
+            stop.wait(0.1)
 
     def __enter__(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES so that rank i samples ITS device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if int(self.idx) < len(ids):
+                    phys = ids[int(self.idx)]
+            handle = nv.nvmlDeviceGetHandleByUUID(phys) if not phys.isdigit() else nv.nvmlDeviceGetHandleByIndex(int(phys))
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle, self._stop), daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return self
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.rows = []
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            self.thread = None
+            return
         if self.proc is None:
             return
-        time.sleep(0.15)
+        time.sleep(0.3)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
+        self.proc = None
         for line in out.splitlines():
             p = [s.strip() for s in line.split(",")]
-            if len(p) >= 8 and p[0] == self.idx:
-                self.rows.append(p)
+            if len(p) >= 8 and p[0] == self.idx and p[1].replace(".", "").isdigit():
+                reasons = [n for i, n in enumerate(self.NAMES) if p[4 + i].lower().startswith("active")]
+                self.rows.append((float(p[1]), float(p[2]) if p[2].replace(".", "").isdigit() else None,
+                                  float(p[3]) if p[3].replace(".", "").isdigit() else None, reasons))
 
     def summary(self):
-        rows = getattr(self, "rows", [])
+        rows = self.rows
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
-        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
-                "power_w_max": max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit()) if rows else None,
-                "reasons": reasons, "samples": len(rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
+        reasons = sorted({r for row in rows for r in row[3]})
+        pw = [r[2] for r in rows if r[2] is not None]
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": rows[0][1],
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows), "how": self.how}
 
 
 def synth_clips(n, device, seed):
@@ -265,16 +321,22 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
             pipe(x_host, out_host)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            pipe(x_host, out_host)
-        e1.record()
-        barrier()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+        # The host side of this path (PCIe, pinned memory, driver calls) shares the box with other tenants: time three
+        # groups of e2e_steps steps and report the MEDIAN group (all three are in the line).
+        groups = []
+        for _ in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(e2e_steps):
+                pipe(x_host, out_host)
+            e1.record()
+            barrier()
+            groups.append(max_over_ranks(e0.elapsed_time(e1)) / e2e_steps)
+        e2e_ms = sorted(groups)[1]
         e2e = {"value": world * n_e2e * CLIP_S / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "clips_per_step": n_e2e, "ms_per_step": e2e_ms,
+               "ms_per_step_groups": [round(g, 3) for g in groups], "steps_per_group": e2e_steps,
                "api": "HostPipeline(DGT + Magnitude)(pinned host tensor) -> pinned host tensor"}
         del x_host, out_host
 
