@@ -2,6 +2,7 @@
 // Rows A6, A8 (Magnitude forward / invert), A10-A13 (Phase, unwrap, IF forward / invert), A14 (polar
 // recombination) of SURVEY.md §8(a).  All HBM bound: one read of the input, one write of the output.
 #include "common.cuh"
+#include <type_traits>
 
 namespace acids {
 
@@ -136,6 +137,32 @@ struct PhaseParams {
 
 #define ACIDS_PI_F 3.14159265358979323846f
 #define ACIDS_2PI_F 6.28318530717958647692f
+#define ACIDS_INV_PI_F 0.31830988618379067154f
+#define ACIDS_INV_2PI_F 0.15915494309189533577f
+
+// atan2 for the phase kernels: |error| < 1e-7 rad (3e-8 of the +-pi range; the parity budget is 1e-4).
+// One approximate division to map the argument into [0, 1], the degree-16 even minimax polynomial of atan(a)/a
+// (Abramowitz & Stegun 4.4.49, |eps| <= 2e-8), octant fix-ups, IEEE sign of zero: atan2(+0, x < 0) = +pi and
+// atan2(-0, x < 0) = -pi (the DC and Nyquist bins carry an exact +0 imaginary part).  ~25 instructions instead of the
+// ~50 of atan2f: the phase kernel is issue bound (82 % issue-slot utilisation measured), not memory bound.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float z = a * a;
+    float p = 0.0028662257f;
+    p = fmaf(p, z, -0.0161657367f);
+    p = fmaf(p, z, 0.0429096138f);
+    p = fmaf(p, z, -0.0752896400f);
+    p = fmaf(p, z, 0.1065626393f);
+    p = fmaf(p, z, -0.1420889944f);
+    p = fmaf(p, z, 0.1999355085f);
+    p = fmaf(p, z, -0.3333314528f);
+    float r = fmaf(p * z, a, a);
+    r = ay > ax ? 1.57079632679489661923f - r : r;
+    r = x < 0.f ? 3.14159265358979323846f - r : r;
+    return copysignf(r, y);
+}
 
 __device__ __forceinline__ float unwrap_correction(float d) {
     // utils/misc.py:19-24: ddmod = (d + pi) % 2pi - pi (python remainder); +pi when it lands on -pi going up
@@ -167,25 +194,31 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
     if (col >= p.B * p.n_bins) return;
     const int64_t b = col / p.n_bins;
     const int f = (int)(col - b * p.n_bins);
-    const float2* __restrict__ X = p.X + b * (int64_t)p.n_frames * p.n_bins + f;
-    const bool write = f >= p.drop_first;
+    if (f < p.drop_first) return;                       // the dropped bin produces no output at all
+    const int T = p.n_frames;
+    const int64_t xs = p.n_bins, os = p.out_row_stride;
+    const float2* __restrict__ xp = p.X + b * (int64_t)T * xs + f;          // next spectrum row to load
     float* __restrict__ out = p.out + b * p.out_clip_stride + (f - p.drop_first);
     const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
     const float inv = p.scale_ptr ? 1.0f / __ldg(p.scale_ptr) : 1.0f;
-    const int T = p.n_frames;
     auto emit = [&](int t, float v) {
         if (WEIGHTED) v *= if_weight(t, T);
-        if (write) stg_stream1(out + (int64_t)t * p.out_row_stride, (v - off) * inv);
+        stg_stream1(out + t * os, (v - off) * inv);
     };
     float prev_raw = 0.f, cum = 0.f;
     float u1 = 0.f, u2 = 0.f;   // unwrapped phase at t-1, t-2
-    for (int t0 = 0; t0 < T; t0 += KB) {
+    // EDGE = false: every frame of the block is interior (1 <= t, t + 1 <= T - 2): no bounds or first / last frame cases
+    auto block = [&](int t0, auto edge_) {
+        constexpr bool EDGE = decltype(edge_)::value;
         float2 a[KB];
         float rawv[KB], corr[KB];
 #pragma unroll
-        for (int k = 0; k < KB; ++k) a[k] = (t0 + k < T) ? ldg_stream2(X + (int64_t)(t0 + k) * p.n_bins) : make_float2(1.f, 0.f);
+        for (int k = 0; k < KB; ++k) {
+            a[k] = (!EDGE || t0 + k < T) ? ldg_stream2(xp) : make_float2(1.f, 0.f);
+            xp += xs;
+        }
 #pragma unroll
-        for (int k = 0; k < KB; ++k) rawv[k] = atan2f(a[k].y, a[k].x);
+        for (int k = 0; k < KB; ++k) rawv[k] = fast_atan2f(a[k].y, a[k].x);
         if (MODE != ACIDS_PHASE_RAW) {
 #pragma unroll
             for (int k = 0; k < KB; ++k) corr[k] = unwrap_correction(rawv[k] - (k == 0 ? prev_raw : rawv[k - 1]));
@@ -194,39 +227,44 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
             const int t = t0 + k;
-            if (t >= T) break;
+            if (EDGE && t >= T) break;
             const float raw = rawv[k];
             if (MODE == ACIDS_PHASE_RAW) {
                 emit(t, raw);
                 continue;
             }
-            if (t > 0) cum += corr[k];
-            const float un = t > 0 ? raw + cum : raw;
+            if (!EDGE || t > 0) cum += corr[k];
+            const float un = (!EDGE || t > 0) ? raw + cum : raw;
             if (MODE == ACIDS_PHASE_UNWRAP) {
                 emit(t, un);
             } else if (METHOD == ACIDS_IF_FORWARD) {
                 // row 0 = phi_0, row t = (phi_t - phi_{t-1}) / 2; rows [:-1] then divided by pi
-                float v = t == 0 ? un : (un - u1) / 2.f;
-                if (t < T - 1) v = v / ACIDS_PI_F;
+                float v = (EDGE && t == 0) ? un : (un - u1) * 0.5f;
+                if (!EDGE || t < T - 1) v = v * ACIDS_INV_PI_F;        // 1 ulp from the reference's division, 1e-7 of the budget
                 emit(t, v);
             } else if (METHOD == ACIDS_IF_BACKWARD) {
                 // row t = (phi_t - phi_{t+1}) / 2 for t < T-1, row T-1 = phi_{T-1}; rows [1:] divided by -pi
-                if (t > 0) {
-                    float v = (u1 - un) / 2.f;
-                    if (t - 1 >= 1) v = v / (-ACIDS_PI_F);
+                if (!EDGE || t > 0) {
+                    float v = (u1 - un) * 0.5f;
+                    if (!EDGE || t - 1 >= 1) v = v * -ACIDS_INV_PI_F;
                     emit(t - 1, v);
                 }
-                if (t == T - 1) emit(t, t >= 1 ? un / (-ACIDS_PI_F) : un);
+                if (EDGE && t == T - 1) emit(t, t >= 1 ? un * -ACIDS_INV_PI_F : un);
             } else {
                 // central: row 0 = phi_0, row t = (phi_{t+1} - phi_{t-1}) / 4 / (2 pi), row T-1 = phi_{T-1}
-                if (t == 0) emit(0, un);
-                if (t >= 2) emit(t - 1, (un - u2) / 4.f / ACIDS_2PI_F);
-                if (t == T - 1 && t > 0) emit(t, un);
+                if (EDGE && t == 0) emit(0, un);
+                if (!EDGE || t >= 2) emit(t - 1, (un - u2) * 0.25f * ACIDS_INV_2PI_F);
+                if (EDGE && t == T - 1 && t > 0) emit(t, un);
             }
             u2 = u1;
             u1 = un;
         }
-    }
+    };
+    // frames 0, 1 and the last two need the special cases of the difference schemes: first and last block are general
+    int t0 = 0;
+    block(t0, std::true_type{});
+    for (t0 = KB; t0 + KB <= T - 2; t0 += KB) block(t0, std::false_type{});
+    for (; t0 < T; t0 += KB) block(t0, std::true_type{});
 }
 
 typedef void (*PhaseFwdKernel)(const PhaseParams);
