@@ -170,9 +170,9 @@ __device__ __forceinline__ void taps(const float* __restrict__ v, int val_stride
     for (int u = 0; u < K; ++u) w[u] = BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        float acc = 0.f;
+        float acc = K > 0 ? v[f * val_stride] * w[0] : 0.f;     // == fmaf(., ., 0): no accumulator to clear
 #pragma unroll
-        for (int u = 0; u < K; ++u) acc = fmaf(v[f * val_stride + u], w[u], acc);
+        for (int u = 1; u < K; ++u) acc = fmaf(v[f * val_stride + u], w[u], acc);
         a[f] = acc;
     }
 }
