@@ -15,6 +15,8 @@ using Fwd256   = Plan<256,   8, 4, 4, 8>;
 using Fwd512   = Plan<512,  16, 4, 8, 8>;
 #if defined(ACIDS_FWD1024_T16)
 using Fwd1024  = Plan<1024, 16, 32, 16>;      // experiment: one exchange, 32 values per thread
+#elif defined(ACIDS_FWD1024_R0)
+using Fwd1024  = Plan<1024, 32, ACIDS_FWD1024_R0, ACIDS_FWD1024_R1, ACIDS_FWD1024_R2>;   // experiment: other radix orders
 #else
 using Fwd1024  = Plan<1024, 32, 8, 8, 8>;
 #endif
