@@ -96,7 +96,12 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
 // launch shape per plan (see FwdCfg): small frame groups run 128-thread CTAs
 template <class P>
 struct InvCfg {
-    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
+    // n_fft = 4096 (T = 128): one frame per CTA.  With two frames the ring (5 x 16 KB) leaves a single 8-warp CTA per
+    // SM whose warps all sit in the same phase; one frame per CTA (ring 4 x 16 KB, 103 KB) gives two independent CTAs.
+#ifndef ACIDS_INV_T128_THREADS
+#define ACIDS_INV_T128_THREADS 128
+#endif
+    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : 256));
     static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL : (P::T <= 256 ? 2 : 1);
     static constexpr int G = THREADS / P::T;
 };
