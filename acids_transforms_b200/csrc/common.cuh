@@ -233,10 +233,14 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
                                               float* __restrict__ out0, int row_step, int col_step, int n_valid) {
     // out0: element (row 0, first output column) of the tile; rows are row_step floats apart, columns col_step
     // (TRANSPOSED: rows are adjacent, row_step is ignored; otherwise columns are adjacent, col_step is ignored)
-    float* orow[NF];
+    // one running pointer per thread (row 0 of its current column) plus loop-invariant row offsets: the column loop
+    // carries no address arithmetic beyond one pointer increment
+    float* __restrict__ o = out0 + (TRANSPOSED ? (int64_t)tid * col_step : (int64_t)tid);
+    const int64_t o_step = TRANSPOSED ? (int64_t)NT * col_step : (int64_t)NT;
+    int64_t roff[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) orow[f] = out0 + (TRANSPOSED ? f : f * row_step);
-    for (int mo = tid; mo < ep.n_out; mo += NT) {
+    for (int f = 0; f < NF; ++f) roff[f] = TRANSPOSED ? (int64_t)f : (int64_t)f * row_step;
+    for (int mo = tid; mo < ep.n_out; mo += NT, o += o_step) {
         const int m = mo + ep.drop_first;
         float a[NF];
         if (BAND != BAND_NONE) {
@@ -245,10 +249,9 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
 #pragma unroll
             for (int f = 0; f < NF; ++f) a[f] = val[f * val_stride + m];
         }
-        const int off = TRANSPOSED ? mo * col_step : mo;
 #pragma unroll
         for (int f = 0; f < NF; ++f)
-            if (FULL || f < n_valid) stg_stream1(orow[f] + off, fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
+            if (FULL || f < n_valid) stg_stream1(o + roff[f], fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
     }
 }
 

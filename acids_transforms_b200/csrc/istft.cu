@@ -101,8 +101,11 @@ struct InvCfg {
 #ifndef ACIDS_INV_T128_THREADS
 #define ACIDS_INV_T128_THREADS 128
 #endif
-    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : 256));
-    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL : (P::T <= 256 ? 2 : 1);
+#ifndef ACIDS_INV_SMALL_THREADS
+#define ACIDS_INV_SMALL_THREADS 128
+#endif
+    static constexpr int THREADS = P::T <= 32 ? ACIDS_INV_SMALL_THREADS : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : 256));
+    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS) : (P::T <= 256 ? 2 : 1);
     static constexpr int G = THREADS / P::T;
 };
 
