@@ -202,8 +202,11 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
             }
         }
 
-        cf nv[MODE == MODE_COMPLEX ? V : 1];
-        if (MODE == MODE_COMPLEX) {
+        // complex output, small plans (3 CTAs / SM leave 168 registers): the next frame's samples are fetched a whole
+        // FFT early into a second register set; larger plans (128 registers) fetch after the stores instead
+        constexpr bool EARLY = MODE == MODE_COMPLEX && T <= 32;
+        cf nv[EARLY ? V : 1];
+        if (EARLY) {
             if (u + 1 < u1) fetch(nv, xclip, uc * G + g);       // lands during this frame's FFT
         }
 
@@ -251,8 +254,12 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
                 }
                 if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
+            if (EARLY) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) v[i] = nv[MODE == MODE_COMPLEX ? i : 0];
+                for (int i = 0; i < V; ++i) v[i] = nv[EARLY ? i : 0];
+            } else {
+                if (u + 1 < u1) fetch(v, xclip, uc * G + g);
+            }
         } else {
             float* __restrict__ vbuf = vrows + buf * (G * VSTR);
             float* __restrict__ val = vbuf + g * VSTR;
