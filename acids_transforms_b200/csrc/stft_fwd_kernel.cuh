@@ -33,8 +33,14 @@ struct FwdParams {
 #endif
 template <class P>
 struct FwdCfg {
-    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : 256);
-    static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 256 ? 2 : 1);
+#ifndef ACIDS_FWD_MID_THREADS
+#define ACIDS_FWD_MID_THREADS 128      // CTA size of the T = 64 / 128 plans (n_fft 2048 / 4096): 3 CTAs x 168 registers, no spills
+#endif
+#ifndef ACIDS_FWD_MID_MINB
+#define ACIDS_FWD_MID_MINB 3
+#endif
+    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256));
+    static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1));
     // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
     // second register set; that needs ~160 registers -> one CTA less per SM for the small plans
     static constexpr int MINB_COMPLEX = P::T <= 32 ? 3 : MINB;
