@@ -104,8 +104,11 @@ struct InvCfg {
 #ifndef ACIDS_INV_SMALL_THREADS
 #define ACIDS_INV_SMALL_THREADS 128
 #endif
-    static constexpr int THREADS = P::T <= 32 ? ACIDS_INV_SMALL_THREADS : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : 256));
-    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS) : (P::T <= 256 ? 2 : 1);
+    // n_fft = 2048 (T = 64): 128-thread CTAs at 3 per SM (168 registers); at 256 threads x 2 the 128-register budget spills
+    static constexpr int THREADS = P::T <= 32 ? ACIDS_INV_SMALL_THREADS
+                                              : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : (P::T == 64 ? 128 : 256)));
+    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS)
+                                           : (P::T == 64 ? 3 : (P::T <= 256 ? 2 : 1));
     static constexpr int G = THREADS / P::T;
 };
 

@@ -81,7 +81,11 @@ def main():
         ms = timeit(lambda: ops.melspec_fwd(x3, hw3, n3, h3, mel, 2.0), iters=10)
         byt = B3 * (4 * L3 + 4 * 128 * T3)
         res["cfg3_melspec_2048_128"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK, audio_s_per_s=B3 * 10 / (ms / 1e3))
-        del x3
+        X3 = ops.stft_fwd(x3[:256], hw3, n3, h3)
+        ms = timeit(lambda: ops.istft_ola(X3, hw3, n3, h3, check_envelope=False), iters=10)
+        byt = 256 * (8 * T3 * (n3 // 2 + 1) + 4 * h3 * (T3 - 1))
+        res["istft_2048_512"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        del x3, X3
         torch.cuda.empty_cache()
         # cfg 4: stereo clips, STFT(4096, 1024) -> complex; ISTFT back; Phase/IF on the spectrum
         B4, n4, h4 = 1024, 4096, 1024
