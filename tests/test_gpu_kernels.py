@@ -99,6 +99,29 @@ def test_stft_istft_oracle(ops, n_fft, hop, L, B):
         assert_parity(host(y), O.istft(Xo, n_fft, hop, w), REL, "inv %d/%d" % (n_fft, hop))
 
 
+def test_fuzz_against_torch_on_device(ops):
+    """Seeded random geometries (n_fft, hop, length, batch, window) against torch.stft / torch.istft on the same GPU
+    (cuFFT: an implementation independent of both this code and the numpy oracle)."""
+    rng = np.random.default_rng(20261018)
+    for case in range(24):
+        n_fft = int(2 ** rng.integers(5, 13))                       # 32 .. 4096
+        hop = int(rng.choice([n_fft // 8, n_fft // 4, n_fft // 2, max(1, n_fft // 4 - 1), max(1, n_fft // 3)]))
+        B = int(rng.integers(1, 6))
+        L = int(n_fft // 2 + 1 + rng.integers(0, 12 * n_fft))
+        g = torch.Generator(device="cuda").manual_seed(case)
+        x = 2 * torch.rand((B, L), generator=g, device="cuda") - 1
+        w = torch.hann_window(n_fft, device="cuda") if case % 2 == 0 else torch.hamming_window(n_fft, device="cuda")
+        want = torch.stft(x, n_fft, hop, window=w, return_complex=True).transpose(-2, -1)
+        got = ops.stft_fwd(x, w, n_fft, hop)
+        tag = "case %d n_fft=%d hop=%d L=%d B=%d" % (case, n_fft, hop, L, B)
+        assert got.shape == want.shape, tag
+        assert_parity(host(torch.view_as_real(got)), host(torch.view_as_real(want.contiguous())), REL, "fuzz fwd " + tag)
+        if want.shape[-2] > 1 and ops.istft_envelope_ok(w, n_fft, hop, want.shape[-2]):
+            y_want = torch.istft(want.transpose(-2, -1), n_fft, hop, window=w)
+            y = ops.istft_ola(want.contiguous(), w, n_fft, hop)
+            assert_parity(host(y), host(y_want), REL, "fuzz inv " + tag)
+
+
 def test_stft_known_answers(ops):
     n, h = 1024, 256
     w = torch.hann_window(n).cuda()
