@@ -297,7 +297,11 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
                 epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
                                                                        out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
             }
+#ifdef ACIDS_FWD_SINGLE_ROWBUF     // tuning experiment: one |X| row buffer (8 KB less shared memory per CTA), two barriers per unit
+            __syncthreads();
+#else
             buf ^= 1;
+#endif
         }
     }
 }
@@ -310,7 +314,12 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     constexpr int THREADS = C::THREADS;
     constexpr int G = C::G;
     size_t smem = C::exch_bytes() + C::win_bytes();
-    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (size_t)2 * G * C::VSTR * sizeof(float);
+#ifdef ACIDS_FWD_SINGLE_ROWBUF
+    constexpr int kRowBufs = 1;
+#else
+    constexpr int kRowBufs = 2;
+#endif
+    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (size_t)kRowBufs * G * C::VSTR * sizeof(float);
     auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
     static PerDevice cache[kMaxDevices];
     PerDevice& pd = per_device(cache);
