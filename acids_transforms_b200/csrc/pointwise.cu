@@ -435,6 +435,28 @@ extern "C" ACIDS_API int acids_midside(const float* x, int64_t B, int64_t L, int
     return ACIDS_OK;
 }
 
+static int launch_group_max(const float* mel, int64_t B, int n_mels, int64_t n_frames, float top_db, int64_t clips_per_group,
+                            float* group_max, cudaStream_t st) {
+    if (top_db < 0.f) return ACIDS_OK;
+    const int64_t groups = B / clips_per_group, per_group = clips_per_group * n_mels * n_frames;
+    ACIDS_REQUIRE(groups < 65536, ACIDS_EINVAL, "mfcc_dct: more than 65535 top_db groups");
+    if (cudaMemsetAsync(group_max, 0, (size_t)groups * sizeof(float), st) != cudaSuccess) {
+        set_error("mfcc_dct: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return ACIDS_ECUDA;
+    }
+    // enough CTAs to stream the whole tensor at HBM speed, split over the groups
+    int64_t chunks = (per_group + 256 * 16 - 1) / (256 * 16);
+    const int64_t cap = ((int64_t)num_sms() * 8 + groups - 1) / groups;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    group_max_kernel<<<dim3((unsigned)chunks, (unsigned)groups), 256, 0, st>>>(mel, per_group, group_max);
+    ACIDS_CHECK_LAUNCH("mfcc group max");
+    return ACIDS_OK;
+}
+
+int acids_mfcc_dct_tc_launch(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct, int n_mfcc, float top_db,
+                             int64_t clips_per_group, const float* group_max, float* out, cudaStream_t st);   // mfcc_tc.cu
+
 extern "C" ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct, int n_mfcc,
                               float top_db, int64_t clips_per_group, float* group_max, float* out, void* stream) {
     ACIDS_REQUIRE(mel && dct && out, ACIDS_EINVAL, "mfcc_dct: NULL pointer");
@@ -443,20 +465,9 @@ extern "C" ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels,
                   "mfcc_dct: top_db needs group_max scratch and a group size dividing B");
     if (B == 0) return ACIDS_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (top_db >= 0.f) {
-        const int64_t groups = B / clips_per_group, per_group = clips_per_group * n_mels * n_frames;
-        ACIDS_REQUIRE(groups < 65536, ACIDS_EINVAL, "mfcc_dct: more than 65535 top_db groups");
-        if (cudaMemsetAsync(group_max, 0, (size_t)groups * sizeof(float), st) != cudaSuccess) {
-            set_error("mfcc_dct: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return ACIDS_ECUDA;
-        }
-        // enough CTAs to stream the whole tensor at HBM speed, split over the groups
-        int64_t chunks = (per_group + 256 * 16 - 1) / (256 * 16);
-        const int64_t cap = ((int64_t)num_sms() * 8 + groups - 1) / groups;
-        if (chunks > cap) chunks = cap;
-        if (chunks < 1) chunks = 1;
-        group_max_kernel<<<dim3((unsigned)chunks, (unsigned)groups), 256, 0, st>>>(mel, per_group, group_max);
-        ACIDS_CHECK_LAUNCH("mfcc group max");
+    {
+        const int rc = launch_group_max(mel, B, n_mels, n_frames, top_db, clips_per_group, group_max, st);
+        if (rc) return rc;
     }
     const int64_t gsize = clips_per_group > 0 ? clips_per_group : 1;
     if (n_mfcc <= 64) {
@@ -497,4 +508,21 @@ extern "C" ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels,
                                                         clips_per_group > 0 ? clips_per_group : 1, out);
     ACIDS_CHECK_LAUNCH("mfcc_dct");
     return ACIDS_OK;
+}
+
+// The same tail with the DCT on the tensor cores (tcgen05, 3xTF32; mfcc_tc.cu).  Shapes: n_mels a multiple of 8 up to
+// 128, n_mfcc <= 48; other shapes return ACIDS_ENOTSUP (use acids_mfcc_dct).
+extern "C" ACIDS_API int acids_mfcc_dct_tc(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct, int n_mfcc,
+                                 float top_db, int64_t clips_per_group, float* group_max, float* out, void* stream) {
+    ACIDS_REQUIRE(mel && dct && out, ACIDS_EINVAL, "mfcc_dct_tc: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_mels > 0 && n_frames > 0 && n_mfcc > 0, ACIDS_EINVAL, "mfcc_dct_tc: bad sizes");
+    ACIDS_REQUIRE(n_mels % 8 == 0 && n_mels <= 128 && n_mfcc <= 48, ACIDS_ENOTSUP,
+                  "mfcc_dct_tc: needs n_mels %% 8 == 0, n_mels <= 128, n_mfcc <= 48 (got %d, %d)", n_mels, n_mfcc);
+    ACIDS_REQUIRE(top_db < 0.f || (group_max && clips_per_group >= 1 && B % clips_per_group == 0), ACIDS_EINVAL,
+                  "mfcc_dct_tc: top_db needs group_max scratch and a group size dividing B");
+    if (B == 0) return ACIDS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = launch_group_max(mel, B, n_mels, n_frames, top_db, clips_per_group, group_max, st);
+    if (rc) return rc;
+    return acids_mfcc_dct_tc_launch(mel, B, n_mels, n_frames, dct, n_mfcc, top_db, clips_per_group, group_max, out, st);
 }

@@ -318,8 +318,10 @@ def melspec_fwd(x, window, n_fft, hop, mel: BandedMatrix, power=2.0, offset=None
     return _ret(out.reshape(tuple(batch) + (mel.n_out, T)), x)
 
 
-def mfcc_dct(mel, dct, top_db: Optional[float] = 80.0):
-    """dB + top_db floor + DCT-II: mel [..., n_mels, T] -> [..., n_mfcc, T]  (torchaudio MFCC, _transforms.py:701-718)."""
+def mfcc_dct(mel, dct, top_db: Optional[float] = 80.0, tensor_cores: Optional[bool] = None):
+    """dB + top_db floor + DCT-II: mel [..., n_mels, T] -> [..., n_mfcc, T]  (torchaudio MFCC, _transforms.py:701-718).
+    tensor_cores: the DCT as a tcgen05 3xTF32 GEMM (needs n_mels % 8 == 0, n_mels <= 128, n_mfcc <= 48); None picks it
+    whenever the shape fits, False forces the FP32 register-tiled kernel."""
     lib = _lib.load()
     md = _dev(mel).to(torch.float32)
     mf, batch = _flat_batch(md, 2)
@@ -332,8 +334,11 @@ def mfcc_dct(mel, dct, top_db: Optional[float] = 80.0):
     out = torch.empty((B, n_mfcc, T), dtype=torch.float32, device=dev)
     gmax = torch.empty((max(B // max(group, 1), 1),), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _run(out, lib.acids_mfcc_dct, _ptr(mf), B, n_mels, T, _ptr(d), n_mfcc, float(-1.0 if top_db is None else top_db),
-                                      max(group, 1), _ptr(gmax), _ptr(out), _stream(dev))
+        if tensor_cores is None:
+            tensor_cores = n_mels % 8 == 0 and n_mels <= 128 and n_mfcc <= 48
+        fn = lib.acids_mfcc_dct_tc if tensor_cores else lib.acids_mfcc_dct
+        _run(out, fn, _ptr(mf), B, n_mels, T, _ptr(d), n_mfcc, float(-1.0 if top_db is None else top_db),
+                      max(group, 1), _ptr(gmax), _ptr(out), _stream(dev))
     return _ret(out.reshape(tuple(batch) + (n_mfcc, T)), mel)
 
 

@@ -132,6 +132,12 @@ ACIDS_API int acids_mfcc_dct(const float* mel, int64_t B, int n_mels, int64_t n_
                    int n_mfcc, float top_db, int64_t clips_per_group, float* group_max, float* out,
                    void* stream);
 
+/* The same tail with the DCT as a tensor-core GEMM (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, accumulator
+ * in TMEM; csrc/mfcc_tc.cu).  Same arguments; n_mels % 8 == 0, n_mels <= 128, n_mfcc <= 48, else ACIDS_ENOTSUP.   */
+ACIDS_API int acids_mfcc_dct_tc(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct,
+                   int n_mfcc, float top_db, int64_t clips_per_group, float* group_max, float* out,
+                   void* stream);
+
 /* ---- (3) phase / unwrap / instantaneous frequency ------------------------------------------
  * Phase.forward (spectral_repr.py:270-278), unwrap (utils/misc.py:12-26), IF.forward
  * (spectral_repr.py:319-357).  X complex64 [B, n_frames, n_bins]; out float32 rows like (2).

@@ -300,6 +300,25 @@ def test_polar_golden(ops):
 # ---------------------------------------------------------------------------------------------
 # MFCC (= MelSpectrogram) and the DCT variant
 # ---------------------------------------------------------------------------------------------
+def test_mfcc_dct_tensor_cores(ops):
+    """The tcgen05 3xTF32 DCT against the FP32 kernel and a float64 reference (dB-scaled data, top_db floor)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for B, n_mels, n_mfcc, T in [(3, 128, 40, 300), (2, 64, 13, 129), (1, 128, 48, 128)]:
+        mel = torch.rand((B, n_mels, T), generator=g, device="cuda") ** 4 * 50.0 + 1e-9
+        k = torch.arange(n_mfcc, dtype=torch.float64)[None, :]
+        n = torch.arange(n_mels, dtype=torch.float64)[:, None]
+        dct = torch.cos(math.pi / n_mels * (n + 0.5) * k) * math.sqrt(2.0 / n_mels)
+        dct[:, 0] *= 1.0 / math.sqrt(2.0)
+        dct = dct.float().cuda()
+        ref32 = ops.mfcc_dct(mel, dct, 80.0, tensor_cores=False)
+        got = ops.mfcc_dct(mel, dct, 80.0, tensor_cores=True)
+        db = 10.0 * torch.log10(torch.clamp(mel.double(), min=1e-10))
+        db = torch.maximum(db, db.amax() - 80.0)
+        want = torch.einsum("bmt,mk->bkt", db, dct.double())
+        assert_parity(host(got), host(want.float()), REL, "tc dct vs float64 (%d, %d, %d)" % (n_mels, n_mfcc, T))
+        assert_parity(host(got), host(ref32), REL, "tc dct vs fp32 kernel")
+
+
 def test_griffinlim_update(ops):
     """The fused fast-Griffin-Lim update against the eager formula (torchaudio functional.py:336-350)."""
     g = torch.Generator(device="cuda").manual_seed(3)
