@@ -32,6 +32,7 @@ _SCHEMAS = {
     "polar_fwd": "(Tensor X, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? mag_offset, "
                  "Tensor? mag_scale, int phase_mode, int method, bool weighted, Tensor? ph_offset, Tensor? ph_scale, "
                  "bool drop_first) -> Tensor",
+    "phase_inv_polar": "(Tensor y, Tensor mag, int mode, int method, Tensor? offset, Tensor? scale, bool pad_last) -> Tensor",
     "polar_to_complex": "(Tensor mag, Tensor phase) -> Tensor",
     "griffinlim_update": "(Tensor rebuilt, Tensor tprev, Tensor mag, float momentum) -> Tensor",
     "istft_ola": "(Tensor X, Tensor window, int n_fft, int hop) -> Tensor",
@@ -104,6 +105,10 @@ def _polar_fwd(X, band_meta, band_coef, contrast: int, eps: float, mag_offset, m
     ops.phase_fwd(Xd, phase_mode, method, weighted, ph_offset, ph_scale, drop_first, out=out, out_slot=1, out_slots=2)
     out = out.reshape(tuple(Xd.shape[:-2]) + (T, 2, n_mag))
     return ops._ret(out, X)
+
+
+def _phase_inv_polar(y, mag, mode: int, method: int, offset, scale, pad_last: bool):
+    return ops.phase_inv_polar(y, mag, mode, method, offset, scale, pad_last)
 
 
 def _polar_to_complex(mag, phase):

@@ -286,50 +286,83 @@ struct PhaseInvParams {
     int pad_last, mode, method;
     const float* offset_ptr;
     const float* scale_ptr;
-    float* out;   // [B, n_frames, n_in + pad_last]
+    float* out;   // [B, n_frames, n_in + pad_last]; complex64 (interleaved) of the same shape when POLAR
+    const float* mag;   // POLAR only: [B, n_frames, n_in + pad_last]
 };
 
+// POLAR: the recombination of spectral_repr.py:452 happens in the same pass — the column's phase never goes to
+// memory, the thread reads the matching magnitude and stores mag * exp(i phase).  (Not for the central method,
+// whose two recurrences use the output column as scratch.)
+template <bool POLAR>
 __global__ void __launch_bounds__(128) phase_inv_kernel(const PhaseInvParams p) {
     const int nb = p.n_in + p.pad_last;
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= p.B * nb) return;
     const int64_t b = col / nb;
     const int f = (int)(col - b * nb);
-    float* __restrict__ out = p.out + b * (int64_t)p.n_frames * nb + f;
+    const int64_t col0 = b * (int64_t)p.n_frames * nb + f;
+    float* __restrict__ out = p.out + (POLAR ? 2 * col0 : col0);
+    const float* __restrict__ mag = POLAR ? p.mag + col0 : nullptr;
     const int T = p.n_frames;
+    auto emit = [&](int t, float ph, float m) {
+        if constexpr (POLAR) {
+            float s, c;
+            sincosf(ph, &s, &c);
+            stg_stream2(reinterpret_cast<float2*>(out) + (int64_t)t * nb, m * c, m * s);
+        } else {
+            out[(int64_t)t * nb] = ph;
+        }
+    };
     if (f >= p.n_in) {   // the zero bin appended when keep_nyquist=False (spectral_repr.py:371-374)
-        for (int t = 0; t < T; ++t) out[(int64_t)t * nb] = 0.f;
+        for (int t = 0; t < T; ++t) emit(t, 0.f, POLAR ? __ldg(mag + (int64_t)t * nb) : 0.f);   // phase 0: out = mag + 0i
         return;
     }
     const float* __restrict__ y = p.y + b * p.y_clip_stride + f;
     const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
     const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
     auto den = [&](int t) { return __ldg(y + (int64_t)t * p.y_row_stride) * sc + off; };
-    if (p.mode != ACIDS_PHASE_IF) {
-        for (int t = 0; t < T; ++t) out[(int64_t)t * nb] = den(t);
-        return;
-    }
-    if (p.method == ACIDS_IF_FORWARD) {
-        // rows[:-1] *= pi; rows[1:] *= 2; cumsum over frames   (spectral_repr.py:365-367, utils/misc.py:82-86)
+    // Every mode but IF-central is one running sum (or none) along the column.  The loads of KB frames are issued
+    // before the first dependent add / sincos so that each thread keeps 2 KB requests in flight: with one load per
+    // iteration the column walk is latency-bound (measured: the POLAR form slower than the two kernels it replaces).
+    //   IF forward : rows[:-1] *= pi; rows[1:] *= 2; cumsum over frames        (spectral_repr.py:365-367, utils/misc.py:82-86)
+    //   IF backward: rows[1:] *= -pi; flip; rows[1:] *= 2; cumsum; flip  == suffix sum with the LAST row undoubled
+    const bool integrate = p.mode == ACIDS_PHASE_IF;
+    if (!integrate || p.method != ACIDS_IF_CENTRAL) {
+        constexpr int KB = 8;
+        const bool reverse = integrate && p.method == ACIDS_IF_BACKWARD;
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) {
-            float v = den(t);
-            if (t < T - 1) v *= ACIDS_PI_F;
-            if (t >= 1) v *= 2.f;
-            acc += v;
-            out[(int64_t)t * nb] = acc;
+        for (int i0 = 0; i0 < T; i0 += KB) {
+            float v[KB], m[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int i = i0 + k;
+                const int t = reverse ? T - 1 - i : i;
+                const bool ok = i < T;
+                v[k] = ok ? __ldg(y + (int64_t)t * p.y_row_stride) : 0.f;
+                m[k] = (POLAR && ok) ? __ldg(mag + (int64_t)t * nb) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int i = i0 + k;
+                if (i >= T) break;
+                const int t = reverse ? T - 1 - i : i;
+                float x = v[k] * sc + off;
+                if (integrate) {
+                    if (reverse) {
+                        if (t >= 1) x *= -ACIDS_PI_F;
+                        if (t < T - 1) x *= 2.f;
+                    } else {
+                        if (t < T - 1) x *= ACIDS_PI_F;
+                        if (t >= 1) x *= 2.f;
+                    }
+                    acc += x;
+                } else {
+                    acc = x;
+                }
+                emit(t, acc, m[k]);
+            }
         }
-    } else if (p.method == ACIDS_IF_BACKWARD) {
-        // rows[1:] *= -pi; flip; rows[1:] *= 2; cumsum; flip  == suffix sum with the LAST row undoubled
-        float acc = 0.f;
-        for (int t = T - 1; t >= 0; --t) {
-            float v = den(t);
-            if (t >= 1) v *= -ACIDS_PI_F;
-            if (t < T - 1) v *= 2.f;
-            acc += v;
-            out[(int64_t)t * nb] = acc;
-        }
-    } else {
+    } else if constexpr (!POLAR) {
         // central: rows[1:-1] *= 2 pi, then fint_central's two recurrences, python negative-index
         // wrap-around included (utils/misc.py:96-104).  The column is its own scratch.
         auto X = [&](int t) {
@@ -490,8 +523,29 @@ extern "C" ACIDS_API int acids_phase_inv(const float* y, int64_t B, int64_t n_fr
     p.y_row_stride = y_row_stride; p.pad_last = pad_last; p.mode = mode; p.method = if_method;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out;
     const int64_t cols = B * (n_in + pad_last);
-    phase_inv_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    phase_inv_kernel<false><<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("phase_inv");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_phase_inv_polar(const float* y, int64_t B, int64_t n_frames, int n_in, int64_t y_clip_stride,
+                                     int64_t y_row_stride, int pad_last, int mode, int if_method, const float* offset,
+                                     const float* scale, const float* mag, float* out, void* stream) {
+    ACIDS_REQUIRE(y && mag && out, ACIDS_EINVAL, "phase_inv_polar: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 31) && n_in > 0, ACIDS_EINVAL, "phase_inv_polar: bad sizes");
+    ACIDS_REQUIRE(mode >= 0 && mode <= 2 && if_method >= 0 && if_method <= 2, ACIDS_EINVAL, "phase_inv_polar: bad mode/method");
+    ACIDS_REQUIRE(!(mode == ACIDS_PHASE_IF && if_method == ACIDS_IF_CENTRAL), ACIDS_EINVAL,
+                  "phase_inv_polar: the central method needs the phase column as scratch; use phase_inv + polar_to_complex");
+    ACIDS_REQUIRE(pad_last == 0 || pad_last == 1, ACIDS_EINVAL, "pad_last must be 0 or 1");
+    ACIDS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, ACIDS_EINVAL, "phase_inv_polar: out must be 8-byte aligned");
+    if (B == 0) return ACIDS_OK;
+    PhaseInvParams p{};
+    p.y = y; p.B = B; p.n_frames = (int)n_frames; p.n_in = n_in; p.y_clip_stride = y_clip_stride;
+    p.y_row_stride = y_row_stride; p.pad_last = pad_last; p.mode = mode; p.method = if_method;
+    p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.mag = mag;
+    const int64_t cols = B * (n_in + pad_last);
+    phase_inv_kernel<true><<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("phase_inv_polar");
     return ACIDS_OK;
 }
 

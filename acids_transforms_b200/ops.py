@@ -390,6 +390,33 @@ def phase_inv(y, mode: int, method="forward", offset=None, scale=None, pad_last=
     return _ret(out.reshape(tuple(yd.shape[:-1]) + (n_in + int(pad_last),)), y)
 
 
+def phase_inv_polar(y, mag, mode: int, method="forward", offset=None, scale=None, pad_last=False):
+    """polar_to_complex(mag, phase_inv(y, ...)) without the phase round trip through memory
+    (SpectralRepresentation.invert, spectral_repr.py:447-452).  IF method `central` takes the two-kernel route."""
+    if mode == 2 and _mid(method) == 2:
+        return polar_to_complex(mag, phase_inv(y, mode, method, offset, scale, pad_last))
+    lib = _lib.load()
+    yd = _dev(y).to(torch.float32)
+    if yd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] tensor)")
+    yf = yd.reshape((-1,) + tuple(yd.shape[-2:]))
+    if yf.stride(-1) != 1 or (yf.shape[0] > 1 and yf.stride(0) < yf.shape[1] * yf.stride(1)):
+        yf = yf.contiguous()
+    B, T, n_in = yf.shape
+    dev = yf.device
+    shape = tuple(yd.shape[:-1]) + (n_in + int(pad_last),)
+    md = _dev(mag).to(device=dev, dtype=torch.float32)
+    if tuple(md.shape) != shape:
+        md = md.expand(shape)          # raises like the reference's broadcast would
+    md = md.contiguous()
+    out = torch.empty(shape, dtype=torch.complex64, device=dev)
+    off, sc = _scalar(offset, dev), _scalar(scale, dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_phase_inv_polar, _ptr(yf), B, T, n_in, yf.stride(0) if B > 1 else T * yf.stride(1), yf.stride(1),
+                                             int(pad_last), mode, _mid(method), _ptr(off), _ptr(sc), _ptr(md), _ptr(out), _stream(dev))
+    return _ret(out, y)
+
+
 def polar_to_complex(mag, phase):
     """mag * exp(i phase) -> complex64  (spectral_repr.py:452)."""
     lib = _lib.load()

@@ -103,6 +103,11 @@ class _Representation(AudioTransform):
         # de-normalise (+ the zero bin appended when keep_nyquist=False), spectral_repr.py:46-53
         return torch.ops.acids_b200.phase_inv(x, 0, 0, self.norm.get_offset(), self.norm.get_scale(), not self.keep_nyquist)
 
+    @torch.jit.export
+    def invert_polar(self, x: torch.Tensor, mag: torch.Tensor) -> torch.Tensor:
+        """mag * exp(i invert(x)) in one kernel: the tail of SpectralRepresentation.invert (spectral_repr.py:447-452)."""
+        return torch.ops.acids_b200.phase_inv_polar(x, mag, 0, 0, self.norm.get_offset(), self.norm.get_scale(), not self.keep_nyquist)
+
     @classmethod
     def test_scripted_transform(cls, transform, invert: bool = True):
         shape = (2, 10, 513)
@@ -380,6 +385,11 @@ class IF(_Representation):
         return torch.ops.acids_b200.phase_inv(x, 2, _method_id(self.method), self.norm.get_offset(), self.norm.get_scale(),
                                               not self.keep_nyquist)
 
+    @torch.jit.export
+    def invert_polar(self, x: torch.Tensor, mag: torch.Tensor) -> torch.Tensor:
+        return torch.ops.acids_b200.phase_inv_polar(x, mag, 2, _method_id(self.method), self.norm.get_offset(),
+                                                    self.norm.get_scale(), not self.keep_nyquist)
+
     def test_inversion(self, x: torch.Tensor):
         flat, batch = reshape_batches(x, -1)
         stft = STFT()
@@ -451,8 +461,8 @@ class SpectralRepresentation(AudioTransform):
     def invert(self, x: torch.Tensor, inversion_mode: Optional[str] = None, tolerance: float = 1.e-4) -> torch.Tensor:
         first, second = self._split(x)
         mag = self.magnitude.invert(first)
-        phase = self.phase.invert(second)
-        return torch.ops.acids_b200.polar_to_complex(mag, phase)         # mag * exp(i phase), spectral_repr.py:452
+        # mag * exp(i phase.invert(second)), spectral_repr.py:450-452; the phase transform does both in one pass
+        return self.phase.invert_polar(second, mag)
 
     def test_forward(self, x: torch.Tensor, time: Optional[torch.Tensor] = None):
         stft = STFT()

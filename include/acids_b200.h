@@ -154,6 +154,13 @@ ACIDS_API int acids_phase_inv(const float* y, int64_t B, int64_t n_frames, int n
                     int64_t y_row_stride, int pad_last, int mode, int if_method,
                     const float* offset, const float* scale, float* out, void* stream);
 
+/* acids_phase_inv and the recombination of spectral_repr.py:452 in one pass (SpectralRepresentation.invert,
+ * spectral_repr.py:447-452): out complex64 [B, n_frames, n_bins] = mag * exp(i phase), mag float32 of the
+ * same shape, contiguous.  IF method `central` is refused (ACIDS_EINVAL): call the two entry points.    */
+ACIDS_API int acids_phase_inv_polar(const float* y, int64_t B, int64_t n_frames, int n_in, int64_t y_clip_stride,
+                    int64_t y_row_stride, int pad_last, int mode, int if_method,
+                    const float* offset, const float* scale, const float* mag, float* out, void* stream);
+
 /* SpectralRepresentation.invert tail, spectral_repr.py:452: out = mag * exp(i phase).          */
 ACIDS_API int acids_polar_to_complex(const float* mag, const float* phase, int64_t n, float* out, void* stream);
 

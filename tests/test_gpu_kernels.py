@@ -295,6 +295,30 @@ def test_polar_golden(ops):
         p = ops.phase_inv(gy[..., 1, :], mode, "forward", po, ps)
         Z = host(ops.polar_to_complex(m, p))
         assert_parity(Z, g[tag + "_inv"], REL, tag + " inv")
+        # the one-pass form the modules use must be the same numbers, not merely close
+        Zf = ops.phase_inv_polar(gy[..., 1, :], m, mode, "forward", po, ps)
+        assert torch.equal(torch.view_as_real(Zf).cpu(), torch.view_as_real(torch.from_numpy(Z))), tag + " fused inv"
+
+
+def test_phase_inv_polar_variants(ops):
+    """phase_inv_polar == polar_to_complex(mag, phase_inv(...)) bit for bit: every mode / method, strided input
+    (the stacked [.., 2, F] layout), the appended zero bin, and the central method's two-kernel route."""
+    from acids_transforms_b200._lib import PHASE_IF, PHASE_RAW, PHASE_UNWRAP
+    g = torch.Generator(device="cuda").manual_seed(5)
+    stacked = torch.randn(3, 2, 17, 2, 96, device="cuda", generator=g)
+    y = stacked[..., 1, :]
+    off = torch.tensor([0.25], device="cuda")
+    sc = torch.tensor([1.5], device="cuda")
+    for mode, method in ((PHASE_RAW, "forward"), (PHASE_UNWRAP, "forward"), (PHASE_IF, "forward"), (PHASE_IF, "backward"), (PHASE_IF, "central")):
+        for pad in (False, True):
+            mag = torch.rand(3, 2, 17, 96 + int(pad), device="cuda", generator=g)
+            want = ops.polar_to_complex(mag, ops.phase_inv(y, mode, method, off, sc, pad))
+            got = ops.phase_inv_polar(y, mag, mode, method, off, sc, pad)
+            assert got.shape == want.shape and got.dtype == torch.complex64
+            assert torch.equal(torch.view_as_real(got), torch.view_as_real(want)), (mode, method, pad)
+    one = ops.phase_inv_polar(y[0, 0], torch.ones(17, 96, device="cuda"), PHASE_IF, "backward")
+    ref = ops.polar_to_complex(torch.ones(17, 96, device="cuda"), ops.phase_inv(y[0, 0], PHASE_IF, "backward"))
+    assert torch.equal(torch.view_as_real(one), torch.view_as_real(ref))
 
 
 # ---------------------------------------------------------------------------------------------
