@@ -93,6 +93,8 @@ def _polar_fwd(X, band_meta, band_coef, contrast: int, eps: float, mag_offset, m
                weighted: bool, ph_offset, ph_scale, drop_first: bool):
     Xd = ops._dev(X)
     band = ops.as_band(band_meta, band_coef)
+    if band is None and Xd.ndim >= 2:       # no mel bank: both halves from one read of the spectrum
+        return ops.polar_fwd(X, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted, ph_offset, ph_scale, drop_first)
     F = Xd.shape[-1]
     n_mag = (band.n_out if band is not None else F) - int(drop_first)
     n_ph = F - int(drop_first)

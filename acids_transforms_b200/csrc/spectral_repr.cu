@@ -133,6 +133,13 @@ struct PhaseParams {
     int drop_first;
     float* out;
     int64_t out_clip_stride, out_row_stride;
+    // MAGC >= 0 only: the band-less Magnitude of the same spectrum, written from the same pass
+    float* mag_out;
+    int64_t mag_clip_stride, mag_row_stride;
+    int contrast;
+    float eps;
+    const float* mag_offset_ptr;
+    const float* mag_scale_ptr;
 };
 
 #define ACIDS_PI_F 3.14159265358979323846f
@@ -187,7 +194,10 @@ __device__ __forceinline__ float if_weight(int t, int T) {
 // frames only depend on the raw spectrum: they are loaded and evaluated as a block (memory- and instruction-level
 // parallelism); only the running sum and the differences run serially, in torch.cumsum's order.
 // MODE / METHOD / WEIGHTED are compile-time: no branching per element.
-template <int MODE, int METHOD, bool WEIGHTED>
+// MAGC >= 0 (a contrast id): Polar / PolarIF without a mel bank (SpectralRepresentation.forward, spectral_repr.py:434-440)
+// — the thread already holds X, so |X| -> contrast -> normalise goes to the magnitude slot from the same load instead
+// of a second pass over the spectrum (same arithmetic as mag_epilogue_kernel<BAND_NONE>).
+template <int MODE, int METHOD, bool WEIGHTED, int MAGC>
 __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
     constexpr int KB = 8;
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +215,14 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
         if (WEIGHTED) v *= if_weight(t, T);
         stg_stream1(out + t * os, (v - off) * inv);
     };
+    float* __restrict__ mout = MAGC >= 0 ? p.mag_out + b * p.mag_clip_stride + (f - p.drop_first) : nullptr;
+    float mgain = 1.f, mbias = 0.f;
+    if (MAGC >= 0) {     // (x - offset) / scale as one FFMA with the lg2 constant folded in, like make_epi_args
+        const float moff = p.mag_offset_ptr ? __ldg(p.mag_offset_ptr) : 0.f;
+        const float minv = p.mag_scale_ptr ? 1.0f / __ldg(p.mag_scale_ptr) : 1.0f;
+        mgain = minv * contrast_gain(MAGC);
+        mbias = -moff * minv;
+    }
     float prev_raw = 0.f, cum = 0.f;
     float u1 = 0.f, u2 = 0.f;   // unwrapped phase at t-1, t-2
     // EDGE = false: every frame of the block is interior (1 <= t, t + 1 <= T - 2): no bounds or first / last frame cases
@@ -216,6 +234,13 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
         for (int k = 0; k < KB; ++k) {
             a[k] = (!EDGE || t0 + k < T) ? ldg_stream2(xp) : make_float2(1.f, 0.f);
             xp += xs;
+        }
+        if (MAGC >= 0) {
+#pragma unroll
+            for (int k = 0; k < KB; ++k)
+                if (!EDGE || t0 + k < T)
+                    stg_stream1(mout + (int64_t)(t0 + k) * p.mag_row_stride,
+                                fmaf(contrast_core<MAGC>(fast_sqrt(a[k].x * a[k].x + a[k].y * a[k].y), p.eps), mgain, mbias));
         }
 #pragma unroll
         for (int k = 0; k < KB; ++k) rawv[k] = fast_atan2f(a[k].y, a[k].x);
@@ -268,14 +293,25 @@ __global__ void __launch_bounds__(128) phase_fwd_kernel(const PhaseParams p) {
 }
 
 typedef void (*PhaseFwdKernel)(const PhaseParams);
-static PhaseFwdKernel pick_phase_kernel(int mode, int method, int weighted) {
-    if (mode == ACIDS_PHASE_RAW) return phase_fwd_kernel<ACIDS_PHASE_RAW, 0, false>;
-    if (mode == ACIDS_PHASE_UNWRAP) return phase_fwd_kernel<ACIDS_PHASE_UNWRAP, 0, false>;
-#define ACIDS_IFK(M) (weighted ? phase_fwd_kernel<ACIDS_PHASE_IF, M, true> : phase_fwd_kernel<ACIDS_PHASE_IF, M, false>)
+template <int MAGC>
+static PhaseFwdKernel pick_phase_kernel_c(int mode, int method, int weighted) {
+    if (mode == ACIDS_PHASE_RAW) return phase_fwd_kernel<ACIDS_PHASE_RAW, 0, false, MAGC>;
+    if (mode == ACIDS_PHASE_UNWRAP) return phase_fwd_kernel<ACIDS_PHASE_UNWRAP, 0, false, MAGC>;
+#define ACIDS_IFK(M) (weighted ? phase_fwd_kernel<ACIDS_PHASE_IF, M, true, MAGC> : phase_fwd_kernel<ACIDS_PHASE_IF, M, false, MAGC>)
     if (method == ACIDS_IF_FORWARD) return ACIDS_IFK(ACIDS_IF_FORWARD);
     if (method == ACIDS_IF_BACKWARD) return ACIDS_IFK(ACIDS_IF_BACKWARD);
     return ACIDS_IFK(ACIDS_IF_CENTRAL);
 #undef ACIDS_IFK
+}
+// contrast < 0: phase only
+static PhaseFwdKernel pick_phase_kernel(int mode, int method, int weighted, int contrast = -1) {
+    switch (contrast) {
+        case ACIDS_CONTRAST_NONE: return pick_phase_kernel_c<ACIDS_CONTRAST_NONE>(mode, method, weighted);
+        case ACIDS_CONTRAST_LOG1P: return pick_phase_kernel_c<ACIDS_CONTRAST_LOG1P>(mode, method, weighted);
+        case ACIDS_CONTRAST_LOG: return pick_phase_kernel_c<ACIDS_CONTRAST_LOG>(mode, method, weighted);
+        case ACIDS_CONTRAST_LOG10: return pick_phase_kernel_c<ACIDS_CONTRAST_LOG10>(mode, method, weighted);
+        default: return pick_phase_kernel_c<-1>(mode, method, weighted);
+    }
 }
 
 struct PhaseInvParams {
@@ -507,6 +543,32 @@ extern "C" ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_fr
     const int64_t cols = B * n_bins;
     pick_phase_kernel(mode, if_method, p.weighted)<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("phase_fwd");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_polar_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, int contrast, float eps,
+                               const float* mag_offset, const float* mag_scale, int mode, int if_method, int weighted,
+                               const float* ph_offset, const float* ph_scale, int drop_first, float* mag_out,
+                               int64_t mag_clip_stride, int64_t mag_row_stride, float* ph_out, int64_t ph_clip_stride,
+                               int64_t ph_row_stride, void* stream) {
+    ACIDS_REQUIRE(X && mag_out && ph_out, ACIDS_EINVAL, "polar_fwd: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 31) && n_bins > 0, ACIDS_EINVAL, "polar_fwd: bad sizes");
+    ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
+    ACIDS_REQUIRE(mode >= 0 && mode <= 2 && if_method >= 0 && if_method <= 2, ACIDS_EINVAL, "polar_fwd: bad mode/method");
+    ACIDS_REQUIRE(!(mode == ACIDS_PHASE_IF && if_method == ACIDS_IF_CENTRAL && n_frames < 2), ACIDS_EINVAL,
+                  "polar_fwd: central differences need at least 2 frames");
+    ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
+    if (B == 0) return ACIDS_OK;
+    PhaseParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.B = B; p.n_frames = (int)n_frames; p.n_bins = n_bins;
+    p.mode = mode; p.method = if_method; p.weighted = (mode == ACIDS_PHASE_IF) ? weighted : 0;
+    p.offset_ptr = ph_offset; p.scale_ptr = ph_scale; p.drop_first = drop_first; p.out = ph_out;
+    p.out_clip_stride = ph_clip_stride; p.out_row_stride = ph_row_stride;
+    p.mag_out = mag_out; p.mag_clip_stride = mag_clip_stride; p.mag_row_stride = mag_row_stride;
+    p.contrast = contrast; p.eps = eps; p.mag_offset_ptr = mag_offset; p.mag_scale_ptr = mag_scale;
+    const int64_t cols = B * n_bins;
+    pick_phase_kernel(mode, if_method, p.weighted, contrast)<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("polar_fwd");
     return ACIDS_OK;
 }
 

@@ -371,6 +371,30 @@ def phase_fwd(X, mode: int, method="forward", weighted=False, offset=None, scale
     return _ret(out, X)
 
 
+def polar_fwd(X, contrast, eps, mag_offset, mag_scale, phase_mode: int, method="forward", weighted=False, ph_offset=None,
+              ph_scale=None, drop_first=False):
+    """Band-less Magnitude.forward and Phase/IF.forward of X [..., T, F] from one read of the spectrum, stacked:
+    -> float32 [..., T, 2, F - drop]  (SpectralRepresentation.forward with stack=-2, spectral_repr.py:434-440)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    if Xd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] spectrum)")
+    Xf, batch = _flat_batch(Xd, 2)
+    B, T, F = Xf.shape
+    n_keep = F - int(drop_first)
+    dev = Xf.device
+    out = torch.empty((B, T, 2, n_keep), dtype=torch.float32, device=dev)
+    flat = out.view(-1)
+    mo, ms = _scalar(mag_offset, dev), _scalar(mag_scale, dev)
+    po, ps = _scalar(ph_offset, dev), _scalar(ph_scale, dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_polar_fwd, _ptr(Xf), B, T, F, _cid(contrast), float(eps), _ptr(mo), _ptr(ms), phase_mode, _mid(method),
+                                       int(bool(weighted)), _ptr(po), _ptr(ps), int(drop_first),
+                                       _ptr(flat), T * 2 * n_keep, 2 * n_keep, _ptr(flat[n_keep:]), T * 2 * n_keep, 2 * n_keep,
+                                       _stream(dev))
+    return _ret(out.reshape(tuple(batch) + (T, 2, n_keep)), X)
+
+
 def phase_inv(y, mode: int, method="forward", offset=None, scale=None, pad_last=False):
     """Phase.invert / IF.invert: y [..., T, n_in] -> phase [..., T, n_in + pad]  (spectral_repr.py:46-53, :359-375)."""
     lib = _lib.load()

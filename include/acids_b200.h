@@ -147,6 +147,15 @@ ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_frames, int n
                     int drop_first, float* out, int64_t out_clip_stride, int64_t out_row_stride,
                     void* stream);
 
+/* SpectralRepresentation.forward for Polar / PolarIF without a mel bank (spectral_repr.py:434-440: magnitude(x),
+ * phase(x), stack): acids_mag_epilogue (band-less) and acids_phase_fwd from ONE read of the spectrum.  mag_out /
+ * ph_out rows like (2); both may point into the same stacked tensor.                                       */
+ACIDS_API int acids_polar_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, int contrast, float eps,
+                    const float* mag_offset, const float* mag_scale, int mode, int if_method, int weighted,
+                    const float* ph_offset, const float* ph_scale, int drop_first,
+                    float* mag_out, int64_t mag_clip_stride, int64_t mag_row_stride,
+                    float* ph_out, int64_t ph_clip_stride, int64_t ph_row_stride, void* stream);
+
 /* IF.invert (spectral_repr.py:359-375; fint_* utils/misc.py:82-104) and Phase.invert
  * (mode RAW/UNWRAP: de-normalise only).  y rows like (2) -> phase float32 [B, n_frames, n_bins]
  * (n_bins = n_in + pad_last).                                                                  */

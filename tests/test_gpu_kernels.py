@@ -300,6 +300,28 @@ def test_polar_golden(ops):
         assert torch.equal(torch.view_as_real(Zf).cpu(), torch.view_as_real(torch.from_numpy(Z))), tag + " fused inv"
 
 
+def test_polar_fwd_one_pass(ops):
+    """polar_fwd (one read of the spectrum) == mag_epilogue(band=None) + phase_fwd: every contrast, mode, method,
+    weighting and keep_nyquist=False; frame counts around the 8-frame blocks of the kernel."""
+    from acids_transforms_b200._lib import PHASE_IF, PHASE_RAW, PHASE_UNWRAP
+    g = torch.Generator(device="cuda").manual_seed(9)
+    mo, ms = torch.tensor([0.3], device="cuda"), torch.tensor([2.5], device="cuda")
+    po, ps = torch.tensor([-0.1], device="cuda"), torch.tensor([0.75], device="cuda")
+    cases = [(PHASE_RAW, "forward", False), (PHASE_UNWRAP, "forward", False), (PHASE_IF, "forward", False),
+             (PHASE_IF, "backward", True), (PHASE_IF, "central", False)]
+    for T in (2, 7, 8, 9, 26):
+        X = torch.view_as_complex(torch.randn(3, 2, T, 70, 2, device="cuda", generator=g))
+        for contrast in ("none", "log1p", "log", "log10"):
+            for mode, method, weighted in cases:
+                for drop in (False, True):
+                    got = ops.polar_fwd(X, contrast, EPS, mo, ms, mode, method, weighted, po, ps, drop)
+                    m = ops.mag_epilogue(X, None, contrast, EPS, mo, ms, drop)
+                    ph = ops.phase_fwd(X, mode, method, weighted, po, ps, drop)
+                    assert got.shape == (3, 2, T, 2, 70 - int(drop))
+                    torch.testing.assert_close(got[..., 0, :], m, rtol=1e-6, atol=1e-6)
+                    assert torch.equal(got[..., 1, :], ph), (T, contrast, mode, method, drop)
+
+
 def test_phase_inv_polar_variants(ops):
     """phase_inv_polar == polar_to_complex(mag, phase_inv(...)) bit for bit: every mode / method, strided input
     (the stacked [.., 2, F] layout), the appended zero bin, and the central method's two-kernel route."""

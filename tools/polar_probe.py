@@ -33,6 +33,20 @@ def main():
         ph = ops.phase_inv(y, mode, "forward")
         res[tag + "_polar"] = timeit(lambda: ops.polar_to_complex(mag, ph))
         res[tag + "_fused"] = timeit(lambda: ops.phase_inv_polar(y, mag, mode, "forward"))
+    del stacked, mag, ph
+    X = torch.view_as_complex(torch.randn(B, T, F, 2, device="cuda"))
+    one = torch.ones(1, device="cuda")
+    res["fwd_mag_epilogue"] = timeit(lambda: ops.mag_epilogue(X, None, "log1p", 1e-7, one, one))
+    res["fwd_phase_if"] = timeit(lambda: ops.phase_fwd(X, PHASE_IF, "forward", False, one, one))
+    res["fwd_polar_one_pass"] = timeit(lambda: ops.polar_fwd(X, "log1p", 1e-7, one, one, PHASE_IF, "forward", False, one, one))
+    del X
+    import acids_transforms_b200.transforms as Tr
+    x4 = 0.5 * (2 * torch.rand((256, 2, 176400), device="cuda") - 1)
+    ms_ = Tr.MidSide().cuda()
+    st = Tr.STFT(n_fft=4096, hop_length=1024).cuda()
+    res["fwd_midside"] = timeit(lambda: ms_(x4))
+    xm = ms_(x4)
+    res["fwd_stft4096"] = timeit(lambda: st(xm))
     print(json.dumps(res))
 
 
