@@ -27,7 +27,8 @@ struct InvParams {
     int chunk_frames;
     int chunks_per_clip;
     int ovc;                // ceil(n_fft / hop)
-    int ring;               // G + ovc - 1 slots
+    int ring;               // G + ovc - 1 slots (1 in accumulate mode)
+    int accum;              // one frame per CTA round, n_fft % hop == 0, hop % 4 == 0: the ring holds n_fft partial sums, not frames
 };
 
 // One spectrum row into registers, in the operand order of the paired first pass (bins k and M - k together).
@@ -97,7 +98,8 @@ __device__ __forceinline__ void inverse_frame(const FrameFFT<P, true>& fft, cons
 template <class P>
 struct InvCfg {
     // n_fft = 4096 (T = 128): one frame per CTA.  With two frames the ring (5 x 16 KB) leaves a single 8-warp CTA per
-    // SM whose warps all sit in the same phase; one frame per CTA (ring 4 x 16 KB, 103 KB) gives two independent CTAs.
+    // SM whose warps all sit in the same phase; one frame per CTA (ring 4 x 16 KB, 103 KB) gives two independent CTAs,
+    // and the accumulate mode of the kernel (16 KB of partial sums instead of the ring, 55 KB) three at 168 registers.
 #ifndef ACIDS_INV_T128_THREADS
 #define ACIDS_INV_T128_THREADS 128
 #endif
@@ -108,7 +110,7 @@ struct InvCfg {
     static constexpr int THREADS = P::T <= 32 ? ACIDS_INV_SMALL_THREADS
                                               : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : (P::T == 64 ? 128 : 256)));
     static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS)
-                                           : (P::T == 64 ? 3 : (P::T <= 256 ? 2 : 1));
+                                           : (P::T == 64 || P::T == 128 ? 3 : (P::T <= 256 ? 2 : 1));
     static constexpr int G = THREADS / P::T;
 };
 
@@ -138,6 +140,12 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     const bool aligned = (N % hop) == 0;             // integer overlap: every hop segment sees the same frames
     const int ov = N / hop;                          // (aligned) frames per hop segment
     const int out_len = (int)p.out_len;
+    // Accumulate mode (G == 1 plans, i.e. n_fft >= 4096): instead of the last ov windowed frames the CTA keeps ONE
+    // n_fft-sample buffer of partial overlap-add sums, sample n of frame t at (t hop + n) mod n_fft.  A frame's last
+    // hop samples open a new hop segment (assigned), the rest is added to what earlier frames left; after frame t the
+    // segment t is complete and is emitted.  Same summation order as the frame ring (ascending frames, like col2im),
+    // a quarter of the shared memory at hop = n_fft / 4: three CTAs per SM instead of two at n_fft = 4096.
+    const bool accum = G == 1 && p.accum != 0;
     // ring slot arithmetic without modulo: arguments stay within (-ring, 2 ring)
     auto wrap = [&](int sl) { return sl < 0 ? sl + p.ring : (sl >= p.ring ? sl - p.ring : sl); };
     if (aligned)
@@ -181,7 +189,28 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
         const bool valid = t < tb;
         cf v[V];
         inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
-        if (valid) {
+        if (G == 1 && accum) {
+            const int rot = (int)(((int64_t)t * hop) & (N - 1));
+            const bool first = tr == t_start;        // nothing of this run is in the buffer yet: every sample opens its segment
+            const int tail = N - hop;
+#pragma unroll
+            for (int b = 0; b < BL; ++b) {
+                const float2* wv = swin + (tid + T * b);
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int n = 2 * (tid + T * b + q * NSL);
+                    const float2 w = wv[q * NSL];
+                    const cf y = cmul2(v[b * RL + q], mk(w.x, w.y));
+                    float2* d = reinterpret_cast<float2*>(ring + ((rot + n) & (N - 1)));
+                    if (first || n >= tail) {
+                        *d = make_float2(y.x, y.y);
+                    } else {
+                        const float2 o = *d;
+                        *d = make_float2(o.x + y.x, o.y + y.y);
+                    }
+                }
+            }
+        } else if (valid) {
             float2* slot = reinterpret_cast<float2*>(ring + (size_t)wrap(base_slot + g) * N);
 #pragma unroll
             for (int b = 0; b < BL; ++b) {
@@ -225,6 +254,36 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                     const int t_lo = max(0, q - ov + 1), t_hi = min(nT - 1, q);
                     const int slot0 = wrap(base_slot + (t_lo - tr));
                     const int n0 = q * hop - p.trim;
+                    if (G == 1 && accum) {
+                        // the finished sums of segment q; interior segments take the precomputed inverse envelope
+                        const float* seg = ring + (int)(((int64_t)q * hop) & (N - 1));
+                        const bool interior = t_hi - t_lo + 1 == ov;
+                        for (int r = r_lo; r < r_hi; r += 128) {
+                            const float4 a = *reinterpret_cast<const float4*>(seg + r);
+                            float yy[4];
+                            if (interior) {
+                                const float4 e = *reinterpret_cast<const float4*>(inv_env + r);
+                                yy[0] = a.x * e.x; yy[1] = a.y * e.y; yy[2] = a.z * e.z; yy[3] = a.w * e.w;
+                            } else {
+                                float4 env = make_float4(0.f, 0.f, 0.f, 0.f);
+                                int o2 = r + (q - t_lo) * hop;
+                                for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
+                                    env.x += g2(o2); env.y += g2(o2 + 1); env.z += g2(o2 + 2); env.w += g2(o2 + 3);
+                                }
+                                yy[0] = a.x / env.x; yy[1] = a.y / env.y; yy[2] = a.z / env.z; yy[3] = a.w / env.w;
+                            }
+                            const int n = n0 + r;
+                            if (n >= 0 && n + 3 < out_len) {
+                                asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outc + n), "f"(yy[0]),
+                                             "f"(yy[1]), "f"(yy[2]), "f"(yy[3]) : "memory");
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (n + j >= 0 && n + j < out_len) stg_stream1(outc + n + j, yy[j]);
+                            }
+                        }
+                        continue;
+                    }
                     if (t_hi - t_lo + 1 == ov) {
                         // interior: ov frames, ascending frame order like torch.istft's col2im; loads issued together
                         auto run = [&](auto ovc_) {
@@ -429,9 +488,10 @@ template <class P>
 struct InvLaunch {
     static constexpr int THREADS = InvCfg<P>::THREADS;
     static constexpr int G = InvCfg<P>::G;
+    static bool accumulates(int hop) { return G == 1 && (P::N % hop) == 0 && (hop & 3) == 0; }
     static size_t smem_ola(int ovc, int hop) {
-        // exchange buffers | frame ring | window pairs | interior inverse envelope
-        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(G + ovc - 1) * P::N * sizeof(float) +
+        // exchange buffers | frame ring (or the partial sums) | window pairs | interior inverse envelope
+        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(accumulates(hop) ? 1 : G + ovc - 1) * P::N * sizeof(float) +
                (size_t)P::M * sizeof(float2) + (size_t)hop * sizeof(float);
     }
     static int ola(InvParams p, cudaStream_t st) {
@@ -447,7 +507,8 @@ struct InvLaunch {
             }
             reserved = smem;
         }
-        p.ring = G + p.ovc - 1;
+        p.accum = accumulates(p.hop) ? 1 : 0;
+        p.ring = p.accum ? 1 : G + p.ovc - 1;
         int& ctas_per_sm = pd.ctas_per_sm;
         size_t& occ_smem = pd.occ_smem;
         if (ctas_per_sm == 0 || occ_smem != smem) {

@@ -122,6 +122,28 @@ def test_fuzz_against_torch_on_device(ops):
             assert_parity(host(y), host(y_want), REL, "fuzz inv " + tag)
 
 
+def test_istft_partial_sum_mode(ops):
+    """n_fft >= 4096 with n_fft % hop == 0 keeps partial overlap-add sums instead of a frame ring: long clips in a small
+    batch (so that CTAs start and stop inside clips and recompute halo frames), every supported overlap, clip edges,
+    against torch.istft on the same GPU; the unaligned hop takes the frame-ring route of the same kernel."""
+    for n_fft, hop, B, T in ((4096, 1024, 3, 700), (4096, 2048, 2, 300), (4096, 512, 2, 500), (4096, 4096 // 16, 1, 400),
+                             (8192, 2048, 3, 250), (8192, 1024, 1, 300), (16384, 4096, 2, 90), (4096, 1000, 2, 300),
+                             (4096, 1024, 5, 2), (4096, 1024, 4, 3)):
+        g = torch.Generator(device="cuda").manual_seed(n_fft + hop + T)
+        w = torch.hann_window(n_fft, device="cuda")
+        X = torch.view_as_complex(torch.randn((B, T, n_fft // 2 + 1, 2), generator=g, device="cuda"))
+        X[..., 0] = X[..., 0].real + 0j
+        X[..., -1] = X[..., -1].real + 0j
+        tag = "n_fft=%d hop=%d B=%d T=%d" % (n_fft, hop, B, T)
+        assert ops.istft_envelope_ok(w, n_fft, hop, T), tag
+        want = torch.istft(X.transpose(-2, -1), n_fft, hop, window=w)
+        got = ops.istft_ola(X, w, n_fft, hop)
+        assert got.shape == want.shape, tag
+        assert_parity(host(got), host(want), REL, "istft partial sums " + tag)
+        again = ops.istft_ola(X, w, n_fft, hop)
+        assert torch.equal(got, again), "not deterministic: " + tag
+
+
 def test_stft_known_answers(ops):
     n, h = 1024, 256
     w = torch.hann_window(n).cuda()
