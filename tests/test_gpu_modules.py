@@ -159,6 +159,38 @@ def test_streaming_modules(T):
             assert_parity(host(out), g["out_%d" % i], REL, "stream out")
 
 
+def test_streaming_step_as_cuda_graph(T):
+    """GraphedStep: the block-by-block round trip replayed from a CUDA graph gives the numbers of the eager modules,
+    block after block (the carried state advances inside the graph), and reset() starts the stream over."""
+    import copy
+    from acids_transforms_b200.streaming import GraphedStep
+    for cls in (T.RealtimeSTFT, T.RealtimeDGT):
+        eager = (T.OverlapAdd(512, 128) + cls(n_fft=512, hop_length=128)).cuda()
+        graphed = copy.deepcopy(eager)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = 2 * torch.rand((3, 8 * 1024), generator=g, device="cuda") - 1
+        blocks = x.split(1024, -1)
+        step = GraphedStep(graphed, lambda b: graphed.invert(graphed(b)), blocks[0])
+        want = [eager.invert(eager(b)).clone() for b in blocks]
+        got = [step(b).clone() for b in blocks]
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert a.shape == b.shape
+            assert torch.equal(a, b), "%s block %d: max diff %g" % (cls.__name__, i, float((a - b).abs().max()))
+        # the stream reproduces the input delayed by the carried overlap, up to the reference's constant gain
+        # (analysis window x synthesis window / gain_compensation, oadd.py:40-47)
+        y = torch.cat(got, -1)
+        delay = 512 - 128
+        a, b = y[:, delay + 512:], x[:, 512:x.shape[1] - delay]
+        gain = float((a * b).sum() / (b * b).sum())
+        assert float((a - gain * b).abs().max()) < 1e-4 * max(1.0, abs(gain))
+        step.reset()
+        again = [step(b).clone() for b in blocks[:3]]
+        for a, b in zip(again, want[:3]):
+            assert torch.equal(a, b)
+        with pytest.raises(RuntimeError):
+            step(x[:, :512])
+
+
 def test_phaseless_inversion(T):
     x = cu(load_golden("stft_1024_256")["x"])
     s = T.STFT(inversion_mode="keep_input").cuda()
