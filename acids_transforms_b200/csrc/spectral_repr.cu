@@ -21,38 +21,42 @@ struct MagParams {
     int64_t out_row_stride;
 };
 
-template <int BAND>
+template <int BAND, int ROWS>
 __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
-    // 8 rows per CTA iteration: each warp stages |X| of one row, then the CTA projects the rows together (tiles of 4)
+    // ROWS rows per CTA iteration: 8 / ROWS warps stage |X| of one row, then the CTA projects the rows together (tiles
+    // of 4).  ROWS = 4 for long rows (n_fft >= 2048): half the shared memory, twice the resident CTAs to overlap one
+    // CTA's staging loads with another's projection.
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WPR = 8 / ROWS;                      // warps per row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wrow = warp / WPR, wsub = warp % WPR;
     const int stride = (p.n_bins + 3) & ~3;
     float* val = reinterpret_cast<float*>(smem_raw);
-    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)8 * stride * sizeof(float));
-    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)8 * stride * sizeof(float) + p.ep.band_bytes_meta);
+    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)ROWS * stride * sizeof(float));
+    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)ROWS * stride * sizeof(float) + p.ep.band_bytes_meta);
     if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
     const EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef,
                                      p.offset_ptr, p.scale_ptr);
     __syncthreads();
-    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < p.rows; r0 += (int64_t)gridDim.x * 8) {
-        const int64_t r = r0 + warp;
+    for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < p.rows; r0 += (int64_t)gridDim.x * ROWS) {
+        const int64_t r = r0 + wrow;
         if (r < p.rows) {
             const float2* __restrict__ row = p.X + r * p.n_bins;
             // 8 independent loads in flight per lane before the first use (the row is streamed once)
-            for (int k0 = lane; k0 < p.n_bins; k0 += 32 * 8) {
+            for (int k0 = lane + 256 * wsub; k0 < p.n_bins; k0 += 256 * WPR) {
                 float2 a[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (k0 + 32 * j < p.n_bins) val[warp * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
+                    if (k0 + 32 * j < p.n_bins) val[wrow * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
             }
         }
         __syncthreads();
-        const int n_valid = (int)min((int64_t)8, p.rows - r0);
+        const int n_valid = (int)min((int64_t)ROWS, p.rows - r0);
         const int rs = (int)p.out_row_stride;
 #pragma unroll 1
-        for (int g0 = 0; g0 < 8 && g0 < n_valid; g0 += 4)
+        for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += 4)
             epilogue_dispatch<256, 4, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
                                                        p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
         __syncthreads();
@@ -78,41 +82,45 @@ struct MagInvParams {
 // 8 rows per CTA iteration: each warp de-normalises and inverts the contrast of one row into shared memory, then the
 // CTA applies the banded inverse matrix to the rows together with the forward kernels' row-tile epilogue (tiles of 4,
 // identity contrast and normalisation): per-column metadata and coefficients are fetched once per 4 rows.
-template <int BAND>
+template <int BAND, int ROWS>
 __global__ void __launch_bounds__(256) mag_invert_kernel(const MagInvParams p) {
+    // ROWS rows per CTA iteration, 8 / ROWS warps stage one row.  ncu (cfg 4, 8 rows, 8 loads per lane): 2 CTAs / SM,
+    // long-scoreboard bound at 41 % of HBM peak -> ROWS = 4 for long rows (3 CTAs / SM) and 16 loads in flight per lane.
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WPR = 8 / ROWS, U = 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wrow = warp / WPR, wsub = warp % WPR;
     const int n_val = p.n_in + p.pad_last;
     const int stride = (n_val + 3) & ~3;
     float* val = reinterpret_cast<float*>(smem_raw);
-    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)8 * stride * sizeof(float));
-    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)8 * stride * sizeof(float) + p.ep.band_bytes_meta);
+    int32_t* smeta = reinterpret_cast<int32_t*>(smem_raw + (size_t)ROWS * stride * sizeof(float));
+    float* scoef = reinterpret_cast<float*>(smem_raw + (size_t)ROWS * stride * sizeof(float) + p.ep.band_bytes_meta);
     if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
     EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef, nullptr, nullptr);
     const float off = p.offset_ptr ? __ldg(p.offset_ptr) : 0.f;
     const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
     __syncthreads();
-    for (int64_t r0 = (int64_t)blockIdx.x * 8; r0 < p.rows; r0 += (int64_t)gridDim.x * 8) {
-        const int64_t r = r0 + warp;
+    for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < p.rows; r0 += (int64_t)gridDim.x * ROWS) {
+        const int64_t r = r0 + wrow;
         if (r < p.rows) {
             const float* __restrict__ row = p.y + r * p.y_row_stride;
-            // 8 independent loads in flight per lane before the first use
-            for (int k0 = lane; k0 < n_val; k0 += 32 * 8) {
-                float a[8];
+            // U independent loads in flight per lane before the first use
+            for (int k0 = lane + 32 * U * wsub; k0 < n_val; k0 += 32 * U * WPR) {
+                float a[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = (k0 + 32 * j < p.n_in) ? __ldg(row + k0 + 32 * j) : 0.f;
+                for (int j = 0; j < U; ++j) a[j] = (k0 + 32 * j < p.n_in) ? __ldg(row + k0 + 32 * j) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < U; ++j) {
                     const int k = k0 + 32 * j;
                     // the zero pad is appended BEFORE the contrast inversion (spectral_repr.py:230-234)
-                    if (k < n_val) val[warp * stride + k] = invert_contrast(k < p.n_in ? a[j] * sc + off : 0.f, p.contrast, p.eps);
+                    if (k < n_val) val[wrow * stride + k] = invert_contrast(k < p.n_in ? a[j] * sc + off : 0.f, p.contrast, p.eps);
                 }
             }
         }
         __syncthreads();
-        const int n_valid = (int)min((int64_t)8, p.rows - r0);
+        const int n_valid = (int)min((int64_t)ROWS, p.rows - r0);
 #pragma unroll 1
-        for (int g0 = 0; g0 < 8 && g0 < n_valid; g0 += 4)
+        for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += 4)
             epilogue_dispatch<256, 4, ACIDS_CONTRAST_NONE, BAND, false>(0, val + g0 * stride, stride, threadIdx.x, ea,
                                                                         p.out + (r0 + g0) * (int64_t)p.n_out, p.n_out, 1, n_valid - g0);
         __syncthreads();
@@ -480,14 +488,19 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     if (rows == 0) return ACIDS_OK;
     MagParams p{};
     p.X = reinterpret_cast<const float2*>(X); p.rows = rows; p.n_bins = n_bins;
-    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, 24 * 1024);
+    const int rows_per_iter = n_bins > 1024 ? 4 : 8;
+    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, rows_per_iter == 4 ? 40 * 1024 : 24 * 1024);
     if (rc) return rc;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
-    const size_t smem = (size_t)8 * ((n_bins + 3) & ~3) * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
-    auto kern = !band.meta ? mag_epilogue_kernel<BAND_NONE> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM> : mag_epilogue_kernel<BAND_GLOBAL>);
+    const size_t smem = (size_t)rows_per_iter * ((n_bins + 3) & ~3) * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
+    void (*kern)(const MagParams);
+    if (rows_per_iter == 4)
+        kern = !band.meta ? mag_epilogue_kernel<BAND_NONE, 4> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM, 4> : mag_epilogue_kernel<BAND_GLOBAL, 4>);
+    else
+        kern = !band.meta ? mag_epilogue_kernel<BAND_NONE, 8> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM, 8> : mag_epilogue_kernel<BAND_GLOBAL, 8>);
     ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
                   ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
-    int64_t grid = (rows + 7) / 8;
+    int64_t grid = (rows + rows_per_iter - 1) / rows_per_iter;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
     kern<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
@@ -510,14 +523,20 @@ extern "C" ACIDS_API int acids_mag_invert(const float* y, int64_t rows, int n_in
     if (rc) return rc;
     p.n_out = p.ep.n_cols;
     p.contrast = contrast; p.eps = eps; p.offset_ptr = offset; p.scale_ptr = scale; p.out = out;
-    const size_t rows_bytes = (size_t)8 * ((n_in + pad_last + 3) & ~3) * sizeof(float);
+    const int rows_per_iter = n_in > 1024 ? 4 : 8;
+    const size_t rows_bytes = (size_t)rows_per_iter * ((n_in + pad_last + 3) & ~3) * sizeof(float);
     const size_t smem = rows_bytes + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
     ACIDS_REQUIRE(smem <= 227 * 1024, ACIDS_ENOTSUP, "mag_invert: %d bins exceed shared memory", n_in);
-    auto kern = !inverse_band.meta ? mag_invert_kernel<BAND_NONE>
-                                   : (p.ep.band_bytes_meta > 0 ? mag_invert_kernel<BAND_SMEM> : mag_invert_kernel<BAND_GLOBAL>);
+    void (*kern)(const MagInvParams);
+    if (rows_per_iter == 4)
+        kern = !inverse_band.meta ? mag_invert_kernel<BAND_NONE, 4>
+                                  : (p.ep.band_bytes_meta > 0 ? mag_invert_kernel<BAND_SMEM, 4> : mag_invert_kernel<BAND_GLOBAL, 4>);
+    else
+        kern = !inverse_band.meta ? mag_invert_kernel<BAND_NONE, 8>
+                                  : (p.ep.band_bytes_meta > 0 ? mag_invert_kernel<BAND_SMEM, 8> : mag_invert_kernel<BAND_GLOBAL, 8>);
     ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
                   ACIDS_ECUDA, "mag_invert: cannot reserve %zu B of shared memory", smem);
-    int64_t grid = (rows + 7) / 8;
+    int64_t grid = (rows + rows_per_iter - 1) / rows_per_iter;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
     kern<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
