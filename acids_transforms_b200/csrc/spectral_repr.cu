@@ -42,13 +42,14 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
         const int64_t r = r0 + wrow;
         if (r < p.rows) {
             const float2* __restrict__ row = p.X + r * p.n_bins;
-            // 8 independent loads in flight per lane before the first use (the row is streamed once)
-            for (int k0 = lane + 256 * wsub; k0 < p.n_bins; k0 += 256 * WPR) {
-                float2 a[8];
+            // U independent loads in flight per lane before the first use (the row is streamed once)
+            constexpr int U = ROWS == 4 ? 16 : 8;
+            for (int k0 = lane + 32 * U * wsub; k0 < p.n_bins; k0 += 32 * U * WPR) {
+                float2 a[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
+                for (int j = 0; j < U; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < U; ++j)
                     if (k0 + 32 * j < p.n_bins) val[wrow * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
             }
         }
