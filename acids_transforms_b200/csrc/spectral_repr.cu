@@ -180,6 +180,18 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
     return copysignf(r, y);
 }
 
+// exp(i x) for the polar recombination (spectral_repr.py:452).  ncu showed phase_inv_kernel<POLAR> issue bound (82 % of
+// issue slots) on sincosf's ~40 instructions.  Here: x is reduced to [-pi, pi] by the nearest multiple of 2 pi (two-constant
+// Cody-Waite, the products exact inside the FMAs), then the SFU sine / cosine (|abs error| <= 2^-21.4 on that interval):
+// |error| < 1e-6 absolute for |x| up to ~1e5 rad, two orders below the 1e-4 parity budget.  exp(i 0) = 1 exactly.
+__device__ __forceinline__ void polar_sincos(float x, float* s, float* c) {
+    const float k = rintf(x * ACIDS_INV_2PI_F);
+    float r = fmaf(k, -6.2831854820251465f, x);      // float(2 pi)
+    r = fmaf(k, 1.7484555e-7f, r);                   // float(2 pi) - 2 pi
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
 __device__ __forceinline__ float unwrap_correction(float d) {
     // utils/misc.py:19-24: ddmod = (d + pi) % 2pi - pi (python remainder); +pi when it lands on -pi going up
     // d is a difference of two principal values, so x = d + pi lies in [-pi, 3 pi]: the float remainder (exact, like
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(128) phase_inv_kernel(const PhaseInvParams p) 
     auto emit = [&](int t, float ph, float m) {
         if constexpr (POLAR) {
             float s, c;
-            sincosf(ph, &s, &c);
+            polar_sincos(ph, &s, &c);
             stg_stream2(reinterpret_cast<float2*>(out) + (int64_t)t * nb, m * c, m * s);
         } else {
             out[(int64_t)t * nb] = ph;
@@ -424,7 +436,8 @@ __global__ void __launch_bounds__(128) phase_inv_kernel(const PhaseInvParams p) 
     }
 }
 
-// four bins per thread: 16-byte loads of mag and phase, two 16-byte streaming stores
+// four bins per thread: 16-byte loads of mag and phase, two 16-byte streaming stores.  Library sincosf here: this
+// kernel is memory bound either way and measured 9 % SLOWER with polar_sincos (0.54 -> 0.59 ms at the cfg-4 shape)
 __global__ void __launch_bounds__(256) polar_to_complex_kernel(const float* __restrict__ mag, const float* __restrict__ phase, int64_t n,
                                                                float2* __restrict__ out) {
     const bool vec = ((reinterpret_cast<uintptr_t>(mag) | reinterpret_cast<uintptr_t>(phase) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;

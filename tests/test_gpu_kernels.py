@@ -317,9 +317,10 @@ def test_polar_golden(ops):
         p = ops.phase_inv(gy[..., 1, :], mode, "forward", po, ps)
         Z = host(ops.polar_to_complex(m, p))
         assert_parity(Z, g[tag + "_inv"], REL, tag + " inv")
-        # the one-pass form the modules use must be the same numbers, not merely close
-        Zf = ops.phase_inv_polar(gy[..., 1, :], m, mode, "forward", po, ps)
-        assert torch.equal(torch.view_as_real(Zf).cpu(), torch.view_as_real(torch.from_numpy(Z))), tag + " fused inv"
+        # the one-pass form the modules use: same phase, SFU sine / cosine (see test_polar_recombination_accuracy)
+        Zf = host(ops.phase_inv_polar(gy[..., 1, :], m, mode, "forward", po, ps))
+        assert_parity(Zf, g[tag + "_inv"], REL, tag + " fused inv")
+        assert float(np.abs(Zf - Z).max()) <= 4e-6 * float(np.abs(Z).max()), tag + " fused vs two kernels"
 
 
 def test_polar_fwd_one_pass(ops):
@@ -344,9 +345,29 @@ def test_polar_fwd_one_pass(ops):
                     assert torch.equal(got[..., 1, :], ph), (T, contrast, mode, method, drop)
 
 
+def test_polar_recombination_accuracy(ops):
+    """phase_inv_polar evaluates exp(i phase) with a 2-pi reduction + the SFU sine / cosine: absolute error against
+    float64 stays below 2e-6 * mag for integrated phases of thousands of radians (parity budget 1e-4), exp(i 0) is
+    exact; polar_to_complex (library sincosf) is held to 5e-7."""
+    from acids_transforms_b200._lib import PHASE_RAW
+    g = torch.Generator(device="cuda").manual_seed(21)
+    for span in (3.2, 700.0, 3.0e4):
+        ph = (2 * torch.rand((4, 16, 4099), generator=g, device="cuda") - 1) * span
+        mag = torch.rand((4, 16, 4099), generator=g, device="cuda") + 0.5
+        p64, m64 = ph.double().cpu(), mag.double().cpu()
+        want = torch.stack([m64 * torch.cos(p64), m64 * torch.sin(p64)], -1)
+        for fn, bound in ((lambda: ops.phase_inv_polar(ph, mag, PHASE_RAW), 2e-6), (lambda: ops.polar_to_complex(mag, ph), 5e-7)):
+            got = torch.view_as_real(fn()).double().cpu()
+            err = float(((got - want).abs() / m64[..., None]).max())
+            assert err < bound, "span %g: %.3e" % (span, err)
+    one = ops.phase_inv_polar(torch.zeros(2, 8, device="cuda"), torch.full((2, 8), 3.0, device="cuda"), PHASE_RAW)
+    assert torch.equal(torch.view_as_real(one).cpu(), torch.tensor([3.0, 0.0]).expand(2, 8, 2))
+
+
 def test_phase_inv_polar_variants(ops):
-    """phase_inv_polar == polar_to_complex(mag, phase_inv(...)) bit for bit: every mode / method, strided input
-    (the stacked [.., 2, F] layout), the appended zero bin, and the central method's two-kernel route."""
+    """phase_inv_polar == polar_to_complex(mag, phase_inv(...)) up to the SFU sine / cosine (4e-6 * mag): every mode /
+    method, strided input (the stacked [.., 2, F] layout), the appended zero bin, and the central method's two-kernel
+    route (identical bits); the one-pass kernel itself is deterministic."""
     from acids_transforms_b200._lib import PHASE_IF, PHASE_RAW, PHASE_UNWRAP
     g = torch.Generator(device="cuda").manual_seed(5)
     stacked = torch.randn(3, 2, 17, 2, 96, device="cuda", generator=g)
@@ -359,10 +380,15 @@ def test_phase_inv_polar_variants(ops):
             want = ops.polar_to_complex(mag, ops.phase_inv(y, mode, method, off, sc, pad))
             got = ops.phase_inv_polar(y, mag, mode, method, off, sc, pad)
             assert got.shape == want.shape and got.dtype == torch.complex64
-            assert torch.equal(torch.view_as_real(got), torch.view_as_real(want)), (mode, method, pad)
+            a, b = torch.view_as_real(got), torch.view_as_real(want)
+            if method == "central":
+                assert torch.equal(a, b), (mode, method, pad)
+            else:
+                assert float(((a - b).abs() / mag[..., None]).max()) <= 4e-6, (mode, method, pad)
+                assert torch.equal(a, torch.view_as_real(ops.phase_inv_polar(y, mag, mode, method, off, sc, pad)))
     one = ops.phase_inv_polar(y[0, 0], torch.ones(17, 96, device="cuda"), PHASE_IF, "backward")
     ref = ops.polar_to_complex(torch.ones(17, 96, device="cuda"), ops.phase_inv(y[0, 0], PHASE_IF, "backward"))
-    assert torch.equal(torch.view_as_real(one), torch.view_as_real(ref))
+    assert float((torch.view_as_real(one) - torch.view_as_real(ref)).abs().max()) <= 4e-6
 
 
 # ---------------------------------------------------------------------------------------------
