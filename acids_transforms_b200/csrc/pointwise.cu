@@ -193,25 +193,48 @@ __global__ void mono_mix_kernel(const float* __restrict__ x, int64_t B, int64_t 
     }
 }
 
-__global__ void midside_kernel(const float* __restrict__ x, int64_t B, int64_t L, int pad_mid, int inverse,
-                               float* __restrict__ out) {
+__device__ __forceinline__ void midside_pair(float a, float c, int pad_mid, int inverse, float& o0, float& o1) {
     const float rt2 = 1.41421356237309504880f;   // float32(math.sqrt(2))
-    const int64_t n = B * L;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / L, j = i - b * L;
-        const float a = __ldg(x + (2 * b) * L + j), c = __ldg(x + (2 * b + 1) * L + j);
-        float o0, o1;
-        if (!inverse) {        // raw.py:155-160
-            o0 = __fdiv_rn(__fadd_rn(a, c), 2.0f);
-            o1 = __fdiv_rn(__fadd_rn(a, -c), 2.0f);
-            if (pad_mid) o0 = __fdiv_rn(o0, rt2);
-        } else {               // raw.py:172-178
-            const float mid = pad_mid ? __fmul_rn(a, rt2) : a;
-            o0 = __fadd_rn(mid, c);
-            o1 = __fadd_rn(mid, -c);
+    if (!inverse) {        // raw.py:155-160; x / 2 == x * 0.5 exactly, the division by sqrt(2) stays an IEEE division
+        o0 = __fmul_rn(__fadd_rn(a, c), 0.5f);
+        o1 = __fmul_rn(__fadd_rn(a, -c), 0.5f);
+        if (pad_mid) o0 = __fdiv_rn(o0, rt2);
+    } else {               // raw.py:172-178
+        const float mid = pad_mid ? __fmul_rn(a, rt2) : a;
+        o0 = __fadd_rn(mid, c);
+        o1 = __fadd_rn(mid, -c);
+    }
+}
+
+// grid = (chunks of a clip, clips): no division per element; 16-byte accesses when the clip rows allow it
+__global__ void __launch_bounds__(256) midside_kernel(const float* __restrict__ x, int64_t B, int64_t L, int pad_mid, int inverse,
+                                                      float* __restrict__ out) {
+    const bool vec = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* __restrict__ x0 = x + 2 * b * L;
+        const float* __restrict__ x1 = x0 + L;
+        float* __restrict__ y0 = out + 2 * b * L;
+        float* __restrict__ y1 = y0 + L;
+        if (vec) {
+            for (int64_t j = j0; j < (L >> 2); j += step) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(x0) + j), c = __ldg(reinterpret_cast<const float4*>(x1) + j);
+                float4 p, q;
+                midside_pair(a.x, c.x, pad_mid, inverse, p.x, q.x);
+                midside_pair(a.y, c.y, pad_mid, inverse, p.y, q.y);
+                midside_pair(a.z, c.z, pad_mid, inverse, p.z, q.z);
+                midside_pair(a.w, c.w, pad_mid, inverse, p.w, q.w);
+                reinterpret_cast<float4*>(y0)[j] = p;
+                reinterpret_cast<float4*>(y1)[j] = q;
+            }
+        } else {
+            for (int64_t j = j0; j < L; j += step) {
+                float p, q;
+                midside_pair(__ldg(x0 + j), __ldg(x1 + j), pad_mid, inverse, p, q);
+                y0[j] = p;
+                y1[j] = q;
+            }
         }
-        out[(2 * b) * L + j] = o0;
-        out[(2 * b + 1) * L + j] = o1;
     }
 }
 
@@ -430,7 +453,12 @@ extern "C" ACIDS_API int acids_midside(const float* x, int64_t B, int64_t L, int
     ACIDS_REQUIRE(x && out, ACIDS_EINVAL, "midside: NULL pointer");
     ACIDS_REQUIRE(B >= 0 && L >= 0, ACIDS_EINVAL, "midside: bad sizes");
     if (B * L == 0) return ACIDS_OK;
-    midside_kernel<<<grid_for(B * L, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, B, L, pad_mid, inverse, out);
+    const int64_t per_clip = ((L & 3) == 0 ? L / 4 : L);
+    int64_t gx = (per_clip + 255) / 256;
+    if (gx > 4096) gx = 4096;
+    if (gx < 1) gx = 1;
+    const int64_t gy = B < 65535 ? B : 65535;
+    midside_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, B, L, pad_mid, inverse, out);
     ACIDS_CHECK_LAUNCH("midside");
     return ACIDS_OK;
 }

@@ -482,6 +482,20 @@ def test_raw_golden(ops):
     assert_parity(host(ops.midside(x)), g["midside"], 1e-6, "midside")
     assert_parity(host(ops.midside(cu(g["midside"]), inverse=True)), g["midside_inv"], 1e-6, "midside inv")
     assert_parity(host(ops.midside(x, pad_mid=False)), g["midside_nopad"], 1e-6, "midside nopad")
+    # bit-exact against the reference's arithmetic (raw.py:155-178) evaluated by torch on the CPU (IEEE division; torch's
+    # CUDA kernel multiplies by the reciprocal of a scalar divisor instead): vector (L % 4 == 0) and scalar (odd L) routes
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for shape in ((3, 2, 4096), (5, 7, 2, 1001), (1, 2, 3), (70, 2, 260)):
+        z = 2 * torch.rand(shape, generator=gen, device="cuda") - 1
+        zc = z.cpu()
+        left, right = zc[..., 0, :], zc[..., 1, :]
+        mid, side = (left + right) / 2, (left - right) / 2
+        want = torch.stack([mid / math.sqrt(2), side], -2)
+        got = ops.midside(z)
+        assert torch.equal(got.cpu(), want), shape
+        back = ops.midside(got, inverse=True).cpu()
+        m2 = want[..., 0, :] * math.sqrt(2)
+        assert torch.equal(back, torch.stack([m2 + want[..., 1, :], m2 - want[..., 1, :]], -2)), shape
 
 
 def test_normalize_stats_golden(ops):
