@@ -21,13 +21,15 @@ struct MagParams {
     int64_t out_row_stride;
 };
 
-template <int BAND, int ROWS>
+template <int BAND, int ROWS, bool PF>
 __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
     // ROWS rows per CTA iteration: 8 / ROWS warps stage |X| of one row, then the CTA projects the rows together (tiles
-    // of 4).  ROWS = 4 for long rows (n_fft >= 2048): half the shared memory, twice the resident CTAs to overlap one
-    // CTA's staging loads with another's projection.
+    // of up to 4).  PF: a lane's share of the row fits 17 registers pairs, so the NEXT iteration's spectrum is loaded
+    // before this iteration's projection and lands while it runs (ncu on the unpipelined kernel: 57 % of the stall
+    // samples on the first use of the staging loads, the CTAs of an SM loading and projecting in lock-step).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WPR = 8 / ROWS;                      // warps per row
+    constexpr int NF = ROWS < 4 ? ROWS : 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wrow = warp / WPR, wsub = warp % WPR;
     const int stride = (p.n_bins + 3) & ~3;
@@ -38,29 +40,57 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
     const EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef,
                                      p.offset_ptr, p.scale_ptr);
     __syncthreads();
-    for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < p.rows; r0 += (int64_t)gridDim.x * ROWS) {
-        const int64_t r = r0 + wrow;
-        if (r < p.rows) {
-            const float2* __restrict__ row = p.X + r * p.n_bins;
-            // U independent loads in flight per lane before the first use (the row is streamed once)
-            constexpr int U = ROWS == 4 ? 16 : 8;
-            for (int k0 = lane + 32 * U * wsub; k0 < p.n_bins; k0 += 32 * U * WPR) {
-                float2 a[U];
-#pragma unroll
-                for (int j = 0; j < U; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < U; ++j)
-                    if (k0 + 32 * j < p.n_bins) val[wrow * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
-            }
-        }
-        __syncthreads();
+    const int rs = (int)p.out_row_stride;
+    auto project = [&](int64_t r0) {
         const int n_valid = (int)min((int64_t)ROWS, p.rows - r0);
-        const int rs = (int)p.out_row_stride;
 #pragma unroll 1
-        for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += 4)
-            epilogue_dispatch<256, 4, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
-                                                       p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
-        __syncthreads();
+        for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += NF)
+            epilogue_dispatch<256, NF, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
+                                                        p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
+    };
+    const int64_t step = (int64_t)gridDim.x * ROWS;
+    if constexpr (PF) {
+        constexpr int U = 17;                          // 32 * WPR * U >= n_bins (checked by the launcher)
+        const int kl = lane + 32 * wsub;               // this lane's bins: kl + 32 * WPR * j
+        float2 a[U];
+        auto issue = [&](int64_t r0) {
+            const int64_t r = r0 + wrow;
+            const float2* __restrict__ row = p.X + r * p.n_bins + kl;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                a[j] = (r < p.rows && kl + 32 * WPR * j < p.n_bins) ? ldg_stream2(row + 32 * WPR * j) : make_float2(0.f, 0.f);
+        };
+        int64_t r0 = (int64_t)blockIdx.x * ROWS;
+        if (r0 < p.rows) issue(r0);
+        for (; r0 < p.rows; r0 += step) {
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (kl + 32 * WPR * j < p.n_bins) val[wrow * stride + kl + 32 * WPR * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
+            __syncthreads();
+            if (r0 + step < p.rows) issue(r0 + step);
+            project(r0);
+            __syncthreads();
+        }
+    } else {
+        for (int64_t r0 = (int64_t)blockIdx.x * ROWS; r0 < p.rows; r0 += step) {
+            const int64_t r = r0 + wrow;
+            if (r < p.rows) {
+                const float2* __restrict__ row = p.X + r * p.n_bins;
+                // U independent loads in flight per lane before the first use (the row is streamed once)
+                constexpr int U = ROWS == 4 ? 16 : 8;
+                for (int k0 = lane + 32 * U * wsub; k0 < p.n_bins; k0 += 32 * U * WPR) {
+                    float2 a[U];
+#pragma unroll
+                    for (int j = 0; j < U; ++j) a[j] = (k0 + 32 * j < p.n_bins) ? ldg_stream2(row + k0 + 32 * j) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < U; ++j)
+                        if (k0 + 32 * j < p.n_bins) val[wrow * stride + k0 + 32 * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
+                }
+            }
+            __syncthreads();
+            project(r0);
+            __syncthreads();
+        }
     }
 }
 
@@ -502,16 +532,26 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     if (rows == 0) return ACIDS_OK;
     MagParams p{};
     p.X = reinterpret_cast<const float2*>(X); p.rows = rows; p.n_bins = n_bins;
-    const int rows_per_iter = n_bins > 1024 ? 4 : 8;
-    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, rows_per_iter == 4 ? 40 * 1024 : 24 * 1024);
+    // rows per CTA iteration: the largest for which a lane's share of a row (n_bins / (32 * warps per row)) fits the 17
+    // prefetch registers; beyond 4352 bins the unpipelined 4-row kernel
+    const bool pf = n_bins <= 4352;
+    const int rows_per_iter = n_bins <= 544 ? 8 : (n_bins <= 1088 ? 4 : (n_bins <= 2176 ? 2 : (pf ? 1 : 4)));
+    const size_t rows_bytes = (size_t)rows_per_iter * ((n_bins + 3) & ~3) * sizeof(float);
+    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, rows_bytes <= 34 * 1024 ? 40 * 1024 : 24 * 1024);
     if (rc) return rc;
     p.offset_ptr = offset; p.scale_ptr = scale; p.out = out; p.out_row_stride = out_row_stride;
-    const size_t smem = (size_t)rows_per_iter * ((n_bins + 3) & ~3) * sizeof(float) + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
-    void (*kern)(const MagParams);
-    if (rows_per_iter == 4)
-        kern = !band.meta ? mag_epilogue_kernel<BAND_NONE, 4> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM, 4> : mag_epilogue_kernel<BAND_GLOBAL, 4>);
-    else
-        kern = !band.meta ? mag_epilogue_kernel<BAND_NONE, 8> : (p.ep.band_bytes_meta > 0 ? mag_epilogue_kernel<BAND_SMEM, 8> : mag_epilogue_kernel<BAND_GLOBAL, 8>);
+    const size_t smem = rows_bytes + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
+    const int bsel = !band.meta ? BAND_NONE : (p.ep.band_bytes_meta > 0 ? BAND_SMEM : BAND_GLOBAL);
+    void (*kern)(const MagParams) = nullptr;
+#define ACIDS_MAGK(R, P)                                                                                        \
+    kern = bsel == BAND_NONE ? mag_epilogue_kernel<BAND_NONE, R, P>                                             \
+                             : (bsel == BAND_SMEM ? mag_epilogue_kernel<BAND_SMEM, R, P> : mag_epilogue_kernel<BAND_GLOBAL, R, P>)
+    if (!pf) { ACIDS_MAGK(4, false); }
+    else if (rows_per_iter == 8) { ACIDS_MAGK(8, true); }
+    else if (rows_per_iter == 4) { ACIDS_MAGK(4, true); }
+    else if (rows_per_iter == 2) { ACIDS_MAGK(2, true); }
+    else { ACIDS_MAGK(1, true); }
+#undef ACIDS_MAGK
     ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
                   ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
     int64_t grid = (rows + rows_per_iter - 1) / rows_per_iter;
