@@ -21,14 +21,16 @@ struct MagParams {
     int64_t out_row_stride;
 };
 
-template <int BAND, int ROWS, bool PF>
-__global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
+template <int BAND, int ROWS, bool PF, int NT = 256>
+__global__ void __launch_bounds__(NT) mag_epilogue_kernel(const MagParams p) {
     // ROWS rows per CTA iteration: 8 / ROWS warps stage |X| of one row, then the CTA projects the rows together (tiles
     // of up to 4).  PF: a lane's share of the row fits 17 registers pairs, so the NEXT iteration's spectrum is loaded
     // before this iteration's projection and lands while it runs (ncu on the unpipelined kernel: 57 % of the stall
     // samples on the first use of the staging loads, the CTAs of an SM loading and projecting in lock-step).
+    // NT = 512 for rows of 1089 .. 4352 bins: 4 (2) rows per iteration keep the 4-row (2-row) projection tiles while a
+    // lane's share still fits the prefetch registers (with 256 threads and 2-row tiles the kernel is MIO bound instead).
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int WPR = 8 / ROWS;                      // warps per row
+    constexpr int WPR = (NT / 32) / ROWS;              // warps per row
     constexpr int NF = ROWS < 4 ? ROWS : 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wrow = warp / WPR, wsub = warp % WPR;
@@ -45,8 +47,8 @@ __global__ void __launch_bounds__(256) mag_epilogue_kernel(const MagParams p) {
         const int n_valid = (int)min((int64_t)ROWS, p.rows - r0);
 #pragma unroll 1
         for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += NF)
-            epilogue_dispatch<256, NF, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
-                                                        p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
+            epilogue_dispatch<NT, NF, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
+                                                       p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
     };
     const int64_t step = (int64_t)gridDim.x * ROWS;
     if constexpr (PF) {
@@ -535,7 +537,8 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     // rows per CTA iteration: the largest for which a lane's share of a row (n_bins / (32 * warps per row)) fits the 17
     // prefetch registers; beyond 4352 bins the unpipelined 4-row kernel
     const bool pf = n_bins <= 4352;
-    const int rows_per_iter = n_bins <= 544 ? 8 : (n_bins <= 1088 ? 4 : (n_bins <= 2176 ? 2 : (pf ? 1 : 4)));
+    const int threads = (pf && n_bins > 1088) ? 512 : 256;
+    const int rows_per_iter = n_bins <= 544 ? 8 : (n_bins <= 2176 ? 4 : (pf ? 2 : 4));
     const size_t rows_bytes = (size_t)rows_per_iter * ((n_bins + 3) & ~3) * sizeof(float);
     rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, rows_bytes <= 34 * 1024 ? 40 * 1024 : 24 * 1024);
     if (rc) return rc;
@@ -543,21 +546,21 @@ extern "C" ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_
     const size_t smem = rows_bytes + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
     const int bsel = !band.meta ? BAND_NONE : (p.ep.band_bytes_meta > 0 ? BAND_SMEM : BAND_GLOBAL);
     void (*kern)(const MagParams) = nullptr;
-#define ACIDS_MAGK(R, P)                                                                                        \
-    kern = bsel == BAND_NONE ? mag_epilogue_kernel<BAND_NONE, R, P>                                             \
-                             : (bsel == BAND_SMEM ? mag_epilogue_kernel<BAND_SMEM, R, P> : mag_epilogue_kernel<BAND_GLOBAL, R, P>)
-    if (!pf) { ACIDS_MAGK(4, false); }
-    else if (rows_per_iter == 8) { ACIDS_MAGK(8, true); }
-    else if (rows_per_iter == 4) { ACIDS_MAGK(4, true); }
-    else if (rows_per_iter == 2) { ACIDS_MAGK(2, true); }
-    else { ACIDS_MAGK(1, true); }
+#define ACIDS_MAGK(R, P, NT)                                                                                            \
+    kern = bsel == BAND_NONE ? mag_epilogue_kernel<BAND_NONE, R, P, NT>                                                 \
+                             : (bsel == BAND_SMEM ? mag_epilogue_kernel<BAND_SMEM, R, P, NT> : mag_epilogue_kernel<BAND_GLOBAL, R, P, NT>)
+    if (!pf) { ACIDS_MAGK(4, false, 256); }
+    else if (rows_per_iter == 8) { ACIDS_MAGK(8, true, 256); }
+    else if (threads == 256) { ACIDS_MAGK(4, true, 256); }
+    else if (rows_per_iter == 4) { ACIDS_MAGK(4, true, 512); }
+    else { ACIDS_MAGK(2, true, 512); }
 #undef ACIDS_MAGK
     ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
                   ACIDS_ECUDA, "mag_epilogue: cannot reserve %zu B of shared memory", smem);
     int64_t grid = (rows + rows_per_iter - 1) / rows_per_iter;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    kern<<<(unsigned)grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("mag_epilogue");
     return ACIDS_OK;
 }

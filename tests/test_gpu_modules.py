@@ -159,6 +159,27 @@ def test_streaming_modules(T):
             assert_parity(host(out), g["out_%d" % i], REL, "stream out")
 
 
+def test_magnitude_row_lengths(T):
+    """Magnitude.forward picks its CTA shape by row length (8 / 4 / 4 / 2 rows per iteration, 256 or 512 threads, the
+    unpipelined kernel beyond 4352 bins): every branch, with and without the mel bank, against the dense torch formula
+    (spectral_repr.py:215-226); row counts that leave partial tiles."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    for n_fft, rows in ((1024, 37), (2048, 21), (4096, 13), (8192, 7), (16384, 5)):
+        F = n_fft // 2 + 1
+        X = torch.view_as_complex(torch.randn((rows, F, 2), generator=g, device="cuda"))
+        for mel in (False, True):
+            if mel and n_fft > 8192:
+                continue                                  # a 8193 x 8193 dense bank only to check a branch the others cover
+            m = T.Magnitude(n_fft=n_fft, mel=mel, mode=None).cuda()
+            want = X.abs()
+            if mel:
+                want = want @ m.mel_bank[0] if m.mel_bank.ndim == 3 else want @ m.mel_bank
+            want = torch.log(1 + want)
+            got = m(X)
+            assert got.shape == want.shape
+            assert_parity(host(got), host(want), REL, "Magnitude n_fft=%d mel=%s" % (n_fft, mel))
+
+
 def test_streaming_step_as_cuda_graph(T):
     """GraphedStep: the block-by-block round trip replayed from a CUDA graph gives the numbers of the eager modules,
     block after block (the carried state advances inside the graph), and reset() starts the stream over."""
