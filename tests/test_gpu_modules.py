@@ -178,6 +178,11 @@ def test_magnitude_row_lengths(T):
             got = m(X)
             assert got.shape == want.shape
             assert_parity(host(got), host(want), REL, "Magnitude n_fft=%d mel=%s" % (n_fft, mel))
+            # and back (spectral_repr.py:228-240): exp(y) - 1, then the inverse bank
+            back = torch.exp(want) - 1
+            if mel:
+                back = back @ (m.inverse_mel_bank[0] if m.inverse_mel_bank.ndim == 3 else m.inverse_mel_bank)
+            assert_parity(host(m.invert(want)), host(back), REL, "Magnitude.invert n_fft=%d mel=%s" % (n_fft, mel))
 
 
 def test_streaming_step_as_cuda_graph(T):
