@@ -493,6 +493,7 @@ def test_raw_golden(ops):
         want = torch.stack([mid / math.sqrt(2), side], -2)
         got = ops.midside(z)
         assert torch.equal(got.cpu(), want), shape
+        assert torch.equal(ops.mono_mix(z).cpu(), zc.sum(-2) / 2), shape          # raw.py:39
         back = ops.midside(got, inverse=True).cpu()
         m2 = want[..., 0, :] * math.sqrt(2)
         assert torch.equal(back, torch.stack([m2 + want[..., 1, :], m2 - want[..., 1, :]], -2)), shape
