@@ -8,19 +8,19 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACIDS_B200_LIB") or os.path.join(_HERE, "libacids_b200.so")   # override: tuning builds only
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACIDS_OK, ACIDS_EINVAL, ACIDS_ENOTSUP, ACIDS_ECUDA, ACIDS_EWORKSPACE = 0, -1, -2, -3, -4
 CONTRAST_IDS = {None: 0, "none": 0, "log1p": 1, "log": 2, "log10": 3}
 IF_METHOD_IDS = {"forward": 0, "backward": 1, "central": 2}
 PHASE_RAW, PHASE_UNWRAP, PHASE_IF = 0, 1, 2
-STATS_REAL, STATS_CABS_CONTRAST = 0, 1
+STATS_REAL, STATS_CABS_CONTRAST, STATS_ABS_CONTRAST = 0, 1, 2
 ONEHOT_IDS = {"none": 0, "categorical": 1, "channel": 2}
 
 
 class Band(Structure):
     """acids_band: banded (column-sparse) matrix descriptor."""
-    _fields_ = [("meta", c_void_p), ("coef", c_void_p), ("n_out", c_int32), ("coef_len", c_int32)]
+    _fields_ = [("meta", c_void_p), ("coef", c_void_p), ("n_out", c_int32), ("coef_len", c_int32), ("n_in", c_int32)]
 
 
 class AcidsError(RuntimeError):

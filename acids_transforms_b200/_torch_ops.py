@@ -41,7 +41,7 @@ _SCHEMAS = {
     "mulaw_encode": "(Tensor x, int channels, int one_hot) -> Tensor",
     "mulaw_decode": "(Tensor q, int channels) -> Tensor",
     "one_hot": "(Tensor q, int n_classes) -> Tensor",
-    "stats": "(Tensor x, int contrast, float eps) -> Tensor",
+    "stats": "(Tensor x, int contrast, float eps, bool abs_contrast=False) -> Tensor",
     "mono_mix": "(Tensor x) -> Tensor",
     "midside": "(Tensor x, bool pad_mid, bool inverse) -> Tensor",
 }
@@ -145,8 +145,8 @@ def _one_hot(q, n_classes: int):
     return ops.one_hot(q, n_classes)
 
 
-def _stats(x, contrast: int, eps: float):
-    return ops._ret(ops.stats(x, contrast, eps), x)
+def _stats(x, contrast: int, eps: float, abs_contrast: bool = False):
+    return ops._ret(ops.stats(x, contrast, eps, abs_contrast), x)
 
 
 def _mono_mix(x):

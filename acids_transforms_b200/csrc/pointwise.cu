@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
         if (kind == ACIDS_STATS_CABS_CONTRAST) {
             const float2 c = ldg_stream2(reinterpret_cast<const float2*>(x) + i);
             v = apply_contrast(sqrtf(c.x * c.x + c.y * c.y), contrast, eps);
+        } else if (kind == ACIDS_STATS_ABS_CONTRAST) {
+            v = apply_contrast(fabsf(__ldg(x + i)), contrast, eps);
         } else {
             v = __ldg(x + i);
         }
@@ -441,7 +443,7 @@ extern "C" ACIDS_API int acids_stats(const float* x, int64_t n, int kind, int co
                            void* stream) {
     ACIDS_REQUIRE(x && scratch && out4, ACIDS_EINVAL, "stats: NULL pointer");
     ACIDS_REQUIRE(n >= 1, ACIDS_EINVAL, "stats: empty input");
-    ACIDS_REQUIRE(kind == ACIDS_STATS_REAL || kind == ACIDS_STATS_CABS_CONTRAST, ACIDS_EINVAL, "stats: unknown kind %d", kind);
+    ACIDS_REQUIRE(kind == ACIDS_STATS_REAL || kind == ACIDS_STATS_CABS_CONTRAST || kind == ACIDS_STATS_ABS_CONTRAST, ACIDS_EINVAL, "stats: unknown kind %d", kind);
     ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int64_t blocks = (n + 255) / 256;

@@ -58,6 +58,10 @@ int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, floa
     ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
     ACIDS_REQUIRE(!band.meta || (band.coef && band.n_out > 0 && band.coef_len >= 0 && (band.coef_len & 31) == 0), ACIDS_EINVAL,
                   "malformed banded matrix (n_out=%d coef_len=%d)", band.n_out, band.coef_len);
+    // the epilogue indexes the |X| row at start[m] + u with no bound of its own: the matrix must have been built for
+    // exactly this row length (the reference's matmul raises for STFT(512) + Magnitude(n_fft=1024), spectral_repr.py:219)
+    ACIDS_REQUIRE(!band.meta || band.n_in == n_bins, ACIDS_EINVAL,
+                  "mat1 and mat2 shapes cannot be multiplied (rows of %d values and a %dx%d matrix)", n_bins, band.n_in, band.n_out);
     ep.meta = band.meta; ep.coef = band.coef;
     ep.n_cols = band.meta ? band.n_out : n_bins;
     ep.contrast = contrast; ep.eps = eps; ep.drop_first = drop_first;

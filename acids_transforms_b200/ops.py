@@ -118,7 +118,9 @@ class BandedMatrix:
         total = int(meta.numel()) - 2
         n_out = next(n for n in range(max(total - 2 * ((total + 31) // 32) - 2, 0), total + 1) if n + 2 * ((n + 31) // 32) == total)
         self.n_out = n_out
-        self.n_in = -1          # read lazily: avoids a device sync when the tensors live on the GPU
+        # host-side bookkeeping pair at the end of meta: read ONCE per bank (as_band caches the view on the buffers'
+        # identity and version), so a CUDA-resident bank costs one 8-byte device->host read at first use and none after
+        self.n_in = int(meta[-2].item()) if meta.numel() >= 2 else -1
         self.coef_len = int(coef.numel())
         self.nnz_stored = self.coef_len
         self._meta, self._coef, self._dev = meta, coef, {}
@@ -129,10 +131,10 @@ class BandedMatrix:
         if key not in self._dev:
             self._dev[key] = (self._meta.to(device).contiguous(), self._coef.to(device).contiguous())
         meta, coef = self._dev[key]
-        return Band(meta.data_ptr(), coef.data_ptr(), self.n_out, self.coef_len)
+        return Band(meta.data_ptr(), coef.data_ptr(), self.n_out, self.coef_len, self.n_in)
 
 
-_NO_BAND = Band(None, None, 0, 0)
+_NO_BAND = Band(None, None, 0, 0, 0)
 _BAND_CACHE = {}
 
 
@@ -222,6 +224,9 @@ def stft_mag_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, 
     xf, batch = _flat_batch(xd, 1)
     B, L = xf.shape
     T = n_frames_centered(L, hop)
+    if band is not None and band.n_in != n_fft // 2 + 1:
+        # the reference's matmul raises the same way when Magnitude.n_fft disagrees with the STFT's
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (B * T, n_fft // 2 + 1, band.n_in, band.n_out))
     n_cols = band.n_out if band is not None else n_fft // 2 + 1
     n_keep = n_cols - int(drop_first)
     dev = xf.device
@@ -258,7 +263,7 @@ def mag_epilogue(X, band: Optional[BandedMatrix], contrast, eps, offset, scale, 
     Xd = _as_complex64(_dev(X)).resolve_conj()
     Xf, batch = _flat_batch(Xd, 1)
     rows, F = Xf.shape
-    if band is not None and band.n_in >= 0 and band.n_in != F:
+    if band is not None and band.n_in != F:
         # the reference's matmul raises the same way when Magnitude.n_fft disagrees with the STFT's
         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, F, band.n_in, band.n_out))
     n_cols = band.n_out if band is not None else F
@@ -288,7 +293,7 @@ def mag_invert(y, inverse_band: Optional[BandedMatrix], contrast, eps, offset, s
         yf = yf.contiguous()
     rows, n_in = yf.shape
     n_val = n_in + int(pad_last)
-    if inverse_band is not None and inverse_band.n_in >= 0 and inverse_band.n_in != n_val:
+    if inverse_band is not None and inverse_band.n_in != n_val:
         raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (rows, n_val, inverse_band.n_in, inverse_band.n_out))
     n_out = inverse_band.n_out if inverse_band is not None else n_val
     dev = yf.device
@@ -480,21 +485,35 @@ def griffinlim_update(rebuilt, tprev, mag, momentum: float, out: Optional[torch.
 # ------------------------------------------------------------------------------------------------
 # (4) inverse
 # ------------------------------------------------------------------------------------------------
+_ENVELOPE_CACHE = {}
+
+
 def istft_envelope_ok(window: torch.Tensor, n_fft: int, hop: int, n_frames: int) -> bool:
     """torch.istft's `window overlap add min` check (_refs/__init__.py:3794-3797), evaluated on the host.
 
-    It depends only on the window, so the reference's RuntimeError can be raised without a device
-    sync.  The envelope is periodic away from the edges, hence a clip of at most 2*ceil(N/hop)+2
-    frames has the same minimum over its trimmed core as the full-length one.
+    It depends only on the window, so the reference's RuntimeError can be raised without looking at the
+    data.  The envelope is periodic away from the edges, hence a clip of at most 2*ceil(N/hop)+2
+    frames has the same minimum over its trimmed core as the full-length one.  The verdict is cached on
+    the window buffer's identity and version: a CUDA-resident window is read back ONCE (64 KB, at the
+    first invert after construction / set_params / load_state_dict), never again — `invert` can be
+    captured in a CUDA graph after one warm-up call and does not synchronise the host.
     """
-    w2 = window.detach().to("cpu", torch.float64)[:n_fft].numpy() ** 2
     t_eff = min(int(n_frames), 2 * ((n_fft + hop - 1) // hop) + 2)
+    key = (window.data_ptr(), window._version, str(window.device), int(n_fft), int(hop), t_eff)
+    ok = _ENVELOPE_CACHE.get(key)
+    if ok is not None:
+        return ok
+    w2 = window.detach().to("cpu", torch.float64)[:n_fft].numpy() ** 2
     length = n_fft + hop * (t_eff - 1)
     env = np.zeros(length, np.float64)
     for t in range(t_eff):
         env[t * hop:t * hop + n_fft] += w2
     core = env[n_fft // 2:length - n_fft // 2]
-    return core.size == 0 or bool(np.abs(core).min() > 1e-11)
+    ok = core.size == 0 or bool(np.abs(core).min() > 1e-11)
+    if len(_ENVELOPE_CACHE) > 256:
+        _ENVELOPE_CACHE.clear()
+    _ENVELOPE_CACHE[key] = ok
+    return ok
 
 
 def istft_ola(X, window, n_fft, hop, check_envelope: bool = True):
@@ -623,9 +642,11 @@ def one_hot(q, n_classes: int):
 # ------------------------------------------------------------------------------------------------
 # statistics, raw-domain prologues
 # ------------------------------------------------------------------------------------------------
-def stats(x, contrast=None, eps=0.0) -> torch.Tensor:
+def stats(x, contrast=None, eps=0.0, abs_contrast: bool = False) -> torch.Tensor:
     """(min, max, mean, unbiased std) as a float64[4] DEVICE tensor — no host sync.
-    Complex input: statistics of contrast(|x|), what Magnitude.scale_data feeds Normalize (spectral_repr.py:242-245)."""
+    Complex input: statistics of contrast(|x|), what Magnitude.scale_data feeds Normalize (spectral_repr.py:242-245).
+    Real input: the values as they are (Normalize.scale_data, norm.py:26-38), or — with `abs_contrast`, what
+    Magnitude.scale_data does for a real-valued spectrogram — contrast(|x|) as well."""
     lib = _lib.load()
     xd = _dev(x)
     dev = xd.device
@@ -634,7 +655,7 @@ def stats(x, contrast=None, eps=0.0) -> torch.Tensor:
         kind = _lib.STATS_CABS_CONTRAST
     else:
         xd = xd.to(torch.float32).contiguous()
-        kind = _lib.STATS_REAL
+        kind = _lib.STATS_ABS_CONTRAST if abs_contrast else _lib.STATS_REAL
     if xd.numel() == 0:
         raise RuntimeError("min(): Expected reduction dim to be specified for input.numel() == 0.")
     scratch = torch.empty((int(lib.acids_stats_scratch_bytes()),), dtype=torch.uint8, device=dev)

@@ -48,12 +48,12 @@ class DGT(STFT):
         return "DGT(n_fft=%d, hop_length=%d, inversion_mode = %s)" % (self._n_fft, self._hop, self.inversion_mode)
 
     def __init__(self, sr: int = 44100, n_fft: int = 1024, hop_length: int = 256, dtype: Optional[torch.dtype] = None,
-                 inversion_mode: Optional[str] = "pghi", tolerance: float = 1.e-2):
+                 inversion_mode: Optional[str] = "pghi", tolerance: float = 1.e-2, track_phase: Optional[bool] = None):
         AudioTransform.__init__(self, sr)
         self._init_buffers(dtype)
         self.window_name = "gaussian"
         self.register_buffer("tolerance", torch.tensor(tolerance))
-        self._finish_init(n_fft, hop_length, inversion_mode)
+        self._finish_init(n_fft, hop_length, inversion_mode, track_phase)
 
     @staticmethod
     def get_inversion_modes() -> List[str]:

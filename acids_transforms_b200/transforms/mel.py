@@ -33,6 +33,18 @@ def create_dct(n_mfcc: int, n_mels: int) -> torch.Tensor:
     return dct.t().contiguous()
 
 
+def _mfcc_reference_keys(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    """A reference checkpoint holds the torchaudio sub-module's buffers (`transform.spectrogram.window`,
+    `transform.mel_scale.fb`, mel.py:43-44).  Both are functions of (n_fft, n_mels, sr), which this module re-derives
+    itself: check that they describe the same transform, then consume the keys so that strict loading succeeds."""
+    w = state_dict.pop(prefix + "transform.spectrogram.window", None)
+    fb = state_dict.pop(prefix + "transform.mel_scale.fb", None)
+    if w is not None and w.numel() != module.n_fft:
+        error_msgs.append("MFCC: checkpoint window has %d taps, this module n_fft=%d" % (w.numel(), module.n_fft))
+    if fb is not None and tuple(fb.shape) != (module.n_fft // 2 + 1, module.n_mels):
+        error_msgs.append("MFCC: checkpoint mel bank is %s, this module needs (%d, %d)" % (tuple(fb.shape), module.n_fft // 2 + 1, module.n_mels))
+
+
 class MFCC(AudioTransform):
     @property
     def invertible(self):
@@ -68,6 +80,7 @@ class MFCC(AudioTransform):
         self.register_buffer("mel_coef", torch.zeros(0), persistent=False)
         self.register_buffer("dct_mat", torch.zeros(0, 0), persistent=False)
         self.set_transform(n_fft, n_mels, hop_length, power)
+        self._register_load_state_dict_pre_hook(_mfcc_reference_keys, with_module=True)
 
     @torch.jit.unused
     def set_transform(self, n_fft: int, n_mels: int, hop_length: int, power: float) -> None:

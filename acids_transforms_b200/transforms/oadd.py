@@ -16,6 +16,15 @@ from .. import _torch_ops  # noqa: F401
 __all__ = ["OverlapAdd"]
 
 
+def _oadd_after_load(module, incompatible_keys):
+    """A loaded checkpoint may carry another n_fft / hop_length / gain: refresh their Python mirrors."""
+    module._n_fft = int(module.n_fft.item())
+    module._hop = int(module.hop_length.item())
+    module.frames_out = module._n_fft // module._hop - 1
+    module.keep = module.frames_out * module._hop
+    module._gain = float(module.gain_compensation)
+
+
 class OverlapAdd(AudioTransform):
     @property
     def invertible(self):
@@ -50,6 +59,7 @@ class OverlapAdd(AudioTransform):
             rec[..., i * self._hop:i * self._hop + self._n_fft] += fr[..., i, :] / (int(self._n_fft / self._hop) / 2)
         self.register_buffer("gain_compensation", rec.max())
         self._gain = float(rec.max())
+        self.register_load_state_dict_post_hook(_oadd_after_load)
 
     @torch.jit.export
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -211,6 +211,13 @@ def melscale_fbanks(n_freqs: int, f_min: float, f_max: float, n_mels: int, sampl
     return torch.max(torch.zeros(1), torch.min(down, up))
 
 
+def _magnitude_after_load(module, incompatible_keys):
+    """load_state_dict may replace `mel_bank` / `inverse_mel_bank` / `eps`: re-derive the banded views the kernels
+    consume and the Python mirror of eps."""
+    module.refresh_bands()
+    module._eps = float(module.eps)
+
+
 class Magnitude(_Representation):
     def __repr__(self):
         if self.mel:
@@ -242,7 +249,7 @@ class Magnitude(_Representation):
         self.register_buffer("inv_meta", torch.zeros(0, dtype=torch.int32), persistent=False)
         self.register_buffer("inv_coef", torch.zeros(0), persistent=False)
         self.refresh_bands()
-        self.register_load_state_dict_post_hook(lambda m, _: m.refresh_bands())
+        self.register_load_state_dict_post_hook(_magnitude_after_load)
 
     @torch.jit.unused
     def refresh_bands(self) -> None:
@@ -310,7 +317,7 @@ class Magnitude(_Representation):
     @torch.jit.export
     def scale_data(self, x: torch.Tensor) -> None:
         # statistics of contrast(|x|) WITHOUT the mel projection, like the reference (spectral_repr.py:242-245)
-        self.norm.set_stats(torch.ops.acids_b200.stats(x, _contrast_id(self.contrast_mode), self._eps))
+        self.norm.set_stats(torch.ops.acids_b200.stats(x, _contrast_id(self.contrast_mode), self._eps, True))
 
     def test_inversion(self, x: torch.Tensor):
         flat, batch = reshape_batches(x, -1)

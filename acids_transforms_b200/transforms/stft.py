@@ -8,11 +8,15 @@ framing + window + real-FFT kernel (`acids_stft_fwd`) and the inverse rFFT + ove
 * `n_fft` / `hop_length` are mirrored in Python ints, so `forward` performs no device->host sync
   (the reference calls `.item()` on device buffers three times per call, stft.py:100-101);
 * `phase_buffer` (stft.py:134-135: a full atan2 pass on every forward) is only filled when it can be
-  consumed, i.e. when the inversion mode is "keep_input"; set `track_phase = True` to force it;
+  consumed, i.e. when the inversion mode is "keep_input".  `STFT(..., track_phase=True)` restores the
+  reference's behaviour (the buffer is rewritten by every forward); asking for "keep_input" on a module
+  that has not been tracking warns, falls back to a random phase like the reference does without a buffer
+  (stft.py:155-158), and turns tracking on for the following forwards;
 * n_fft must be a power of two in [32, 16384];
 * the CPU index tensors that crash the reference on CUDA (stft.py:110) are built on the data's device.
 """
 import math
+import warnings
 from typing import Dict, List, Optional
 
 import torch
@@ -63,12 +67,12 @@ class STFT(AudioTransform):
         return "STFT(n_fft=%d, hop_length=%d, inversion_mode = %s)" % (self._n_fft, self._hop, self.inversion_mode)
 
     def __init__(self, sr: int = 44100, n_fft: int = 1024, hop_length: int = 256, dtype: Optional[torch.dtype] = None,
-                 inversion_mode: str = "griffin_lim", window: str = "hann"):
+                 inversion_mode: str = "griffin_lim", window: str = "hann", track_phase: Optional[bool] = None):
         super().__init__(sr=sr)
         self._init_buffers(dtype)
         make_window(window, 8)                       # raises ValueError for an unknown window (stft.py:54)
         self.window_name = window
-        self._finish_init(n_fft, hop_length, inversion_mode)
+        self._finish_init(n_fft, hop_length, inversion_mode, track_phase)
 
     # ---- construction helpers shared with DGT ----
     def _init_buffers(self, dtype: Optional[torch.dtype]):
@@ -86,7 +90,7 @@ class STFT(AudioTransform):
         self.inversion_mode = ""
         self.register_load_state_dict_post_hook(_sync_ints_after_load)
 
-    def _finish_init(self, n_fft, hop_length, inversion_mode):
+    def _finish_init(self, n_fft, hop_length, inversion_mode, track_phase: Optional[bool] = None):
         if n_fft is not None:
             assert hop_length is not None, "n_fft and hop_length must be given together"
         if hop_length is not None:
@@ -97,7 +101,9 @@ class STFT(AudioTransform):
             self.inversion_mode = inversion_mode
         else:
             raise ValueError("Inversion mode %s not known" % inversion_mode)
-        self.track_phase = inversion_mode == "keep_input"
+        # None: fill `phase_buffer` only when this module's own mode can consume it; True: on every forward, like the
+        # reference (stft.py:103, :134-135); False: never
+        self.track_phase = (inversion_mode == "keep_input") if track_phase is None else bool(track_phase)
 
     @torch.jit.export
     def set_params(self, n_fft: int, hop_length: int) -> None:
@@ -189,6 +195,11 @@ class STFT(AudioTransform):
         if mode == "keep_input":
             phase = self._get_phase_buffer(x)
             if phase.size(0) == 0:
+                if not self.track_phase:
+                    warnings.warn("keep_input: this module has not been recording the phase of its input (track_phase "
+                                  "is off unless inversion_mode='keep_input' or track_phase=True is given at construction); "
+                                  "falling back to a random phase and recording from the next forward on")
+                    self.track_phase = True
                 return self._random_phase_istft(x)
             return self._istft(torch.ops.acids_b200.polar_to_complex(x, phase.to(x.device)))
         if mode == "griffin_lim":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACIDS_ABI_VERSION 1
+#define ACIDS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ACIDS_API __attribute__((visibility("default")))
@@ -60,6 +60,7 @@ extern "C" {
 /* statistics input kinds for acids_stats */
 #define ACIDS_STATS_REAL 0           /* float32 values as they are                       */
 #define ACIDS_STATS_CABS_CONTRAST 1  /* complex64 in, statistics of contrast(|x|)        */
+#define ACIDS_STATS_ABS_CONTRAST 2   /* float32 in, statistics of contrast(|x|) (Magnitude.scale_data on a real spectrogram) */
 
 /* one-hot layouts — MuLaw.one_hot, raw.py:285-292 */
 #define ACIDS_ONEHOT_NONE 0
@@ -80,6 +81,9 @@ typedef struct acids_band {
     const float* coef;     /* device, coef_len floats */
     int32_t n_out;         /* number of output columns */
     int32_t coef_len;
+    int32_t n_in;          /* number of input rows the matrix was built for; every entry point checks it against the
+                            * row length it is applied to (the reference's matmul raises on a mismatch, e.g. an
+                            * STFT(512) feeding Magnitude(n_fft=1024)) */
 } acids_band;
 
 /* ---- (1) framing + window + real FFT ------------------------------------------------------
@@ -219,7 +223,8 @@ ACIDS_API int acids_one_hot(const int64_t* q, int64_t n, int n_classes, int64_t*
 /* ---- Normalize.scale_data statistics: norm.py:26-38, spectral_repr.py:242-245 -----------------
  * out4 (device, 4 doubles): min, max, mean, unbiased std of the (transformed) values.
  * kind = ACIDS_STATS_REAL: x float32 [n]; ACIDS_STATS_CABS_CONTRAST: x complex64 [n], statistics of
- * contrast(|x|).  scratch: device buffer of acids_stats_scratch_bytes() bytes.                   */
+ * contrast(|x|); ACIDS_STATS_ABS_CONTRAST: x float32 [n], statistics of contrast(|x|).
+ * scratch: device buffer of acids_stats_scratch_bytes() bytes.                                    */
 ACIDS_API int64_t acids_stats_scratch_bytes(void);
 ACIDS_API int acids_stats(const float* x, int64_t n, int kind, int contrast, float eps, void* scratch,
                 double* out4, void* stream);
