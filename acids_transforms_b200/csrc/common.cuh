@@ -227,8 +227,36 @@ __device__ __forceinline__ void band_column(const float* __restrict__ val, int v
 #undef ACIDS_TAPS
 }
 
-// FULL: all NF rows exist (no row predicates); otherwise rows f >= n_valid are skipped
-template <int NT, int NF, int CONTRAST, int BAND, bool TRANSPOSED, bool FULL>
+// generic (runtime tap count) projection of ONE (row, column) pair — the spread tail of epilogue_tile
+template <int BAND>
+__device__ __forceinline__ float band_single(const float* __restrict__ vrow, const int32_t* __restrict__ meta,
+                                             const float* __restrict__ coef, int n_groups, int m) {
+    int cnt;
+    const float* __restrict__ v;
+    const float* __restrict__ c;
+    if (BAND == BAND_SMEM) {
+        const int2 rec = reinterpret_cast<const int2*>(meta)[m];
+        cnt = (int)((unsigned)rec.y >> 16);
+        v = vrow + rec.x;
+        c = coef + (rec.y & 0xffff);
+    } else {
+        cnt = __ldg(meta + 2 * (m >> 5));
+        const int base = __ldg(meta + 2 * (m >> 5) + 1);
+        v = vrow + __ldg(meta + 2 * n_groups + m);
+        c = coef + (base << 5) + (m & 31);
+    }
+    float acc = 0.f;
+    for (int u = 0; u < cnt; ++u) acc = fmaf(v[u], BAND == BAND_GLOBAL ? __ldg(c + (u << 5)) : c[u << 5], acc);
+    return acc;
+}
+
+// FULL: all NF rows exist (no row predicates); otherwise rows f >= n_valid are skipped.
+// RS > 0: the output row step is known at compile time (the common contiguous [.., T, F] output): the NF stores of a
+// column are one pointer plus immediates instead of NF 64-bit additions.
+// SPREAD: when the columns left over after the last full sweep of NT, times the NF rows, fit one sweep of the CTA
+// (n_out = 513 = 4 * 128 + 1 is the common case), those (row, column) pairs are dealt one per thread to the LAST warps
+// instead of costing warp 0 a whole extra iteration with one active lane — the slowest warp sets the CTA's pace.
+template <int NT, int NF, int CONTRAST, int BAND, bool TRANSPOSED, bool FULL, int RS = 0, bool SPREAD = false>
 __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int val_stride, int tid, const EpiArgs& ep,
                                               float* __restrict__ out0, int row_step, int col_step, int n_valid) {
     // out0: element (row 0, first output column) of the tile; rows are row_step floats apart, columns col_step
@@ -239,8 +267,13 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
     const int64_t o_step = TRANSPOSED ? (int64_t)NT * col_step : (int64_t)NT;
     int64_t roff[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) roff[f] = TRANSPOSED ? (int64_t)f : (int64_t)f * row_step;
-    for (int mo = tid; mo < ep.n_out; mo += NT, o += o_step) {
+    for (int f = 0; f < NF; ++f) roff[f] = TRANSPOSED ? (int64_t)f : (RS > 0 ? (int64_t)f * RS : (int64_t)f * row_step);
+    int n_main = ep.n_out;
+    if (SPREAD) {
+        const int rem = ep.n_out % NT;
+        if (rem * NF <= NT) n_main = ep.n_out - rem;
+    }
+    for (int mo = tid; mo < n_main; mo += NT, o += o_step) {
         const int m = mo + ep.drop_first;
         float a[NF];
         if (BAND != BAND_NONE) {
@@ -253,17 +286,29 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
         for (int f = 0; f < NF; ++f)
             if (FULL || f < n_valid) stg_stream1(o + roff[f], fmaf(contrast_core<CONTRAST>(a[f], ep.eps), ep.gain, ep.bias));
     }
+    if (SPREAD && n_main < ep.n_out) {
+        const int i = NT - 1 - tid;                      // dealt from the last thread backwards
+        const int f = i % NF, c = i / NF;                // row of the tile, left-over column
+        if (c < ep.n_out - n_main && (FULL || f < n_valid)) {
+            const int mo = n_main + c, m = mo + ep.drop_first;
+            const float a = BAND != BAND_NONE ? band_single<BAND>(val + f * val_stride, ep.meta, ep.coef, ep.n_groups, m)
+                                              : val[f * val_stride + m];
+            float* __restrict__ oo = out0 + (TRANSPOSED ? (int64_t)mo * col_step + f
+                                                        : (int64_t)mo + (RS > 0 ? (int64_t)f * RS : (int64_t)f * row_step));
+            stg_stream1(oo, fmaf(contrast_core<CONTRAST>(a, ep.eps), ep.gain, ep.bias));
+        }
+    }
 }
 
 // runtime contrast / row count -> compile-time (one dispatch per tile; call sites that know the contrast at compile
 // time pass it as CSEL >= 0 and pay no dispatch)
-template <int NT, int NF, int CSEL, int BAND, bool TRANSPOSED>
+template <int NT, int NF, int CSEL, int BAND, bool TRANSPOSED, int RS = 0, bool SPREAD = false>
 __device__ __forceinline__ void epilogue_dispatch(int contrast, const float* __restrict__ val, int val_stride, int tid,
                                                   const EpiArgs& ep, float* __restrict__ out0, int row_step, int col_step, int n_valid) {
 #define ACIDS_TILE(C)                                                                                                   \
     do {                                                                                                                \
-        if (n_valid >= NF) epilogue_tile<NT, NF, C, BAND, TRANSPOSED, true>(val, val_stride, tid, ep, out0, row_step, col_step, NF); \
-        else epilogue_tile<NT, NF, C, BAND, TRANSPOSED, false>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid);       \
+        if (n_valid >= NF) epilogue_tile<NT, NF, C, BAND, TRANSPOSED, true, RS, SPREAD>(val, val_stride, tid, ep, out0, row_step, col_step, NF); \
+        else epilogue_tile<NT, NF, C, BAND, TRANSPOSED, false, RS, SPREAD>(val, val_stride, tid, ep, out0, row_step, col_step, n_valid);       \
     } while (0)
     if (CSEL >= 0) {
         ACIDS_TILE((CSEL >= 0 ? CSEL : 0));

@@ -31,7 +31,13 @@ struct FwdParams {
 #ifndef ACIDS_FWD_MINB_SMALL
 #define ACIDS_FWD_MINB_SMALL 4
 #endif
-template <class P>
+#ifndef ACIDS_FWD_FPW_1024
+#define ACIDS_FWD_FPW_1024 1           // 2: two frames in flight per warp at 168 registers, measured SLOWER (1.35 vs 1.16 ms fused)
+#endif
+#ifndef ACIDS_FWD_THREADS_1024
+#define ACIDS_FWD_THREADS_1024 256     // 8 frames per unit: the epilogue amortises a column's metadata / coefficients over 8 rows
+#endif
+template <class P, int MODE>
 struct FwdCfg {
 #ifndef ACIDS_FWD_MID_THREADS
 #define ACIDS_FWD_MID_THREADS 128      // CTA size of the T = 64 / 128 plans (n_fft 2048 / 4096): 3 CTAs x 168 registers, no spills
@@ -39,16 +45,27 @@ struct FwdCfg {
 #ifndef ACIDS_FWD_MID_MINB
 #define ACIDS_FWD_MID_MINB 3
 #endif
-    static constexpr int THREADS = P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256));
-    static constexpr int MINB = P::T <= 32 ? ACIDS_FWD_MINB_SMALL : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1));
+    // FPW: frames a thread group keeps in flight.  With two, every phase of the transform (exchange loads, butterflies,
+    // exchange stores) has two independent instruction streams per warp, the window taps are read from shared memory once
+    // for both, and the epilogue amortises a column's metadata / coefficients / dispatch over twice the rows.  Costs
+    // registers: 168 per thread, 3 CTAs / SM (n_fft = 1024: 1.17 -> see DESIGN.md section 5).
+    static constexpr int FPW = P::N == 1024 ? ACIDS_FWD_FPW_1024 : 1;
+    static constexpr int THREADS = (P::N == 1024 && MODE == 1 /* MODE_REAL */) ? ACIDS_FWD_THREADS_1024
+                                                : (P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256)));
+    static constexpr int MINB = FPW > 1 ? 3 : (P::T <= 32 ? ACIDS_FWD_MINB_SMALL * 128 / THREADS : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1)));
     // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
     // second register set; that needs ~160 registers -> one CTA less per SM for the small plans
     static constexpr int MINB_COMPLEX = P::T <= 32 ? 3 : MINB;
-    static constexpr int G = THREADS / P::T;
-    static constexpr int NF = G < 4 ? G : 4;                    // rows per epilogue tile
-    static constexpr int VSTR = (P::F + 3) & ~3;                // |X| row stride in shared memory (floats)
+    static constexpr int GT = THREADS / P::T;                   // thread groups per CTA
+    static constexpr int G = GT * FPW;                          // frames per unit
+    static constexpr int NF = (P::N == 1024 && G % 8 == 0) ? 8 : (G < 4 ? G : 4);   // rows per epilogue tile
+    // FPW > 1: the |X| row of a frame is parked in the frame's own exchange buffer (free once the last pass has read
+    // it) instead of a separate double-buffered tile: 51 KB instead of 84 KB per CTA, three CTAs fit an SM
+    static constexpr bool ROWS_IN_EXCH = FPW > 1;
+    static constexpr int VSTR = ROWS_IN_EXCH ? 2 * P::SMEM_CF : ((P::F + 3) & ~3);   // |X| row stride in shared memory (floats)
     static constexpr int VW = (P::bpt(0) % 2 == 0) ? 4 : 2;     // floats per vector load of the first pass
     static_assert(G % NF == 0, "rows per CTA must be a multiple of the row tile");
+    static_assert(!ROWS_IN_EXCH || 2 * P::SMEM_CF >= P::F, "a row must fit the exchange buffer");
     static constexpr size_t exch_bytes() { return (size_t)G * P::SMEM_CF * sizeof(cf); }
     static constexpr size_t win_bytes() { return (size_t)P::M * sizeof(float2); }
 };
@@ -66,18 +83,20 @@ __device__ __forceinline__ float pow_value(cf a, float power) {
 
 // CSEL: contrast known at compile time (ACIDS_CONTRAST_*) or -1 (dispatched once per row tile)
 template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
-__global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? FwdCfg<P>::MINB_COMPLEX : FwdCfg<P>::MINB)
+__global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX ? FwdCfg<P, MODE>::MINB_COMPLEX : FwdCfg<P, MODE>::MINB)
     stft_fwd_kernel(const FwdParams p) {
-    using C = FwdCfg<P>;
+    using C = FwdCfg<P, MODE>;
     constexpr int THREADS = C::THREADS;
-    constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW;
+    constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW, FPW = C::FPW;
     constexpr int R0 = P::radix(0), B0 = P::bpt(0), NB0 = P::nb(0);
+    constexpr bool RIE = MODE == MODE_REAL && C::ROWS_IN_EXCH;
     using FFT = FrameFFT<P, false>;
     using PR = typename FFT::PR;
     constexpr int RP = PR::R, NBP = PR::NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
-    cf* const s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
+    // exchange buffer of frame f of this group: frames g * FPW + f of a unit
+    cf* const s0 = reinterpret_cast<cf*>(smem_raw) + (size_t)g * FPW * P::SMEM_CF;
     auto gsync = [&]() { group_sync<T, THREADS>(g); };
 
     // ---- frame-invariant state: twiddles in registers; the analysis window as (w[2n], w[2n+1]) / 2 pairs in shared
@@ -96,8 +115,9 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
         if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
         ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef, p.offset_ptr,
                            p.scale_ptr);
-        // |X| rows of a unit, double buffered: the next unit's FFT never waits for the slowest epilogue thread
-        vrows = reinterpret_cast<float*>(bandmem + (BAND == BAND_SMEM ? p.band_smem_bytes : 0));
+        // |X| rows of a unit: in the frames' exchange buffers (RIE), or double buffered so that the next unit's FFT never
+        // waits for the slowest epilogue thread
+        vrows = RIE ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(bandmem + (BAND == BAND_SMEM ? p.band_smem_bytes : 0));
     }
     __syncthreads();
 
@@ -110,23 +130,29 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
     // Raw (un-windowed) samples of frame (b, t) in first-pass operand order.  Interior, aligned frames: vector
     // loads straight into registers.  Edge frames (torch.stft center=True, pad_mode="reflect") and unaligned
     // inputs: the group stages the frame in its exchange buffer with scalar loads, then reads its operands.
-    auto fetch = [&](cf* v, const float* __restrict__ xb, int t) {
+    // fetch_fast issues the vector loads when the frame allows it and says whether the frame still needs staging.
+    // Frames past the end of a clip (the last unit of a clip is padded to G frames) are never stored: instead of
+    // zero-filling their registers they re-read an interior frame of the same clip when there is one.
+    const int t_safe = (p.pad + p.hop - 1) / p.hop;
+    const bool has_safe = t_safe < n_frames && t_safe * p.hop - p.pad + N <= L;
+    auto fetch_fast = [&](cf* v, const float* __restrict__ xb, int t) -> bool {
         const bool valid = t < n_frames;
+        if (!valid && has_safe) t = t_safe;
 #ifdef ACIDS_DEBUG_NOLOAD       // tuning experiment only: every frame reads the same (cached) samples
-        const int s0 = N;
+        const int s0i = N;
         xb = p.x;
 #else
-        const int s0 = t * p.hop - p.pad;
+        const int s0i = t * p.hop - p.pad;
 #endif
-        const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0 >= 0 && s0 + N <= L;
+        const bool fast = (p.vec_ok & (VW == 4 ? 2 : 1)) && s0i >= 0 && s0i + N <= L;
         bool stage = valid && !fast;
         if (T < 32) stage = __any_sync(0xffffffffu, stage);     // frame groups sharing a warp take the same path
         if (!stage) {
-            if (valid) {
+            if (valid || (has_safe && fast)) {
 #pragma unroll
                 for (int r = 0; r < R0; ++r) {
                     // this thread's B0 butterflies are consecutive: B0 adjacent complex operands per radix slot
-                    const float* __restrict__ src = xb + s0 + 2 * (tid * B0 + r * NB0);
+                    const float* __restrict__ src = xb + s0i + 2 * (tid * B0 + r * NB0);
                     if (VW == 4) {
 #pragma unroll
                         for (int b0 = 0; b0 < B0; b0 += 2) {
@@ -146,22 +172,29 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = mk(0.f, 0.f);
             }
-        } else {
-            float* sf = reinterpret_cast<float*>(s);
-            gsync();   // the group is done reading the exchange buffer
-            for (int i = tid; i < N; i += T) {
-                int k = s0 + i;
-                if (k < 0) k = -k;
-                if (k >= L) k = 2 * (L - 1) - k;
-                k = k < 0 ? 0 : (k >= L ? L - 1 : k);
-                sf[i] = valid ? __ldg(xb + k) : 0.f;
-            }
-            gsync();
-#pragma unroll
-            for (int b0 = 0; b0 < B0; ++b0)
-#pragma unroll
-                for (int r = 0; r < R0; ++r) v[b0 * R0 + r] = *reinterpret_cast<const cf*>(sf + 2 * fft.template in_index<0>(b0, r));
         }
+        return stage;
+    };
+    auto fetch_staged = [&](cf* v, cf* s, const float* __restrict__ xb, int t) {
+        const bool valid = t < n_frames;
+        const int s0i = t * p.hop - p.pad;
+        float* sf = reinterpret_cast<float*>(s);
+        gsync();   // the group is done reading the exchange buffer
+        for (int i = tid; i < N; i += T) {
+            int k = s0i + i;
+            if (k < 0) k = -k;
+            if (k >= L) k = 2 * (L - 1) - k;
+            k = k < 0 ? 0 : (k >= L ? L - 1 : k);
+            sf[i] = valid ? __ldg(xb + k) : 0.f;
+        }
+        gsync();
+#pragma unroll
+        for (int b0 = 0; b0 < B0; ++b0)
+#pragma unroll
+            for (int r = 0; r < R0; ++r) v[b0 * R0 + r] = *reinterpret_cast<const cf*>(sf + 2 * fft.template in_index<0>(b0, r));
+    };
+    auto fetch = [&](cf* v, cf* s, const float* __restrict__ xb, int t) {
+        if (fetch_fast(v, xb, t)) fetch_staged(v, s, xb, t);
     };
 
     // clip and unit-in-clip advance incrementally: no division, no 64-bit multiply per frame
@@ -171,11 +204,17 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
     float* __restrict__ oclip = MODE == MODE_COMPLEX ? p.out + b * ((int64_t)n_frames * P::F * 2) : p.out + b * p.out_clip_stride;
     const int64_t oclip_step = MODE == MODE_COMPLEX ? (int64_t)n_frames * P::F * 2 : p.out_clip_stride;
     int buf = 0;
-    cf v[V];
-    if (u0 < u1) fetch(v, xclip, uc * G + g);
+    cf v[FPW][V];
+    bool pend[FPW];                  // RIE: frames of the next unit that must be staged once the rows have been consumed
+    const float* __restrict__ pend_clip = xclip;
+#pragma unroll
+    for (int f = 0; f < FPW; ++f) pend[f] = false;
+    if (u0 < u1) {
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
+    }
     for (int64_t u = u0; u < u1; ++u) {
-        const int t = uc * G + g;
-        const bool valid = t < n_frames;
+        const int tb = uc * G + g * FPW;             // first frame of this group in the unit
         const int cur_uc = uc;
         float* __restrict__ const cur_out = oclip;
         if (++uc == upc) {
@@ -184,124 +223,204 @@ __global__ void __launch_bounds__(FwdCfg<P>::THREADS, MODE == MODE_COMPLEX ? Fwd
             oclip += oclip_step;
         }
 
-        // ---- window (first-pass operand order, same adjacency as the loads) ----
+        if (RIE) {
+            // the previous unit's rows (in the exchange buffers) have been consumed by every thread of the CTA before
+            // anybody overwrites them: frames that need staging first, all others as late as the first exchange store
+            bool any_pend = false;
 #pragma unroll
-        for (int r = 0; r < R0; ++r) {
-            const float2* __restrict__ wv = swin + (tid * B0 + r * NB0);
-            if (VW == 4) {
+            for (int f = 0; f < FPW; ++f) any_pend |= pend[f];
+            if (any_pend) {
+                __syncthreads();
 #pragma unroll
-                for (int b0 = 0; b0 < B0; b0 += 2) {
-#ifdef ACIDS_DEBUG_NOWINDOW     // tuning experiment only: what would the kernel cost if the window taps were free?
-                    const float4 w = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-#else
-                    const float4 w = *reinterpret_cast<const float4*>(wv + b0);
-#endif
-                    v[b0 * R0 + r] = cmul2(v[b0 * R0 + r], mk(w.x, w.y));
-                    v[(b0 + 1) * R0 + r] = cmul2(v[(b0 + 1) * R0 + r], mk(w.z, w.w));
+                for (int f = 0; f < FPW; ++f)
+                    if (pend[f]) fetch_staged(v[f], s0 + f * P::SMEM_CF, pend_clip, tb + f);
+            }
+            // ---- window (first-pass operand order, same adjacency as the loads) ----
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const float2* __restrict__ wv = swin + (tid * B0 + r * NB0);
+                if (VW == 4) {
+#pragma unroll
+                    for (int b0 = 0; b0 < B0; b0 += 2) {
+                        const float4 w = *reinterpret_cast<const float4*>(wv + b0);
+#pragma unroll
+                        for (int f = 0; f < FPW; ++f) {
+                            v[f][b0 * R0 + r] = cmul2(v[f][b0 * R0 + r], mk(w.x, w.y));
+                            v[f][(b0 + 1) * R0 + r] = cmul2(v[f][(b0 + 1) * R0 + r], mk(w.z, w.w));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b0 = 0; b0 < B0; ++b0) {
+                        const float2 w = wv[b0];
+#pragma unroll
+                        for (int f = 0; f < FPW; ++f) v[f][b0 * R0 + r] = cmul2(v[f][b0 * R0 + r], mk(w.x, w.y));
+                    }
                 }
-            } else {
+            }
 #pragma unroll
-                for (int b0 = 0; b0 < B0; ++b0) {
-                    const float2 w = wv[b0];
-                    v[b0 * R0 + r] = cmul2(v[b0 * R0 + r], mk(w.x, w.y));
+            for (int f = 0; f < FPW; ++f) fft.template butterflies<0>(v[f]);
+            if (!any_pend) __syncthreads();
+        } else {
+            // ---- window (first-pass operand order, same adjacency as the loads) ----
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const float2* __restrict__ wv = swin + (tid * B0 + r * NB0);
+                if (VW == 4) {
+#pragma unroll
+                    for (int b0 = 0; b0 < B0; b0 += 2) {
+#ifdef ACIDS_DEBUG_NOWINDOW     // tuning experiment only: what would the kernel cost if the window taps were free?
+                        const float4 w = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+#else
+                        const float4 w = *reinterpret_cast<const float4*>(wv + b0);
+#endif
+#pragma unroll
+                        for (int f = 0; f < FPW; ++f) {
+                            v[f][b0 * R0 + r] = cmul2(v[f][b0 * R0 + r], mk(w.x, w.y));
+                            v[f][(b0 + 1) * R0 + r] = cmul2(v[f][(b0 + 1) * R0 + r], mk(w.z, w.w));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int b0 = 0; b0 < B0; ++b0) {
+                        const float2 w = wv[b0];
+#pragma unroll
+                        for (int f = 0; f < FPW; ++f) v[f][b0 * R0 + r] = cmul2(v[f][b0 * R0 + r], mk(w.x, w.y));
+                    }
                 }
             }
         }
 
         // complex output, plans that run 3 CTAs / SM (168 registers, n_fft <= 4096): the next frame's samples are fetched a
         // whole FFT early into a second register set (n_fft = 4096: 1.09 -> 0.96 ms); larger plans (128 registers) fetch
-        // after the stores instead
-        constexpr bool EARLY = MODE == MODE_COMPLEX && T <= 128;
+        // after the stores instead; with two frames in flight the second register set IS the second frame
+        constexpr bool EARLY = MODE == MODE_COMPLEX && T <= 128 && FPW == 1;
         cf nv[EARLY ? V : 1];
         if (EARLY) {
-            if (u + 1 < u1) fetch(nv, xclip, uc * G + g);       // lands during this frame's FFT
+            if (u + 1 < u1) fetch(nv, s0, xclip, uc * G + g);       // lands during this frame's FFT
         }
 
         // ---- passes ----
-        fft.template butterflies<0>(v);
-        gsync();   // the previous frame's readers of s are done
-        fft.template store<0>(v, s);
+        if (!RIE) {
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template butterflies<0>(v[f]);
+            gsync();   // the previous frame's readers of s are done
+        }
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) fft.template store<0>(v[f], s0 + f * P::SMEM_CF);
         gsync();
-        fft.template load<1>(v, s);
-        fft.template butterflies<1>(v);
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) fft.template load<1>(v[f], s0 + f * P::SMEM_CF);
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) fft.template butterflies<1>(v[f]);
         if constexpr (P::NP > 2) {
             gsync();
-            fft.template store<1>(v, s);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template store<1>(v[f], s0 + f * P::SMEM_CF);
             gsync();
-            fft.template load<2>(v, s);
-            fft.template butterflies<2>(v);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template load<2>(v[f], s0 + f * P::SMEM_CF);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template butterflies<2>(v[f]);
         }
         if constexpr (P::NP > 3) {
             gsync();
-            fft.template store<2>(v, s);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template store<2>(v[f], s0 + f * P::SMEM_CF);
             gsync();
-            fft.template load<3>(v, s);
-            fft.template butterflies<3>(v);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template load<3>(v[f], s0 + f * P::SMEM_CF);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) fft.template butterflies<3>(v[f]);
         }
-
-        // ---- untangle in registers ----
-        cf o1[V / 2], o2[V / 2], ex;
-        fft.untangle_fwd(v, o1, o2, ex);
+        if (RIE) gsync();    // every lane has read the last pass's operands: the buffers may take the |X| rows
 
         if (MODE == MODE_COMPLEX) {
-            if (valid) {
-                float2* __restrict__ row = reinterpret_cast<float2*>(cur_out) + t * P::F;
 #pragma unroll
-                for (int c = 0; c < PR::PC; ++c) {
-                    // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
-                    float2* lo = row + PR::klo(tid, c);
-                    float2* hi = row + PR::khi(tid, c);
-                    float2* mlo = row + (M - PR::klo(tid, c));
-                    float2* mhi = row + (M - PR::khi(tid, c));
+            for (int f = 0; f < FPW; ++f) {
+                // ---- untangle in registers ----
+                cf o1[V / 2], o2[V / 2], ex;
+                fft.untangle_fwd(v[f], o1, o2, ex);
+                const int t = tb + f;
+                if (t < n_frames) {
+                    float2* __restrict__ row = reinterpret_cast<float2*>(cur_out) + t * P::F;
 #pragma unroll
-                    for (int q = 0; q < RP; ++q) {
-                        stg_stream2((q < RP / 2 ? lo : hi) + q * NBP, o1[c * RP + q].x, o1[c * RP + q].y);
-                        stg_stream2((q < RP / 2 ? mlo : mhi) - q * NBP, o2[c * RP + q].x, o2[c * RP + q].y);
+                    for (int c = 0; c < PR::PC; ++c) {
+                        // bins k = base + q*NB and M - k: two per-thread bases, compile-time offsets
+                        float2* lo = row + PR::klo(tid, c);
+                        float2* hi = row + PR::khi(tid, c);
+                        float2* mlo = row + (M - PR::klo(tid, c));
+                        float2* mhi = row + (M - PR::khi(tid, c));
+#pragma unroll
+                        for (int q = 0; q < RP; ++q) {
+                            stg_stream2((q < RP / 2 ? lo : hi) + q * NBP, o1[c * RP + q].x, o1[c * RP + q].y);
+                            stg_stream2((q < RP / 2 ? mlo : mhi) - q * NBP, o2[c * RP + q].x, o2[c * RP + q].y);
+                        }
                     }
+                    if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
                 }
-                if (tid == 0) stg_stream2(row + M / 2, ex.x, ex.y);
             }
             if (EARLY) {
 #pragma unroll
-                for (int i = 0; i < V; ++i) v[i] = nv[EARLY ? i : 0];
+                for (int i = 0; i < V; ++i) v[0][i] = nv[EARLY ? i : 0];
             } else {
-                if (u + 1 < u1) fetch(v, xclip, uc * G + g);
-            }
-        } else {
-            float* __restrict__ vbuf = vrows + buf * (G * VSTR);
-            float* __restrict__ val = vbuf + g * VSTR;
+                if (u + 1 < u1) {
 #pragma unroll
-            for (int c = 0; c < PR::PC; ++c) {
-                float* lo = val + PR::klo(tid, c);
-                float* hi = val + PR::khi(tid, c);
-                float* mlo = val + (M - PR::klo(tid, c));
-                float* mhi = val + (M - PR::khi(tid, c));
-#pragma unroll
-                for (int q = 0; q < RP; ++q) {
-                    (q < RP / 2 ? lo : hi)[q * NBP] = pow_value<PMODE>(o1[c * RP + q], p.power);
-                    (q < RP / 2 ? mlo : mhi)[-q * NBP] = pow_value<PMODE>(o2[c * RP + q], p.power);
+                    for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
                 }
             }
-            if (tid == 0) val[M / 2] = pow_value<PMODE>(ex, p.power);
+        } else {
+            float* __restrict__ vbuf = RIE ? vrows : vrows + buf * (G * VSTR);
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) {
+                cf o1[V / 2], o2[V / 2], ex;
+                fft.untangle_fwd(v[f], o1, o2, ex);
+                float* __restrict__ val = vbuf + (g * FPW + f) * VSTR;
+#pragma unroll
+                for (int c = 0; c < PR::PC; ++c) {
+                    float* lo = val + PR::klo(tid, c);
+                    float* hi = val + PR::khi(tid, c);
+                    float* mlo = val + (M - PR::klo(tid, c));
+                    float* mhi = val + (M - PR::khi(tid, c));
+#pragma unroll
+                    for (int q = 0; q < RP; ++q) {
+                        (q < RP / 2 ? lo : hi)[q * NBP] = pow_value<PMODE>(o1[c * RP + q], p.power);
+                        (q < RP / 2 ? mlo : mhi)[-q * NBP] = pow_value<PMODE>(o2[c * RP + q], p.power);
+                    }
+                }
+                if (tid == 0) val[M / 2] = pow_value<PMODE>(ex, p.power);
+            }
             // v, o1, o2 are dead: start fetching the next frame's samples, they land during the epilogue
-            if (u + 1 < u1) fetch(v, xclip, uc * G + g);
-            // One barrier per unit: the rows are complete.  (Writers of this buffer two units from now have passed
-            // the next barrier, i.e. every thread has left this epilogue.)
+            if (u + 1 < u1) {
+                pend_clip = xclip;
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) {
+                    if (RIE) pend[f] = fetch_fast(v[f], xclip, uc * G + g * FPW + f);
+                    else fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
+                }
+            }
+            // One barrier per unit: the rows are complete.  (Double-buffered rows: writers of this buffer two units from now
+            // have passed the next barrier, i.e. every thread has left this epilogue.  RIE: see the barrier at the loop top.)
             __syncthreads();
             const int t0 = cur_uc * G;
             const int n_valid = min(G, n_frames - t0);
             const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
             float* out0 = cur_out + (TRANSPOSED ? t0 : t0 * rs);
+            constexpr bool SPREAD = !TRANSPOSED;
 #pragma unroll 1
             for (int g0 = 0; g0 < G; g0 += NF) {
                 if (g0 >= n_valid) break;
-                epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
-                                                                       out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
+                if (!TRANSPOSED && N == 1024 && rs == P::F)
+                    epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, P::F, SPREAD>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
+                                                                                          out0 + g0 * rs, rs, cs, n_valid - g0);
+                else
+                    epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, 0, SPREAD>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
+                                                                                       out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
             }
 #ifdef ACIDS_FWD_SINGLE_ROWBUF     // tuning experiment: one |X| row buffer (8 KB less shared memory per CTA), two barriers per unit
             __syncthreads();
 #else
-            buf ^= 1;
+            if (!RIE) buf ^= 1;
 #endif
         }
     }
@@ -311,7 +430,7 @@ static const size_t kBandSmemBudget = 24 * 1024;
 
 template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
 static int launch_fwd(FwdParams p, cudaStream_t st) {
-    using C = FwdCfg<P>;
+    using C = FwdCfg<P, MODE>;
     constexpr int THREADS = C::THREADS;
     constexpr int G = C::G;
     size_t smem = C::exch_bytes() + C::win_bytes();
@@ -320,7 +439,7 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
 #else
     constexpr int kRowBufs = 2;
 #endif
-    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (size_t)kRowBufs * G * C::VSTR * sizeof(float);
+    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (C::ROWS_IN_EXCH ? 0 : (size_t)kRowBufs * G * C::VSTR * sizeof(float));
     auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
     static PerDevice cache[kMaxDevices];
     PerDevice& pd = per_device(cache);

@@ -15,7 +15,13 @@ batch.  One JSON line is printed by rank 0.
              (4 L + 4 T F per clip) / measured launch duration, against MEASURED_PEAKS.json.
   e2e        same metric through the public host API (HostPipeline over the module chain) with pinned HOST
              buffers: H2D of the clips and D2H of the features inside the timed region.
-  cpu_baseline  the oracle's torch-CPU port of the reference chain on this box's host cores (rank 0, N=1).
+  cpu_baseline  the reference chain on this box's host cores (rank 0, N=1): the UNMODIFIED reference imported from
+             oracle/_ref when that install exists (oracle/build_ref.py, kind "reference"), else the oracle's torch-CPU
+             port of the same call sequence (kind "port").
+  sub        the other BASELINE.json configurations, device-resident like `value`: cfg3 (MFCC 128 mel / 40 coefficients,
+             4096 x 10 s), cfg4 (stereo MidSide + STFT(4096) + PolarIF forward and inverse chains, 1024 clips), cfg5
+             (8192 clips per GPU in 1024-clip micro-batches over distinct data, forward and inverse), eager_cuda (the
+             reference chain moved to this GPU: cuFFT + cuBLAS + ATen) and a >= 1 s sustained run of the headline step.
 """
 import argparse
 import json
@@ -170,54 +176,264 @@ def synth_clips(n, device, seed):
     return x
 
 
-def cpu_port_run(n_clips, iters, seed=1234):
-    """Times the oracle's torch-CPU port of the reference chain (all host threads).  Returns audio-s/s, detail."""
+def host_threads():
+    """Threads the CPU arm may use: every core this process is allowed on (torchrun exports OMP_NUM_THREADS=1, which
+    would otherwise throttle the reference to one thread and inflate every GPU/CPU ratio)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def import_reference():
+    """The unmodified reference package from oracle/_ref (pip --target install made by oracle/build_ref.py; the only
+    shim is a stub `turtle` module for acids_transforms/transforms/misc.py:1).  None when absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "acids_transforms")):
+        return None
+    import types
+    sys.modules.setdefault("turtle", types.ModuleType("turtle"))
+    if not hasattr(sys.modules["turtle"], "forward"):
+        sys.modules["turtle"].forward = None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import acids_transforms as ref
+        return ref
+    except Exception as exc:      # torchaudio missing etc.: fall back to the port and say so
+        sys.stderr.write("bench: oracle/_ref present but not importable (%r); using the torch port\n" % (exc,))
+        return None
+
+
+def reference_chain(ref, device="cpu"):
+    """cfg 2 with the reference's own classes and stock code path."""
+    T = ref.transforms
+    ch = T.DGT(sr=SR, n_fft=N_FFT, hop_length=HOP) + T.Magnitude(sr=SR, mel=True, mode="unipolar", contrast="log1p", n_fft=N_FFT)
+    return ch.to(device) if device != "cpu" else ch
+
+
+def cpu_reference_run(n_clips, iters, seed=1234, scripted=False):
+    """Times the reference's CPU implementation of cfg 2 on `n_clips` clips, all host threads; best of `iters`.
+    Returns (audio-s/s, kind, detail)."""
     import torch
-    from oracle import torch_port as P
-    from oracle import np_oracle as O
-    import numpy as np
+    torch.set_num_threads(host_threads())
     x = synth_clips(n_clips, "cpu", seed)
-    w = P.gaussian_window(N_FFT)
-    fwd, _ = O.magnitude_banks(SR, N_FFT)
-    bank = torch.from_numpy(fwd)[None]
-    off, sc = torch.tensor(0.05), torch.tensor(5.0)
-    P.cfg2_forward(x[:4], w, bank, off, sc)                 # warm-up (thread pool, MKL plans)
-    best = float("inf")
-    times = []
-    for _ in range(iters):
-        t0 = time.perf_counter()
-        P.cfg2_forward(x, w, bank, off, sc)
-        dt = time.perf_counter() - t0
-        times.append(dt)
-        best = min(best, dt)
-    return n_clips * CLIP_S / best, {"times_s": [round(t, 4) for t in times]}
+    ref = import_reference()
+    detail = {}
+    if ref is not None:
+        chain = reference_chain(ref)
+        chain.scale_data(x[:16])
+        fns = {"eager": chain}
+        if scripted:
+            try:
+                fns["scripted"] = torch.jit.script(chain)
+            except Exception as exc:
+                detail["scripted_error"] = repr(exc)[:200]
+        kind = "reference"
+    else:
+        from oracle import torch_port as P
+        from oracle import np_oracle as O
+        w = P.gaussian_window(N_FFT)
+        fwd, _ = O.magnitude_banks(SR, N_FFT)
+        bank = torch.from_numpy(fwd)[None]
+        off, sc = torch.tensor(0.05), torch.tensor(5.0)
+        fns = {"eager": lambda t: P.cfg2_forward(t, w, bank, off, sc)}
+        kind = "port"
+    best = {}
+    for name, fn in fns.items():
+        with torch.no_grad():
+            fn(x[:4])                                      # warm-up (thread pool, MKL plans, JIT profiling runs)
+            fn(x[:4])
+            times = []
+            for _ in range(iters):
+                t0 = time.perf_counter()
+                fn(x)
+                times.append(time.perf_counter() - t0)
+        best[name] = n_clips * CLIP_S / min(times)
+        detail[name + "_times_s"] = [round(t, 4) for t in times]
+        detail[name + "_audio_s_per_s"] = best[name]
+    return best["eager"], kind, detail
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is pure
-    Python on torch CPU ops and cannot travel to this box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (the unmodified
+    package from oracle/_ref; the oracle port only if that install is absent), all host threads, a bounded sample of
+    the workload per step."""
     if rank != 0:
         return
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)               # before torch spins up its pools
+    os.environ["MKL_NUM_THREADS"] = str(n)
     import torch
-    cores = torch.get_num_threads()
-    n_clips = 64
-    x_steps = max(1, args.steps)
-    # warm-up steps are folded into cpu_port_run's own warm-up; time `steps` passes of the 64-clip sample
+    torch.set_num_threads(n)
+    n_clips = 256
+    steps = max(1, args.steps)
     t0 = time.perf_counter()
-    value, detail = cpu_port_run(n_clips, x_steps)
+    value, kind, detail = cpu_reference_run(n_clips, steps, scripted=True)
     wall = time.perf_counter() - t0
-    sample = "%d of the %d clips per step (torch-CPU port of DGT.forward incl. its angle() phase buffer + Magnitude.forward), best of %d" % (
-        n_clips, CLIPS_PER_GPU, x_steps)
+    what = "unmodified reference (oracle/_ref): DGT.forward + Magnitude.forward, eager" if kind == "reference" else \
+           "torch-CPU port of DGT.forward incl. its angle() phase buffer + Magnitude.forward"
+    sample = "%d of the %d clips per step (%s), best of %d" % (n_clips, CLIPS_PER_GPU, what, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_clips * CLIP_S / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_step_timed": n_clips, "where": "host CPU"},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "clips_per_step_timed": n_clips, "where": "host CPU",
+                   "note": "same chain and clip shape as the GPU arm on a %d-clip sample per step instead of %d clips per GPU: "
+                           "a per-clip rate, not a like-for-like batch" % (n_clips, CLIPS_PER_GPU)},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+                         "scripted_value": detail.get("scripted_audio_s_per_s")},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": round(wall, 2), "host": {"cpu_count": os.cpu_count(), "torch_threads": cores},
+        "gpu_launches": 0, "wall_s": round(wall, 2),
+        "host": {"cpu_count": os.cpu_count(), "affinity": n, "torch_threads": torch.get_num_threads()}, "detail": detail,
     }
     print(json.dumps(line), flush=True)
+
+
+def pin_rank_to_cores(local_rank, world):
+    """One slice of the allowed cores per rank (all GPUs of this pool report the same CPU affinity / NUMA node, so the
+    ranks otherwise pile onto the same cores and their copy-engine submissions contend)."""
+    if world <= 1:
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return [mine[0], mine[-1]]
+    except (AttributeError, OSError):
+        return None
+
+
+def copy_ceiling_ms(torch, x_host, out_host, dev, barrier, max_over_ranks, iters=5):
+    """Plain pinned copies of one e2e step's bytes: H2D and D2H concurrently on two streams."""
+    xin = torch.empty(x_host.shape, dtype=x_host.dtype, device=dev)
+    yout = torch.empty(out_host.shape, dtype=out_host.dtype, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def one():
+        cur = torch.cuda.current_stream(dev)
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            xin.copy_(x_host, non_blocking=True)
+        with torch.cuda.stream(s2):
+            out_host.copy_(yout, non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+
+    one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / iters
+
+
+def sub_results(torch, Tr, chain, stft, x, dev, world, peak, timed, fwd_step_ms):
+    """The other BASELINE.json configurations on this rank's GPU, inputs resident in HBM, CUDA events, max over ranks.
+    `frac` = algorithmic bytes / time / measured HBM peak."""
+    res = {}
+    n_local = x.shape[0]
+
+    def entry(ms, n_clips, seconds, bytes_per_clip, **kw):
+        d = {"ms": ms, "audio_s_per_s": world * n_clips * seconds / (ms / 1e3), "gbs": n_clips * bytes_per_clip / ms / 1e6,
+             "frac": n_clips * bytes_per_clip / ms / 1e6 / peak, "clips_per_gpu": n_clips}
+        d.update(kw)
+        return d
+
+    # ---- sustained: the headline step back to back for >= 1 s (clocks / power settle; the K-step number is ~25 ms) ----
+    n_sus = max(200, int(1200.0 / max(fwd_step_ms, 1e-3)))
+    ms = timed(lambda: chain(x), n_sus, 3) / n_sus
+    res["sustained_fwd"] = entry(ms, n_local, CLIP_S, FWD_BYTES_PER_CLIP, steps=n_sus)
+
+    # ---- eager_cuda: the reference chain moved to this GPU (cuFFT + cuBLAS SGEMM + ATen elementwise) ----
+    try:
+        ref = import_reference()
+        with torch.no_grad():
+            if ref is not None:
+                rch = reference_chain(ref, dev)
+                rch.scale_data(x[:16])
+                what = "unmodified reference modules .to(cuda)"
+            else:
+                from oracle import torch_port as P
+                from oracle import np_oracle as O
+                w = P.gaussian_window(N_FFT).to(dev)
+                bank = torch.from_numpy(O.magnitude_banks(SR, N_FFT)[0])[None].to(dev)
+                off, sc = torch.tensor(0.05, device=dev), torch.tensor(5.0, device=dev)
+                rch = lambda t: P.cfg2_forward(t, w, bank, off, sc)
+                what = "torch port of the reference chain on cuda"
+            ms = timed(lambda: rch(x), 5, 3) / 5
+        res["eager_cuda"] = entry(ms, n_local, CLIP_S, FWD_BYTES_PER_CLIP, what=what, speedup_of_fused=ms / fwd_step_ms)
+        del rch
+    except Exception as exc:          # the reference has CPU-only index tensors on some paths (SURVEY.md 8a)
+        res["eager_cuda"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
+
+    # ---- cfg 3: MFCC(n_fft=2048, hop=512, 128 mels) on 4096 x 10 s; reference semantics (mel spectrogram) and 40 coefficients ----
+    B3, L3, N3, H3, M3 = 4096, 441000, 2048, 512, 128
+    T3 = 1 + L3 // H3
+    g = torch.Generator(device=dev).manual_seed(77)
+    x3 = torch.empty((B3, L3), device=dev)
+    for i in range(0, B3, 512):
+        x3[i:i + 512] = 0.5 * (2 * torch.rand((512, L3), generator=g, device=dev) - 1)
+    m128 = Tr.MFCC(n_fft=N3, hop_length=H3, n_mels=M3).to(dev)
+    ms = timed(lambda: m128(x3), 5, 3) / 5
+    res["cfg3_mel128"] = entry(ms, B3, 10, 4 * L3 + 4 * M3 * T3)
+    m40 = Tr.MFCC(n_fft=N3, hop_length=H3, n_mels=M3, n_mfcc=40).to(dev)
+    ms = timed(lambda: m40(x3), 5, 3) / 5
+    res["cfg3_mfcc40"] = entry(ms, B3, 10, 4 * L3 + 4 * 40 * T3)
+    del x3, m128, m40
+    torch.cuda.empty_cache()
+
+    # ---- cfg 4: MidSide + STFT(4096, 1024) + PolarIF on 1024 stereo 4 s clips, forward and inverse chains ----
+    B4, N4, H4 = 1024, 4096, 1024
+    T4, F4 = 1 + L // H4, N4 // 2 + 1
+    x4 = torch.empty((B4, 2, L), device=dev)
+    for i in range(0, B4, 256):
+        x4[i:i + 256] = 0.5 * (2 * torch.rand((256, 2, L), generator=g, device=dev) - 1)
+    ch4 = (Tr.MidSide() + Tr.STFT(n_fft=N4, hop_length=H4) + Tr.PolarIF(
+        magnitude_args={"mode": "bipolar", "n_fft": N4}, phase_args={"mode": "bipolar"})).to(dev)
+    ch4.scale_data(x4[:8])
+    y4 = ch4(x4)
+    ms = timed(lambda: ch4(x4), 5, 3) / 5
+    res["cfg4_fwd"] = entry(ms, B4, CLIP_S, 2 * (4 * L + 8 * T4 * F4), out_shape=list(y4.shape))
+    ms = timed(lambda: ch4.invert(y4), 5, 3) / 5
+    res["cfg4_inv"] = entry(ms, B4, CLIP_S, 2 * (8 * T4 * F4 + 4 * H4 * (T4 - 1)))
+    del x4, y4, ch4
+    torch.cuda.empty_cache()
+
+    # ---- cfg 5: 8192 clips per GPU in 1024-clip micro-batches over DISTINCT data, forward and inverse sweep ----
+    B5, MB = 8192, 1024
+    x5 = torch.empty((B5, L), device=dev)
+    for i in range(0, B5, MB):
+        x5[i:i + MB] = synth_clips(MB, dev, 4321 + i)
+    outs = [None] * (B5 // MB)       # the module API allocates its output: distinct inputs AND outputs per micro-batch
+
+    def fwd_sweep():
+        for j, i in enumerate(range(0, B5, MB)):
+            outs[j] = chain(x5[i:i + MB])
+
+    ms = timed(fwd_sweep, 3, 3) / 3
+    res["cfg5_fwd"] = entry(ms, B5, CLIP_S, FWD_BYTES_PER_CLIP, micro_batch=MB)
+    outs = [None] * (B5 // MB)
+    torch.cuda.empty_cache()
+    X5 = [stft(x5[i:i + MB]) for i in range(0, B5, MB)]          # 23 GB of spectra, resident
+    del x5
+    wav = [None] * len(X5)
+
+    def inv_sweep():
+        for j, Xj in enumerate(X5):
+            wav[j] = stft.invert(Xj)
+
+    ms = timed(inv_sweep, 3, 3) / 3
+    res["cfg5_inv"] = entry(ms, B5, CLIP_S, INV_BYTES_PER_CLIP, micro_batch=MB)
+    del X5, wav
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -229,6 +445,7 @@ def main():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the cfg3 / cfg4 / cfg5 / eager_cuda / sustained sub-results")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -250,6 +467,7 @@ def main():
 
     _lib.load()                                   # no CUDA extension -> fail loudly, there is no fallback
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    pinned_cores = pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -334,11 +552,24 @@ def main():
             barrier()
             groups.append(max_over_ranks(e0.elapsed_time(e1)) / e2e_steps)
         e2e_ms = sorted(groups)[1]
-        e2e = {"value": world * n_e2e * CLIP_S / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+        # what the box's host path allows: the same bytes as plain pinned copies, H2D and D2H on two streams at once, on
+        # every rank at the same time, no kernel and no Python between them
+        probe_ms = copy_ceiling_ms(torch, x_host, out_host, dev, barrier, max_over_ranks)
+        e2e_value = world * n_e2e * CLIP_S / (e2e_ms / 1e3)
+        ceiling = world * n_e2e * CLIP_S / (probe_ms / 1e3)
+        e2e = {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "clips_per_step": n_e2e, "ms_per_step": e2e_ms,
                "ms_per_step_groups": [round(g, 3) for g in groups], "steps_per_group": e2e_steps,
-               "api": "HostPipeline(DGT + Magnitude)(pinned host tensor) -> pinned host tensor"}
+               "api": "HostPipeline(DGT + Magnitude)(pinned host tensor) -> pinned host tensor",
+               "copy_ceiling": {"value": ceiling, "unit": "audio-s/s", "ms_per_step": probe_ms,
+                                "h2d_gbs": pipe.h2d_bytes / probe_ms / 1e6, "d2h_gbs": pipe.d2h_bytes / probe_ms / 1e6,
+                                "how": "cudaMemcpyAsync of the same pinned buffers, H2D || D2H, all ranks at once, max over ranks"},
+               "frac_of_copy_ceiling": e2e_value / ceiling, "pinned_cores": pinned_cores}
         del x_host, out_host
+
+    sub = None
+    if not args.no_sub:
+        sub = sub_results(torch, Tr, chain, stft, x, dev, world, peak, timed, fwd_step_ms)
 
     clk.__exit__()
     clocks = clk.summary()
@@ -346,10 +577,10 @@ def main():
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
-        v, detail = cpu_port_run(256, 5)
-        cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": "256 of the 1024 clips (torch-CPU port of the reference chain, oracle/torch_port.py), best of 5 passes"}
+        v, kind, detail = cpu_reference_run(256, 5)
+        cpu = {"value": v, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "256 of the 1024 clips (%s), best of 5 passes" % (
+                   "unmodified reference from oracle/_ref, eager" if kind == "reference" else "torch-CPU port of the reference chain, oracle/torch_port.py")}
 
     if rank == 0:
         kname = "stft_fwd_kernel<Fwd1024,MODE_REAL>"
@@ -367,7 +598,7 @@ def main():
                         "roofline": {"bound": "hbm", "kernel": "istft_ola_kernel<Inv1024>", "achieved": inv_gbs, "peak": peak,
                                      "unit": "GB/s", "frac": inv_gbs / peak, "traffic": traffic_from_profiles("istft_ola_kernel<Inv1024>"),
                                      "algorithmic_bytes_per_launch": n_local * INV_BYTES_PER_CLIP}},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": args.steps, "clocks": clocks,
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": args.steps, "clocks": clocks, "sub": sub,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
