@@ -35,6 +35,8 @@ _PROTOTYPES = {
     "acids_stft_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int64, _P, _P]),
     "acids_stft_mag_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int64, Band, c_int,
                                    c_float, _P, _P, c_int, _P, c_int64, c_int64, _P]),
+    "acids_stft_polar_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int64, c_int, Band, c_int, c_float,
+                                     _P, _P, c_int, c_int, c_int, _P, _P, c_int, _P, c_int64, c_int64, _P, c_int64, c_int64, _P]),
     "acids_mag_epilogue": (c_int, [_P, c_int64, c_int, Band, c_int, c_float, _P, _P, c_int, _P, c_int64, _P]),
     "acids_mag_invert": (c_int, [_P, c_int64, c_int, c_int64, c_int, Band, c_int, c_float, _P, _P, _P, _P]),
     "acids_melspec_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int64, Band, c_float, _P, _P, _P, _P]),

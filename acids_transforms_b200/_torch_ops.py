@@ -19,7 +19,7 @@ _SCHEMAS = {
                     "float eps, Tensor? offset, Tensor? scale, bool drop_first) -> Tensor",
     "stft_polar_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, "
                       "float eps, Tensor? mag_offset, Tensor? mag_scale, int phase_mode, int method, bool weighted, "
-                      "Tensor? ph_offset, Tensor? ph_scale, bool drop_first) -> Tensor",
+                      "Tensor? ph_offset, Tensor? ph_scale, bool drop_first, int midside=0) -> Tensor",
     "mag_epilogue": "(Tensor X, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? offset, "
                     "Tensor? scale, bool drop_first) -> Tensor",
     "mag_invert": "(Tensor y, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, Tensor? offset, "
@@ -57,9 +57,15 @@ def _stft_mag_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contras
 
 
 def _stft_polar_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contrast: int, eps: float, mag_offset, mag_scale,
-                    phase_mode: int, method: int, weighted: bool, ph_offset, ph_scale, drop_first: bool):
-    """wave -> stacked [..., T, 2, F'] (Polar / PolarIF after an STFT): the spectrum is produced once and
-    consumed by the two representation kernels writing straight into their slot of the stacked tensor."""
+                    phase_mode: int, method: int, weighted: bool, ph_offset, ph_scale, drop_first: bool, midside: int = 0):
+    """[MidSide ->] STFT -> Polar / PolarIF, wave -> stacked [..., T, 2, F'].  One kernel when the phase mode needs no scan
+    over the frames (raw phase, forward-difference IF); otherwise the spectrum is produced once and consumed by the two
+    representation kernels writing straight into their slot of the stacked tensor."""
+    if ops.fusable_phase(phase_mode, method):
+        return ops.stft_polar_fwd(x, window, n_fft, hop, ops.as_band(band_meta, band_coef), contrast, eps, mag_offset, mag_scale,
+                                  phase_mode, method, weighted, ph_offset, ph_scale, drop_first, midside)
+    if midside:
+        x = ops.midside(x, midside == 2, False)
     X = ops.stft_fwd(x, window, n_fft, hop, True)
     return _polar_fwd(X, band_meta, band_coef, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted,
                       ph_offset, ph_scale, drop_first)

@@ -77,6 +77,55 @@ __device__ __forceinline__ void stg_stream1(float* p, float x) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(x) : "memory");
 }
 
+// ---- phase helpers shared by the phase kernels (spectral_repr.cu) and the fused STFT -> Polar epilogue ----
+#define ACIDS_PI_F 3.14159265358979323846f
+#define ACIDS_2PI_F 6.28318530717958647692f
+#define ACIDS_INV_PI_F 0.31830988618379067154f
+#define ACIDS_INV_2PI_F 0.15915494309189533577f
+
+// atan2 for the phase kernels: |error| < 1e-7 rad (3e-8 of the +-pi range; the parity budget is 1e-4).
+// One approximate division to map the argument into [0, 1], the degree-16 even minimax polynomial of atan(a)/a
+// (Abramowitz & Stegun 4.4.49, |eps| <= 2e-8), octant fix-ups, IEEE sign of zero: atan2(+0, x < 0) = +pi and
+// atan2(-0, x < 0) = -pi (the DC and Nyquist bins carry an exact +0 imaginary part).  ~25 instructions instead of the
+// ~50 of atan2f: the phase kernel is issue bound (82 % issue-slot utilisation measured), not memory bound.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float z = a * a;
+    float p = 0.0028662257f;
+    p = fmaf(p, z, -0.0161657367f);
+    p = fmaf(p, z, 0.0429096138f);
+    p = fmaf(p, z, -0.0752896400f);
+    p = fmaf(p, z, 0.1065626393f);
+    p = fmaf(p, z, -0.1420889944f);
+    p = fmaf(p, z, 0.1999355085f);
+    p = fmaf(p, z, -0.3333314528f);
+    float r = fmaf(p * z, a, a);
+    r = ay > ax ? 1.57079632679489661923f - r : r;
+    r = x < 0.f ? 3.14159265358979323846f - r : r;
+    return copysignf(r, y);
+}
+
+__device__ __forceinline__ float unwrap_correction(float d) {
+    // utils/misc.py:19-24: ddmod = (d + pi) % 2pi - pi (python remainder); +pi when it lands on -pi going up
+    // d is a difference of two principal values, so x = d + pi lies in [-pi, 3 pi]: the float remainder (exact, like
+    // fmodf) reduces to one conditional subtraction (exact by Sterbenz' lemma), then python's sign fix-up
+    const float x = d + ACIDS_PI_F;
+    float r = x >= ACIDS_2PI_F ? x - ACIDS_2PI_F : x;
+    if (r < 0.f) r += ACIDS_2PI_F;
+    float dd = r - ACIDS_PI_F;
+    if (dd == -ACIDS_PI_F && d > 0.f) dd = ACIDS_PI_F;
+    return fabsf(d) < ACIDS_PI_F ? 0.f : dd - d;
+}
+
+__device__ __forceinline__ float if_weight(int t, int T) {
+    // spectral_repr.py:341-342
+    const float N = (float)T, n = (float)t;
+    const float a = (n - (N / 2.f - 1.f)) / (N / 2.f);
+    return (1.5f * N) / (N * N - 1.f) * (1.f - a * a);
+}
+
 // ---- epilogue shared by the fused STFT kernel and the stand-alone Magnitude kernels -------------
 //
 // Banded matrix, "group-ELL" layout (built by the host, see ops.BandedMatrix): output columns are taken

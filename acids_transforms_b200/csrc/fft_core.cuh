@@ -42,7 +42,7 @@ struct alignas(16) cf2 { cf a, b; };
 #endif
 
 ACIDS_HD cf mk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(ACIDS_NO_PACKED)     // ACIDS_NO_PACKED: tuning experiment (scalar FADD / FFMA instead)
 // Blackwell packed FP32 (CUDA 12.9 float2 builtins -> FADD2 / FMUL2 / FFMA2): a complex value is one aligned
 // register pair, so a complex add / sub is ONE instruction and a complex multiply TWO
 // (FMUL2 a, w.x ; FFMA2 swap(a) * (-w.y, +w.y) + .) — ptxas folds the swap, the per-half sign and the scalar

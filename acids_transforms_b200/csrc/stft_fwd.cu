@@ -70,10 +70,11 @@ int fill_epilogue(EpiParams& ep, acids_band band, int n_bins, int contrast, floa
 }
 
 // which kernel variant serves a fused launch: where the band lives, and (mel-spectrogram) the exponent
-static int real_variant(FwdParams& p, bool melspec) {
+static int real_variant(FwdParams& p, bool melspec, bool polar = false) {
     const bool band = p.ep.meta != nullptr;
     const bool in_smem = band && p.ep.band_bytes_meta > 0;
     p.band_smem_bytes = in_smem ? (int)round16((size_t)p.ep.band_bytes_meta + p.ep.band_bytes_coef) : 0;
+    if (polar) return !band ? VAR_POLAR_NOBAND : (in_smem ? VAR_POLAR_SMEM : VAR_POLAR_GLOBAL);
     if (!melspec) return !band ? VAR_MAG_NOBAND : (in_smem ? VAR_MAG_SMEM : VAR_MAG_GLOBAL);
     if (p.power == 2.0f) return in_smem ? VAR_MEL_POWER_SMEM : VAR_MEL_POWER_GLOBAL;
     return in_smem ? VAR_MEL_ANY_SMEM : VAR_MEL_ANY_GLOBAL;
@@ -129,4 +130,37 @@ extern "C" ACIDS_API int acids_melspec_fwd(const float* x, int64_t B, int64_t L,
     p.out = out; p.out_clip_stride = (int64_t)mel.n_out * n_frames; p.out_row_stride = 1; p.out_col_stride = n_frames;
     p.power = power;
     return dispatch_fwd(real_variant(p, true), n_fft, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" ACIDS_API int acids_stft_polar_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window, int n_fft,
+                                    int hop, int64_t n_frames, int midside, acids_band band, int contrast, float eps,
+                                    const float* mag_offset, const float* mag_scale, int phase_mode, int if_method,
+                                    int weighted, const float* ph_offset, const float* ph_scale, int drop_first,
+                                    float* mag_out, int64_t mag_clip_stride, int64_t mag_row_stride, float* ph_out,
+                                    int64_t ph_clip_stride, int64_t ph_row_stride, void* stream) {
+    FwdParams p{};
+    ACIDS_REQUIRE(midside >= 0 && midside <= 2, ACIDS_EINVAL, "stft_polar_fwd: midside must be 0, 1 or 2");
+    ACIDS_REQUIRE(!midside || (B % 2 == 0 && ldx == L), ACIDS_EINVAL,
+                  "stft_polar_fwd: the MidSide prologue takes contiguous stereo pairs (B=%lld even, ldx == L)", (long long)B);
+    // the frame-difference scheme that needs no scan over the frames: raw phase, or forward-difference IF; the unwrapped
+    // phase and the backward / central differences stay on acids_phase_fwd (the caller falls back)
+    ACIDS_REQUIRE(phase_mode == ACIDS_PHASE_RAW || (phase_mode == ACIDS_PHASE_IF && if_method == ACIDS_IF_FORWARD), ACIDS_ENOTSUP,
+                  "stft_polar_fwd: only the raw phase and the forward-difference IF are fused (mode %d, method %d)", phase_mode, if_method);
+    int rc = fill_common(p, x, B, L, ldx, window, n_fft, hop, 1, n_frames);
+    if (rc) return rc;
+    rc = fill_epilogue(p.ep, band, n_fft / 2 + 1, contrast, eps, drop_first, kBandSmemBudget);
+    if (rc) return rc;
+    ACIDS_REQUIRE(p.ep.n_cols == n_fft / 2 + 1, ACIDS_EINVAL,
+                  "stack expects each tensor to be equal size, but got [%d] and [%d] bins", p.ep.n_cols - drop_first, n_fft / 2 + 1 - drop_first);
+    ACIDS_REQUIRE(mag_out && ph_out, ACIDS_EINVAL, "stft_polar_fwd: NULL output");
+    ACIDS_REQUIRE(mag_row_stride >= 0 && ph_row_stride >= 0 && (n_frames + 4) * mag_row_stride < ((int64_t)1 << 31) &&
+                  (n_frames + 4) * ph_row_stride < ((int64_t)1 << 31), ACIDS_ENOTSUP, "stft_polar_fwd: more than 2^31 output elements per clip");
+    p.offset_ptr = mag_offset; p.scale_ptr = mag_scale;
+    p.out = mag_out; p.out_clip_stride = mag_clip_stride; p.out_row_stride = mag_row_stride; p.out_col_stride = 1;
+    p.power = 1.0f;
+    p.midside = midside;
+    p.ph_out = ph_out; p.ph_clip_stride = ph_clip_stride; p.ph_row_stride = ph_row_stride;
+    p.ph_offset_ptr = ph_offset; p.ph_scale_ptr = ph_scale;
+    p.ph_mode = phase_mode; p.ph_weighted = weighted;
+    return dispatch_fwd(real_variant(p, false, true), n_fft, p, static_cast<cudaStream_t>(stream));
 }

@@ -7,9 +7,11 @@
 
 namespace acids {
 
-enum { MODE_COMPLEX = 0, MODE_REAL = 1 };
+// MODE_POLAR = MODE_REAL plus a second output: the raw phase or the forward-difference instantaneous frequency of every
+// bin (Polar / PolarIF right after the STFT, spectral_repr.py:431-440) — the spectrum never reaches HBM
+enum { MODE_COMPLEX = 0, MODE_REAL = 1, MODE_POLAR = 2 };
 enum { VAR_COMPLEX = 0, VAR_MAG_NOBAND, VAR_MAG_SMEM, VAR_MAG_GLOBAL, VAR_MEL_POWER_SMEM, VAR_MEL_POWER_GLOBAL, VAR_MEL_ANY_SMEM,
-       VAR_MEL_ANY_GLOBAL };
+       VAR_MEL_ANY_GLOBAL, VAR_POLAR_NOBAND, VAR_POLAR_SMEM, VAR_POLAR_GLOBAL };
 
 struct FwdParams {
     const float* x;
@@ -25,6 +27,15 @@ struct FwdParams {
     float power;     // MODE_REAL: value = |X|^power (1 -> magnitude, 2 -> power spectrum)
     int vec_ok;      // clip rows and frame starts are aligned for the first pass's vector loads (bit 0: 8 B, bit 1: 16 B)
     int band_smem_bytes;   // shared memory reserved for the banded matrix (16-byte multiple; 0: read it from global)
+    // raw-domain prologue folded into the loads: x is [B / 2, 2, L] stereo and clip 2 b + c is channel c of
+    // MidSide.forward (raw.py:145-161): mid = (l + r) / 2 [/ sqrt 2 when midside == 2], side = (l - r) / 2
+    int midside;
+    // MODE_POLAR: the phase output (rows like `out`), its normalisation, ACIDS_PHASE_RAW or ACIDS_PHASE_IF (forward differences)
+    float* ph_out;
+    int64_t ph_clip_stride, ph_row_stride;
+    const float* ph_offset_ptr;
+    const float* ph_scale_ptr;
+    int ph_mode, ph_weighted;
 };
 
 // launch shape per plan: small frame groups run 128-thread CTAs at 4 CTAs / SM (<= 128 registers)
@@ -50,7 +61,7 @@ struct FwdCfg {
     // for both, and the epilogue amortises a column's metadata / coefficients / dispatch over twice the rows.  Costs
     // registers: 168 per thread, 3 CTAs / SM (n_fft = 1024: 1.17 -> see DESIGN.md section 5).
     static constexpr int FPW = P::N == 1024 ? ACIDS_FWD_FPW_1024 : 1;
-    static constexpr int THREADS = (P::N == 1024 && MODE == 1 /* MODE_REAL */) ? ACIDS_FWD_THREADS_1024
+    static constexpr int THREADS = (P::N == 1024 && MODE != 0 /* MODE_REAL, MODE_POLAR */) ? ACIDS_FWD_THREADS_1024
                                                 : (P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256)));
     static constexpr int MINB = FPW > 1 ? 3 : (P::T <= 32 ? ACIDS_FWD_MINB_SMALL * 128 / THREADS : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1)));
     // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
@@ -89,7 +100,9 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     constexpr int THREADS = C::THREADS;
     constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW, FPW = C::FPW;
     constexpr int R0 = P::radix(0), B0 = P::bpt(0), NB0 = P::nb(0);
-    constexpr bool RIE = MODE == MODE_REAL && C::ROWS_IN_EXCH;
+    constexpr bool REALISH = MODE != MODE_COMPLEX, POLAR = MODE == MODE_POLAR;
+    constexpr bool RIE = REALISH && C::ROWS_IN_EXCH;
+    static_assert(!POLAR || !RIE, "the polar epilogue keeps its rows in their own buffers");
     using FFT = FrameFFT<P, false>;
     using PR = typename FFT::PR;
     constexpr int RP = PR::R, NBP = PR::NB;
@@ -108,7 +121,9 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         swin[n] = make_float2(0.5f * __ldg(p.window + 2 * n), 0.5f * __ldg(p.window + 2 * n + 1));
     EpiArgs ea{};
     float* vrows = nullptr;
-    if (MODE == MODE_REAL) {
+    float* prows = nullptr;      // POLAR: raw phase rows of the unit
+    float* pcarry = nullptr;     // POLAR: last phase row of the previous units (rotating)
+    if (REALISH) {
         unsigned char* bandmem = smem_raw + C::exch_bytes() + C::win_bytes();
         int32_t* smeta = reinterpret_cast<int32_t*>(bandmem);
         float* scoef = reinterpret_cast<float*>(bandmem + p.ep.band_bytes_meta);
@@ -118,6 +133,19 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         // |X| rows of a unit: in the frames' exchange buffers (RIE), or double buffered so that the next unit's FFT never
         // waits for the slowest epilogue thread
         vrows = RIE ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(bandmem + (BAND == BAND_SMEM ? p.band_smem_bytes : 0));
+        // POLAR: raw phase rows.  G == 1: three rotating rows (the previous frame's row is the previous unit's);
+        // G > 1: double-buffered unit tiles like vrows plus three rotating carry rows holding the last row of a unit.
+        // Three, not two: a thread that has left the epilogue of unit u writes unit u + 1's rows while a slower one may
+        // still read unit u - 1's last row; by unit u + 2 everybody has passed the barrier of unit u + 1.
+        if (POLAR) {
+            prows = vrows + 2 * G * VSTR;
+            pcarry = G == 1 ? prows : prows + 2 * G * VSTR;
+        }
+    }
+    float ph_off = 0.f, ph_inv = 1.f;
+    if (POLAR) {
+        ph_off = p.ph_offset_ptr ? __ldg(p.ph_offset_ptr) : 0.f;
+        ph_inv = p.ph_scale_ptr ? 1.0f / __ldg(p.ph_scale_ptr) : 1.0f;
     }
     __syncthreads();
 
@@ -126,6 +154,10 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     const int64_t total = p.B * upc;
     const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
     const int L = (int)p.L;                              // < 2^31 - 2 n_fft (checked by the host)
+    // POLAR with frame differences: a CTA whose run starts inside a clip first runs the unit before it without
+    // storing anything (a halo), so that the phase row of the frame preceding its first one is there (0.3 % extra work)
+    const bool ph_if = POLAR && p.ph_mode == ACIDS_PHASE_IF;
+    const int64_t ustart = (ph_if && u0 < u1 && (u0 % upc) != 0) ? u0 - 1 : u0;
 
     // Raw (un-windowed) samples of frame (b, t) in first-pass operand order.  Interior, aligned frames: vector
     // loads straight into registers.  Edge frames (torch.stft center=True, pad_mode="reflect") and unaligned
@@ -135,7 +167,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     // zero-filling their registers they re-read an interior frame of the same clip when there is one.
     const int t_safe = (p.pad + p.hop - 1) / p.hop;
     const bool has_safe = t_safe < n_frames && t_safe * p.hop - p.pad + N <= L;
-    auto fetch_fast = [&](cf* v, const float* __restrict__ xb, int t) -> bool {
+    auto fetch_fast = [&](cf* v, const float* __restrict__ xb, int t, float ms_sign, float ms_gain) -> bool {
         const bool valid = t < n_frames;
         if (!valid && has_safe) t = t_safe;
 #ifdef ACIDS_DEBUG_NOLOAD       // tuning experiment only: every frame reads the same (cached) samples
@@ -156,14 +188,23 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
                     if (VW == 4) {
 #pragma unroll
                         for (int b0 = 0; b0 < B0; b0 += 2) {
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
+                            float4 a = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
+                            if (p.midside) {
+                                const float4 o = __ldg(reinterpret_cast<const float4*>(src + p.ldx) + (b0 >> 1));
+                                a = make_float4(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain,
+                                                fmaf(ms_sign, o.z, a.z) * ms_gain, fmaf(ms_sign, o.w, a.w) * ms_gain);
+                            }
                             v[b0 * R0 + r] = mk(a.x, a.y);
                             v[(b0 + 1) * R0 + r] = mk(a.z, a.w);
                         }
                     } else {
 #pragma unroll
                         for (int b0 = 0; b0 < B0; ++b0) {
-                            const float2 a = __ldg(reinterpret_cast<const float2*>(src) + b0);
+                            float2 a = __ldg(reinterpret_cast<const float2*>(src) + b0);
+                            if (p.midside) {
+                                const float2 o = __ldg(reinterpret_cast<const float2*>(src + p.ldx) + b0);
+                                a = make_float2(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain);
+                            }
                             v[b0 * R0 + r] = mk(a.x, a.y);
                         }
                     }
@@ -175,7 +216,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         }
         return stage;
     };
-    auto fetch_staged = [&](cf* v, cf* s, const float* __restrict__ xb, int t) {
+    auto fetch_staged = [&](cf* v, cf* s, const float* __restrict__ xb, int t, float ms_sign, float ms_gain) {
         const bool valid = t < n_frames;
         const int s0i = t * p.hop - p.pad;
         float* sf = reinterpret_cast<float*>(s);
@@ -185,7 +226,9 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             if (k < 0) k = -k;
             if (k >= L) k = 2 * (L - 1) - k;
             k = k < 0 ? 0 : (k >= L ? L - 1 : k);
-            sf[i] = valid ? __ldg(xb + k) : 0.f;
+            float smp = valid ? __ldg(xb + k) : 0.f;
+            if (p.midside && valid) smp = fmaf(ms_sign, __ldg(xb + p.ldx + k), smp) * ms_gain;
+            sf[i] = smp;
         }
         gsync();
 #pragma unroll
@@ -193,34 +236,57 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
             for (int r = 0; r < R0; ++r) v[b0 * R0 + r] = *reinterpret_cast<const cf*>(sf + 2 * fft.template in_index<0>(b0, r));
     };
+    // MidSide folded into the loads: (sign, gain) of the clip being fetched — channel 0: (l + r) gain, channel 1: (l - r) / 2
+    float ms_s = 1.f, ms_g = 1.f;
     auto fetch = [&](cf* v, cf* s, const float* __restrict__ xb, int t) {
-        if (fetch_fast(v, xb, t)) fetch_staged(v, s, xb, t);
+        if (fetch_fast(v, xb, t, ms_s, ms_g)) fetch_staged(v, s, xb, t, ms_s, ms_g);
     };
 
     // clip and unit-in-clip advance incrementally: no division, no 64-bit multiply per frame
-    int64_t b = u0 / upc;
-    int uc = (int)(u0 - b * upc);
-    const float* __restrict__ xclip = p.x + b * p.ldx;                // clip of the NEXT unit (the one being fetched)
+    int64_t b = ustart / upc;
+    int uc = (int)(ustart - b * upc);
+    // clip of the NEXT unit (the one being fetched); with MidSide: the LEFT row of the clip's stereo pair
+    const float* __restrict__ xclip = p.midside ? p.x + (b >> 1) * 2 * p.ldx : p.x + b * p.ldx;
+    int ms_ch = (int)(b & 1);
+    const float ms_mid_gain = p.midside == 2 ? 0.35355339059327376220f : 0.5f;      // 1/2 or 1/(2 sqrt 2) (raw.py:151-155)
+    auto ms_update = [&]() {
+        if (p.midside) {
+            ms_s = ms_ch ? -1.f : 1.f;
+            ms_g = ms_ch ? 0.5f : ms_mid_gain;
+        }
+    };
+    ms_update();
     float* __restrict__ oclip = MODE == MODE_COMPLEX ? p.out + b * ((int64_t)n_frames * P::F * 2) : p.out + b * p.out_clip_stride;
     const int64_t oclip_step = MODE == MODE_COMPLEX ? (int64_t)n_frames * P::F * 2 : p.out_clip_stride;
     int buf = 0;
+    int pidx = 0;                    // POLAR: rotating index (0..2) of the carry row this unit writes
     cf v[FPW][V];
     bool pend[FPW];                  // RIE: frames of the next unit that must be staged once the rows have been consumed
     const float* __restrict__ pend_clip = xclip;
+    float pend_s = 1.f, pend_g = 1.f;
 #pragma unroll
     for (int f = 0; f < FPW; ++f) pend[f] = false;
+    float* __restrict__ phclip = POLAR ? p.ph_out + b * p.ph_clip_stride : nullptr;
     if (u0 < u1) {
 #pragma unroll
         for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
     }
-    for (int64_t u = u0; u < u1; ++u) {
+    for (int64_t u = ustart; u < u1; ++u) {
         const int tb = uc * G + g * FPW;             // first frame of this group in the unit
         const int cur_uc = uc;
         float* __restrict__ const cur_out = oclip;
+        float* __restrict__ const cur_ph = phclip;
         if (++uc == upc) {
             uc = 0;
-            xclip += p.ldx;
+            if (p.midside) {
+                ms_ch ^= 1;
+                if (!ms_ch) xclip += 2 * p.ldx;
+                ms_update();
+            } else {
+                xclip += p.ldx;
+            }
             oclip += oclip_step;
+            if (POLAR) phclip += p.ph_clip_stride;
         }
 
         if (RIE) {
@@ -233,7 +299,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
                 __syncthreads();
 #pragma unroll
                 for (int f = 0; f < FPW; ++f)
-                    if (pend[f]) fetch_staged(v[f], s0 + f * P::SMEM_CF, pend_clip, tb + f);
+                    if (pend[f]) fetch_staged(v[f], s0 + f * P::SMEM_CF, pend_clip, tb + f, pend_s, pend_g);
             }
             // ---- window (first-pass operand order, same adjacency as the loads) ----
 #pragma unroll
@@ -335,7 +401,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         }
         if (RIE) gsync();    // every lane has read the last pass's operands: the buffers may take the |X| rows
 
-        if (MODE == MODE_COMPLEX) {
+        if (!REALISH) {
 #pragma unroll
             for (int f = 0; f < FPW; ++f) {
                 // ---- untangle in registers ----
@@ -389,13 +455,44 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
                     }
                 }
                 if (tid == 0) val[M / 2] = pow_value<PMODE>(ex, p.power);
+                if (POLAR) {
+                    // raw phase of every bin, same row layout; the unit's last row also goes to the rotating carry row
+                    float* __restrict__ pval = G == 1 ? prows + pidx * VSTR : prows + buf * (G * VSTR) + (g * FPW + f) * VSTR;
+                    const bool last = G > 1 && (g * FPW + f) == G - 1;
+                    const int cd = last ? (int)((pcarry + pidx * VSTR) - pval) : 0;      // carry row relative to the tile row
+#pragma unroll
+                    for (int c = 0; c < PR::PC; ++c) {
+                        float* lo = pval + PR::klo(tid, c);
+                        float* hi = pval + PR::khi(tid, c);
+                        float* mlo = pval + (M - PR::klo(tid, c));
+                        float* mhi = pval + (M - PR::khi(tid, c));
+#pragma unroll
+                        for (int q = 0; q < RP; ++q) {
+                            const float a1 = fast_atan2f(o1[c * RP + q].y, o1[c * RP + q].x);
+                            const float a2 = fast_atan2f(o2[c * RP + q].y, o2[c * RP + q].x);
+                            (q < RP / 2 ? lo : hi)[q * NBP] = a1;
+                            (q < RP / 2 ? mlo : mhi)[-q * NBP] = a2;
+                            if (last) {
+                                (q < RP / 2 ? lo : hi)[q * NBP + cd] = a1;
+                                (q < RP / 2 ? mlo : mhi)[-q * NBP + cd] = a2;
+                            }
+                        }
+                    }
+                    if (tid == 0) {
+                        const float ae = fast_atan2f(ex.y, ex.x);
+                        pval[M / 2] = ae;
+                        if (last) pval[M / 2 + cd] = ae;
+                    }
+                }
             }
             // v, o1, o2 are dead: start fetching the next frame's samples, they land during the epilogue
             if (u + 1 < u1) {
                 pend_clip = xclip;
+                pend_s = ms_s;
+                pend_g = ms_g;
 #pragma unroll
                 for (int f = 0; f < FPW; ++f) {
-                    if (RIE) pend[f] = fetch_fast(v[f], xclip, uc * G + g * FPW + f);
+                    if (RIE) pend[f] = fetch_fast(v[f], xclip, uc * G + g * FPW + f, ms_s, ms_g);
                     else fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
                 }
             }
@@ -403,7 +500,8 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             // have passed the next barrier, i.e. every thread has left this epilogue.  RIE: see the barrier at the loop top.)
             __syncthreads();
             const int t0 = cur_uc * G;
-            const int n_valid = min(G, n_frames - t0);
+            const bool halo = POLAR && u < u0;           // the unit before the CTA's run: rows only, nothing is stored
+            const int n_valid = halo ? 0 : min(G, n_frames - t0);
             const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
             float* out0 = cur_out + (TRANSPOSED ? t0 : t0 * rs);
             constexpr bool SPREAD = !TRANSPOSED;
@@ -417,6 +515,36 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
                     epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, 0, SPREAD>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
                                                                                        out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
             }
+            if (POLAR) {
+                // ---- phase epilogue: raw phase, or the forward-difference IF of spectral_repr.py:319-323 as the wrapped
+                // difference of two consecutive raw phases (= the difference of the unwrapped phases of utils/misc.py:12-26
+                // without the running sum), the +-pi scalings of spectral_repr.py:352-356, weighting, normalisation ----
+                const float* __restrict__ pb = G == 1 ? prows + pidx * VSTR : prows + buf * (G * VSTR);
+                const float* __restrict__ pprev = pcarry + (pidx == 0 ? 2 : pidx - 1) * VSTR;
+                const int df = p.ep.drop_first, n_keep = P::F - df;
+                const int prs = (int)p.ph_row_stride;
+#pragma unroll 1
+                for (int g0 = 0; g0 < n_valid; ++g0) {
+                    const int t = t0 + g0;
+                    const float* __restrict__ cur = pb + g0 * VSTR + df;
+                    const float* __restrict__ prv = g0 > 0 ? cur - VSTR : pprev + df;
+                    float* __restrict__ o = cur_ph + (int64_t)t * prs;
+                    const bool diff = ph_if && t > 0;
+                    const float s_pi = (ph_if && t < n_frames - 1) ? ACIDS_INV_PI_F : 1.f;
+                    const float wgt = p.ph_weighted ? if_weight(t, n_frames) : 1.f;
+                    for (int k = threadIdx.x; k < n_keep; k += THREADS) {
+                        float v = cur[k];
+                        if (diff) {
+                            const float d = v - prv[k];
+                            v = (d + unwrap_correction(d)) * 0.5f;
+                        }
+                        v = v * s_pi;
+                        if (p.ph_weighted) v *= wgt;
+                        stg_stream1(o + k, (v - ph_off) * ph_inv);
+                    }
+                }
+                pidx = pidx == 2 ? 0 : pidx + 1;
+            }
 #ifdef ACIDS_FWD_SINGLE_ROWBUF     // tuning experiment: one |X| row buffer (8 KB less shared memory per CTA), two barriers per unit
             __syncthreads();
 #else
@@ -426,7 +554,10 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     }
 }
 
-static const size_t kBandSmemBudget = 24 * 1024;
+#ifndef ACIDS_FWD_BAND_BUDGET
+#define ACIDS_FWD_BAND_BUDGET (24 * 1024)
+#endif
+static const size_t kBandSmemBudget = ACIDS_FWD_BAND_BUDGET;
 
 template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
 static int launch_fwd(FwdParams p, cudaStream_t st) {
@@ -439,7 +570,8 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
 #else
     constexpr int kRowBufs = 2;
 #endif
-    if (MODE == MODE_REAL) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (C::ROWS_IN_EXCH ? 0 : (size_t)kRowBufs * G * C::VSTR * sizeof(float));
+    if (MODE != MODE_COMPLEX) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (C::ROWS_IN_EXCH ? 0 : (size_t)kRowBufs * G * C::VSTR * sizeof(float));
+    if (MODE == MODE_POLAR) smem += (size_t)(G == 1 ? 3 : 2 * G + 3) * C::VSTR * sizeof(float);
     auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
     static PerDevice cache[kMaxDevices];
     PerDevice& pd = per_device(cache);
@@ -475,6 +607,9 @@ static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
         case VAR_MEL_POWER_GLOBAL: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
         case VAR_MEL_ANY_SMEM: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
         case VAR_MEL_ANY_GLOBAL: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
+        case VAR_POLAR_NOBAND: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false>(p, st);
+        case VAR_POLAR_SMEM: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false>(p, st);
+        case VAR_POLAR_GLOBAL: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_GLOBAL, false>(p, st);
     }
     set_error("stft_fwd: unknown kernel variant %d", variant);
     return ACIDS_EINVAL;

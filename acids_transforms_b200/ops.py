@@ -247,6 +247,46 @@ def stft_mag_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, 
     return _ret(out, x)
 
 
+def stft_polar_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, eps, mag_offset, mag_scale, phase_mode,
+                   method, weighted, ph_offset, ph_scale, drop_first: bool = False, midside: int = 0):
+    """Fused [MidSide ->] STFT -> Polar / PolarIF: x [..., L] (midside: [..., 2, L]) -> float32 stacked [..., T, 2, F']
+    (raw.py:145-162, stft.py:101-102, spectral_repr.py:431-440); one kernel, the spectrum never reaches HBM.
+    Fused phase modes: raw phase and forward-difference IF (`fusable_phase`)."""
+    lib = _lib.load()
+    xd = _dev(x)
+    _check_stft_input(xd, n_fft)
+    if midside and (xd.ndim < 2 or xd.shape[-2] != 2):
+        raise RuntimeError("acids_b200: the fused MidSide prologue needs a stereo [..., 2, L] input")
+    xf, batch = _flat_batch(xd, 1)
+    B, L = xf.shape
+    T = n_frames_centered(L, hop)
+    F = n_fft // 2 + 1
+    if band is not None and band.n_in != F:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (B * T, F, band.n_in, band.n_out))
+    n_mag = (band.n_out if band is not None else F) - int(drop_first)
+    n_keep = F - int(drop_first)
+    if n_mag != n_keep:
+        raise RuntimeError("stack expects each tensor to be equal size, but got [%d] and [%d] bins" % (n_mag, n_keep))
+    dev = xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((B, T, 2, n_keep), dtype=torch.float32, device=dev)
+    mo, ms = _scalar(mag_offset, dev), _scalar(mag_scale, dev)
+    po, ps = _scalar(ph_offset, dev), _scalar(ph_scale, dev)
+    flat = out.view(-1)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_stft_polar_fwd, _ptr(xf), B, L, L, _ptr(w), n_fft, hop, T, int(midside), _band(band, dev),
+                                            _cid(contrast), float(eps), _ptr(mo), _ptr(ms), int(phase_mode), _mid(method),
+                                            int(bool(weighted)), _ptr(po), _ptr(ps), int(drop_first),
+                                            _ptr(flat), T * 2 * n_keep, 2 * n_keep, _ptr(flat[n_keep:]), T * 2 * n_keep, 2 * n_keep,
+                                            _stream(dev))
+    return _ret(out.reshape(tuple(batch) + (T, 2, n_keep)), x)
+
+
+def fusable_phase(phase_mode: int, method: int) -> bool:
+    """Phase modes acids_stft_polar_fwd evaluates without a scan over the frames."""
+    return phase_mode == PHASE_RAW or (phase_mode == PHASE_IF and method == IF_METHOD_IDS["forward"])
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) Magnitude on a spectrum
 # ------------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@ from .base import AudioTransform, frame_times
 from .spectral_repr import Magnitude, Polar, PolarIF, _contrast_id
 from .stft import STFT
 from .dgt import DGT
+from .raw import MidSide
 from .. import _torch_ops  # noqa: F401
 
 
@@ -55,21 +56,48 @@ class FusedSTFTMagnitude(AudioTransform):
 
 
 class FusedSTFTPolar(AudioTransform):
+    """[MidSide +] (STFT | DGT) + (Polar | PolarIF): one kernel, wave -> stacked [..., T, 2, F'] (raw.py:145-162,
+    stft.py:101-102, spectral_repr.py:431-440) when the phase half needs no scan over the frames (raw phase or the
+    forward-difference IF); any other configuration runs the children in turn."""
     scriptable = True
     invertible = True
     needs_scaling = True
 
-    def __init__(self, stft: STFT, polar):
+    def __init__(self, stft: STFT, polar, midside: Optional[MidSide] = None):
         super().__init__(sr=stft.sr)
         self.stft = stft
         self.polar = polar
+        self.has_midside = midside is not None
+        self.midside = midside if midside is not None else MidSide(sr=stft.sr)
 
     def __repr__(self):
-        return "Fused(%r -> %r)" % (self.stft, self.polar)
+        return "Fused(%s%r -> %r)" % ("%r -> " % self.midside if self.has_midside else "", self.stft, self.polar)
+
+    def _prologue(self, x: torch.Tensor) -> torch.Tensor:
+        if self.has_midside:
+            x = self.midside(x)
+        return x
 
     @torch.jit.export
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.polar(self.stft(x))
+        stack = self.polar.stack
+        mode = self.polar._phase_mode()
+        method = self.polar._phase_method()
+        fusable = (mode == 0 or (mode == 2 and method == 0)) and stack is not None and stack == -2 and not self.stft.track_phase
+        stereo = x.ndim >= 2 and x.size(-2) == 2
+        if self.has_midside and (self.midside.normalize or not stereo):
+            fusable = False
+        if not fusable:
+            return self.polar(self.stft(self._prologue(x)))
+        ms = 0
+        if self.has_midside:
+            ms = 2 if self.midside.pad_mid else 1
+        mag = self.polar.magnitude
+        return torch.ops.acids_b200.stft_polar_fwd(x, self.stft.window, self.stft._n_fft, self.stft._hop, mag.band_meta(),
+                                                   mag.band_coef(), _contrast_id(mag.contrast_mode), mag._eps,
+                                                   mag.norm.get_offset(), mag.norm.get_scale(), mode, method,
+                                                   self.polar._phase_weighted(), self.polar.phase.norm.get_offset(),
+                                                   self.polar.phase.norm.get_scale(), not self.polar.keep_nyquist, ms)
 
     @torch.jit.export
     def forward_with_time(self, x: torch.Tensor, time: torch.Tensor):
@@ -78,11 +106,18 @@ class FusedSTFTPolar(AudioTransform):
 
     @torch.jit.export
     def scale_data(self, x: torch.Tensor) -> None:
-        self.polar.scale_data(self.stft(x))
+        self.polar.scale_data(self.stft(self._prologue(x)))
 
     @torch.jit.export
     def invert(self, x: torch.Tensor, inversion_mode: Optional[str] = None) -> torch.Tensor:
-        return self.stft.invert(self.polar.invert(x, inversion_mode), inversion_mode)
+        y = self.stft.invert(self.polar.invert(x, inversion_mode), inversion_mode)
+        if self.has_midside:
+            y = self.midside.invert(y, inversion_mode)
+        return y
+
+
+def _bank_fits(mag: Magnitude, stft: STFT) -> bool:
+    return (not mag.mel) or mag.mel_bank.shape[-2] == stft._n_fft // 2 + 1
 
 
 def build_plan(transforms):
@@ -92,10 +127,16 @@ def build_plan(transforms):
     while i < len(items):
         t = items[i]
         nxt = items[i + 1] if i + 1 < len(items) else None
-        if type(t) in (STFT, DGT) and type(nxt) is Magnitude and (
-                not nxt.mel or nxt.mel_bank.shape[-2] == t._n_fft // 2 + 1):
+        nxt2 = items[i + 2] if i + 2 < len(items) else None
+        if type(t) in (STFT, DGT) and type(nxt) is Magnitude and _bank_fits(nxt, t):
             plan.append(FusedSTFTMagnitude(t, nxt))
             i += 2
+        elif type(t) in (STFT, DGT) and type(nxt) in (Polar, PolarIF) and _bank_fits(nxt.magnitude, t):
+            plan.append(FusedSTFTPolar(t, nxt))
+            i += 2
+        elif type(t) is MidSide and type(nxt) in (STFT, DGT) and type(nxt2) in (Polar, PolarIF) and _bank_fits(nxt2.magnitude, nxt):
+            plan.append(FusedSTFTPolar(nxt, nxt2, t))
+            i += 3
         else:
             plan.append(t)
             i += 1

@@ -106,6 +106,25 @@ ACIDS_API int acids_stft_mag_fwd(const float* x, int64_t B, int64_t L, int64_t l
                        int drop_first, float* out, int64_t out_clip_stride, int64_t out_row_stride,
                        void* stream);
 
+/* ---- (2a) fused [MidSide ->] STFT -> Polar / PolarIF ------------------------------------------
+ * Replaces the chain raw.py:145-162 (optional) -> stft.py:101-102 -> spectral_repr.py:431-440 (magnitude(x),
+ * phase(x), stack) in ONE kernel: the spectrum never reaches HBM.  The magnitude rows are those of (2); the
+ * phase rows (n_fft/2+1 - drop_first values at ph_out + b * ph_clip_stride + t * ph_row_stride) hold
+ *   phase_mode = ACIDS_PHASE_RAW: angle(X)                                   (spectral_repr.py:270-278)
+ *   phase_mode = ACIDS_PHASE_IF, if_method = ACIDS_IF_FORWARD: the forward-difference instantaneous frequency
+ *     (spectral_repr.py:319-323, :352-356) evaluated as the wrapped difference of two consecutive raw phases —
+ *     the difference of the unwrapped phases of utils/misc.py:12-26 without their running sum;
+ * any other phase mode returns ACIDS_ENOTSUP (use acids_stft_fwd + acids_polar_fwd).  Both outputs usually point
+ * into the two slots of one stacked [B, T, 2, F'] tensor.
+ * midside: 0 = x is [B, L]; 1 / 2 = x is stereo [B/2, 2, L] and clip 2p+c is channel c of MidSide.forward
+ * (1: pad_mid=False, 2: pad_mid=True, mid additionally / sqrt 2), evaluated in the sample loads.               */
+ACIDS_API int acids_stft_polar_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
+                       int n_fft, int hop, int64_t n_frames, int midside, acids_band band, int contrast,
+                       float eps, const float* mag_offset, const float* mag_scale, int phase_mode,
+                       int if_method, int weighted, const float* ph_offset, const float* ph_scale,
+                       int drop_first, float* mag_out, int64_t mag_clip_stride, int64_t mag_row_stride,
+                       float* ph_out, int64_t ph_clip_stride, int64_t ph_row_stride, void* stream);
+
 /* Same epilogue on an existing spectrum: Magnitude.forward, spectral_repr.py:215-226.
  *   X complex64 [rows, n_bins] -> out float32, row r at out + r * out_row_stride.              */
 ACIDS_API int acids_mag_epilogue(const float* X, int64_t rows, int n_bins, acids_band band, int contrast,

@@ -44,6 +44,10 @@ def main():
     res["fused_fwd_nomel_log1p"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
     ms = timeit(lambda: ops.stft_mag_fwd(x, w, n, h, None, None, eps, None, None, out=out))
     res["fused_fwd_mag_only"] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+    if "--fwd-only" in sys.argv:
+        for k, v in res.items():
+            print(k, json.dumps({a: round(b, 4) for a, b in v.items()}))
+        return
     X = ops.stft_fwd(x, hw, n, h)
     ms = timeit(lambda: ops.stft_fwd(x, hw, n, h))
     byt = B * (4 * L + 8 * T * F)
