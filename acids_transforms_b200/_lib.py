@@ -58,6 +58,7 @@ _PROTOTYPES = {
     "acids_one_hot": (c_int, [_P, c_int64, c_int, _P, _P]),
     "acids_stats_scratch_bytes": (c_int64, []),
     "acids_stats": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "acids_stft_stats": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int64, c_int, c_float, _P, _P, _P]),
     "acids_mono_mix": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "acids_midside": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P]),
 }

@@ -4,6 +4,7 @@ The nn.Module mirror of the reference calls these, which keeps every module Torc
 (`torch.jit.script` resolves `torch.ops.<ns>.<op>` from the registered schema).  The implementations
 are the ctypes calls of ops.py — CUDA kernels behind the C ABI; there is no other backend.
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -11,7 +12,17 @@ import torch
 from . import ops
 
 NS = "acids_b200"
-_lib = torch.library.Library(NS, "DEF")
+SHIM_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libacids_b200_torch.so")
+# Two registrations of the same schemas over the same C ABI:
+#   * libacids_b200_torch.so (csrc/torch_shim.cpp, TORCH_LIBRARY in C++) — the default whenever it is built: a chain saved
+#     with torch.jit.save loads in any process that dlopens it, Python or not;
+#   * the Python registration below — used when the shim is absent or ACIDS_B200_PY_OPS=1 (the ctypes twin, ops.py).
+USE_SHIM = os.path.exists(SHIM_PATH) and os.environ.get("ACIDS_B200_PY_OPS", "0") != "1" and os.environ.get("ACIDS_B200_LIB") is None
+if USE_SHIM:
+    torch.ops.load_library(SHIM_PATH)
+    _lib = None
+else:
+    _lib = torch.library.Library(NS, "DEF")
 
 _SCHEMAS = {
     "stft_fwd": "(Tensor x, Tensor window, int n_fft, int hop, bool center) -> Tensor",
@@ -42,6 +53,7 @@ _SCHEMAS = {
     "mulaw_decode": "(Tensor q, int channels) -> Tensor",
     "one_hot": "(Tensor q, int n_classes) -> Tensor",
     "stats": "(Tensor x, int contrast, float eps, bool abs_contrast=False) -> Tensor",
+    "stft_stats": "(Tensor x, Tensor window, int n_fft, int hop, int contrast, float eps) -> Tensor",
     "mono_mix": "(Tensor x) -> Tensor",
     "midside": "(Tensor x, bool pad_mid, bool inverse) -> Tensor",
 }
@@ -155,6 +167,10 @@ def _stats(x, contrast: int, eps: float, abs_contrast: bool = False):
     return ops._ret(ops.stats(x, contrast, eps, abs_contrast), x)
 
 
+def _stft_stats(x, window, n_fft: int, hop: int, contrast: int, eps: float):
+    return ops._ret(ops.stft_stats(x, window, n_fft, hop, contrast, eps), x)
+
+
 def _mono_mix(x):
     return ops.mono_mix(x)
 
@@ -163,6 +179,7 @@ def _midside(x, pad_mid: bool, inverse: bool):
     return ops.midside(x, pad_mid, inverse)
 
 
-for _name, _schema in _SCHEMAS.items():
-    _lib.define(_name + _schema)
-    _lib.impl(_name, globals()["_" + _name], "CompositeExplicitAutograd")
+if _lib is not None:
+    for _name, _schema in _SCHEMAS.items():
+        _lib.define(_name + _schema)
+        _lib.impl(_name, globals()["_" + _name], "CompositeExplicitAutograd")

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.environ.get("ACIDS_B200_OBJ") or os.path.join(PKG, "build")
 LIB = os.environ.get("ACIDS_B200_LIB") or os.path.join(PKG, "libacids_b200.so")
+SHIM = os.path.join(PKG, "libacids_b200_torch.so")       # TORCH_LIBRARY(acids_b200): csrc/torch_shim.cpp on top of the C ABI
 SOURCES = ["capi.cu", "stft_fwd.cu", "istft.cu", "spectral_repr.cu", "pointwise.cu", "mfcc_tc.cu"]
 # the fused forward kernels: one translation unit per FFT plan (stft_fwd_plan.cu -DACIDS_FWD_PLAN_N=n), built in parallel
 FWD_PLANS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
@@ -71,7 +72,30 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if os.environ.get("ACIDS_B200_LIB") is None:       # tuning variants (ACIDS_B200_LIB=...) reuse the product shim
+        build_shim(force)
     return LIB
+
+
+def build_shim(force=False):
+    """libacids_b200_torch.so: the dispatcher registration of torch.ops.acids_b200.* in C++ (csrc/torch_shim.cpp), linked
+    against libtorch and libacids_b200.so — what a libtorch-only host dlopens before torch::jit::load of a saved chain."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    src = os.path.join(CSRC, "torch_shim.cpp")
+    hdr = os.path.join(ROOT, "include", "acids_b200.h")
+    if not (force or _stale(SHIM, [src, hdr, os.path.abspath(__file__)])):
+        return SHIM
+    tl = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-I" + p for p in ce.include_paths()] + ["-I" + os.path.join(cuda_home, "include")]
+    cmd += [src, "-o", SHIM, "-L" + tl, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-L" + PKG, "-l:libacids_b200.so",
+            "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tl]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("torch shim build failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:]))
+    return SHIM
 
 
 if __name__ == "__main__":

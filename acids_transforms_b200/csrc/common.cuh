@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <float.h>
 #include "../../include/acids_b200.h"
 #include "fft_core.cuh"
 
@@ -124,6 +125,51 @@ __device__ __forceinline__ float if_weight(int t, int T) {
     const float N = (float)T, n = (float)t;
     const float a = (n - (N / 2.f - 1.f)) / (N / 2.f);
     return (1.5f * N) / (N * N - 1.f) * (1.f - a * a);
+}
+
+// ---- one-pass statistics (min, max, sum, sum of squares in double) shared by acids_stats and the STFT statistics mode ----
+struct StatAcc {
+    double mn, mx, s, s2;
+};
+constexpr int kStatsBlocks = 1024;       // partials the scratch buffer of acids_stats_scratch_bytes() holds
+int launch_stats_final(const StatAcc* part, int nparts, int64_t n, double* out4, cudaStream_t st);     // pointwise.cu
+
+__device__ __forceinline__ void stat_merge(StatAcc& a, const StatAcc& b) {
+    a.mn = fmin(a.mn, b.mn);
+    a.mx = fmax(a.mx, b.mx);
+    a.s += b.s;
+    a.s2 += b.s2;
+}
+
+// all threads of the CTA call it; the result is valid on thread 0
+__device__ __forceinline__ StatAcc stat_block_reduce(StatAcc a) {
+    __shared__ StatAcc sh[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        StatAcc b;
+        b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
+        b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+        b.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+        b.s2 = __shfl_xor_sync(0xffffffffu, a.s2, o);
+        stat_merge(a, b);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) sh[warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        StatAcc b = lane < nw ? sh[lane] : StatAcc{DBL_MAX, -DBL_MAX, 0.0, 0.0};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            StatAcc c;
+            c.mn = __shfl_xor_sync(0xffffffffu, b.mn, o);
+            c.mx = __shfl_xor_sync(0xffffffffu, b.mx, o);
+            c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
+            c.s2 = __shfl_xor_sync(0xffffffffu, b.s2, o);
+            stat_merge(b, c);
+        }
+        a = b;
+    }
+    return a;
 }
 
 // ---- epilogue shared by the fused STFT kernel and the stand-alone Magnitude kernels -------------

@@ -101,49 +101,6 @@ __global__ void one_hot_kernel(const int64_t* __restrict__ q, int64_t n, int C, 
 // ---------------------------------------------------------------------------------------------
 // statistics: min, max, mean, unbiased std in one pass (double accumulators), two tiny stages
 // ---------------------------------------------------------------------------------------------
-static const int kStatsBlocks = 1024;
-
-struct StatAcc {
-    double mn, mx, s, s2;
-};
-
-__device__ __forceinline__ void stat_merge(StatAcc& a, const StatAcc& b) {
-    a.mn = fmin(a.mn, b.mn);
-    a.mx = fmax(a.mx, b.mx);
-    a.s += b.s;
-    a.s2 += b.s2;
-}
-
-__device__ __forceinline__ StatAcc block_reduce(StatAcc a) {
-    __shared__ StatAcc sh[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        StatAcc b;
-        b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
-        b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
-        b.s = __shfl_xor_sync(0xffffffffu, a.s, o);
-        b.s2 = __shfl_xor_sync(0xffffffffu, a.s2, o);
-        stat_merge(a, b);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    if (lane == 0) sh[warp] = a;
-    __syncthreads();
-    if (warp == 0) {
-        StatAcc b = lane < nw ? sh[lane] : StatAcc{DBL_MAX, -DBL_MAX, 0.0, 0.0};
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            StatAcc c;
-            c.mn = __shfl_xor_sync(0xffffffffu, b.mn, o);
-            c.mx = __shfl_xor_sync(0xffffffffu, b.mx, o);
-            c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
-            c.s2 = __shfl_xor_sync(0xffffffffu, b.s2, o);
-            stat_merge(b, c);
-        }
-        a = b;
-    }
-    return a;
-}
-
 __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restrict__ x, int64_t n, int kind, int contrast,
                                                             float eps, StatAcc* __restrict__ part) {
     StatAcc a{DBL_MAX, -DBL_MAX, 0.0, 0.0};
@@ -163,7 +120,7 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const float* __restr
         a.s += d;
         a.s2 += d * d;
     }
-    a = block_reduce(a);
+    a = stat_block_reduce(a);
     if (threadIdx.x == 0) part[blockIdx.x] = a;
 }
 
@@ -171,7 +128,7 @@ __global__ void __launch_bounds__(256) stats_final_kernel(const StatAcc* __restr
                                                           double* __restrict__ out4) {
     StatAcc a{DBL_MAX, -DBL_MAX, 0.0, 0.0};
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) stat_merge(a, part[i]);
-    a = block_reduce(a);
+    a = stat_block_reduce(a);
     if (threadIdx.x == 0) {
         const double mean = a.s / (double)n;
         double var = (a.s2 - a.s * a.s / (double)n) / (double)(n - 1);   // unbiased, like torch.std
@@ -436,6 +393,14 @@ extern "C" ACIDS_API int acids_one_hot(const int64_t* q, int64_t n, int n_classe
     ACIDS_CHECK_LAUNCH("one_hot");
     return ACIDS_OK;
 }
+
+namespace acids {
+int launch_stats_final(const StatAcc* part, int nparts, int64_t n, double* out4, cudaStream_t st) {
+    stats_final_kernel<<<1, 256, 0, st>>>(part, nparts, n, out4);
+    ACIDS_CHECK_LAUNCH("stats");
+    return ACIDS_OK;
+}
+}  // namespace acids
 
 extern "C" ACIDS_API int64_t acids_stats_scratch_bytes(void) { return (int64_t)kStatsBlocks * (int64_t)sizeof(StatAcc); }
 

@@ -164,3 +164,20 @@ extern "C" ACIDS_API int acids_stft_polar_fwd(const float* x, int64_t B, int64_t
     p.ph_mode = phase_mode; p.ph_weighted = weighted;
     return dispatch_fwd(real_variant(p, false, true), n_fft, p, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" ACIDS_API int acids_stft_stats(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window, int n_fft,
+                                int hop, int64_t n_frames, int contrast, float eps, void* scratch, double* out4, void* stream) {
+    FwdParams p{};
+    int rc = fill_common(p, x, B, L, ldx, window, n_fft, hop, 1, n_frames);
+    if (rc) return rc;
+    ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
+    ACIDS_REQUIRE(scratch && out4, ACIDS_EINVAL, "stft_stats: NULL pointer");
+    ACIDS_REQUIRE(B * n_frames >= 1, ACIDS_EINVAL, "stft_stats: empty input");
+    p.ep.contrast = contrast; p.ep.eps = eps;
+    p.stat_part = static_cast<StatAcc*>(scratch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int parts = dispatch_fwd(VAR_STATS, n_fft, p, st);
+    if (parts < 0) return parts;
+    ACIDS_REQUIRE(parts >= 1 && parts <= kStatsBlocks, ACIDS_ECUDA, "stft_stats: %d partials do not fit the scratch buffer", parts);
+    return launch_stats_final(p.stat_part, parts, B * n_frames * (int64_t)(n_fft / 2 + 1), out4, st);
+}

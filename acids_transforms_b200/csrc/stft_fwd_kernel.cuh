@@ -9,9 +9,11 @@ namespace acids {
 
 // MODE_POLAR = MODE_REAL plus a second output: the raw phase or the forward-difference instantaneous frequency of every
 // bin (Polar / PolarIF right after the STFT, spectral_repr.py:431-440) — the spectrum never reaches HBM
-enum { MODE_COMPLEX = 0, MODE_REAL = 1, MODE_POLAR = 2 };
+// MODE_STATS: nothing is stored; min / max / sum / sum of squares of contrast(|X|) over every bin go to one StatAcc per CTA
+// (Magnitude.scale_data on the spectrum, spectral_repr.py:242-245 + norm.py:26-38, without materialising it)
+enum { MODE_COMPLEX = 0, MODE_REAL = 1, MODE_POLAR = 2, MODE_STATS = 3 };
 enum { VAR_COMPLEX = 0, VAR_MAG_NOBAND, VAR_MAG_SMEM, VAR_MAG_GLOBAL, VAR_MEL_POWER_SMEM, VAR_MEL_POWER_GLOBAL, VAR_MEL_ANY_SMEM,
-       VAR_MEL_ANY_GLOBAL, VAR_POLAR_NOBAND, VAR_POLAR_SMEM, VAR_POLAR_GLOBAL };
+       VAR_MEL_ANY_GLOBAL, VAR_POLAR_NOBAND, VAR_POLAR_SMEM, VAR_POLAR_GLOBAL, VAR_STATS };
 
 struct FwdParams {
     const float* x;
@@ -36,6 +38,7 @@ struct FwdParams {
     const float* ph_offset_ptr;
     const float* ph_scale_ptr;
     int ph_mode, ph_weighted;
+    StatAcc* stat_part;      // MODE_STATS: one partial per CTA (gridDim.x of them)
 };
 
 // launch shape per plan: small frame groups run 128-thread CTAs at 4 CTAs / SM (<= 128 registers)
@@ -61,9 +64,10 @@ struct FwdCfg {
     // for both, and the epilogue amortises a column's metadata / coefficients / dispatch over twice the rows.  Costs
     // registers: 168 per thread, 3 CTAs / SM (n_fft = 1024: 1.17 -> see DESIGN.md section 5).
     static constexpr int FPW = P::N == 1024 ? ACIDS_FWD_FPW_1024 : 1;
-    static constexpr int THREADS = (P::N == 1024 && MODE != 0 /* MODE_REAL, MODE_POLAR */) ? ACIDS_FWD_THREADS_1024
+    static constexpr int THREADS = (P::N == 1024 && MODE == 1 /* MODE_REAL */) ? ACIDS_FWD_THREADS_1024
                                                 : (P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256)));
-    static constexpr int MINB = FPW > 1 ? 3 : (P::T <= 32 ? ACIDS_FWD_MINB_SMALL * 128 / THREADS : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1)));
+    // MODE_POLAR (2), small plans: 168 registers (3 CTAs / SM) — the arctangents next to the |X| rows spill 100+ bytes at 128
+    static constexpr int MINB = (FPW > 1 || (MODE == 2 && P::T <= 32)) ? 3 : (P::T <= 32 ? ACIDS_FWD_MINB_SMALL * 128 / THREADS : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1)));
     // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
     // second register set; that needs ~160 registers -> one CTA less per SM for the small plans
     static constexpr int MINB_COMPLEX = P::T <= 32 ? 3 : MINB;
@@ -93,14 +97,16 @@ __device__ __forceinline__ float pow_value(cf a, float power) {
 }
 
 // CSEL: contrast known at compile time (ACIDS_CONTRAST_*) or -1 (dispatched once per row tile)
-template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
+// MS: the MidSide prologue is folded into the sample loads (a compile-time switch: as a run-time one it cost every variant
+// registers — 16..120 bytes of spills at 128 registers, the headline kernel 1.11 -> 1.44 ms)
+template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED, bool MS = false>
 __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX ? FwdCfg<P, MODE>::MINB_COMPLEX : FwdCfg<P, MODE>::MINB)
     stft_fwd_kernel(const FwdParams p) {
     using C = FwdCfg<P, MODE>;
     constexpr int THREADS = C::THREADS;
     constexpr int N = P::N, M = P::M, T = P::T, V = P::V, G = C::G, NF = C::NF, VSTR = C::VSTR, VW = C::VW, FPW = C::FPW;
     constexpr int R0 = P::radix(0), B0 = P::bpt(0), NB0 = P::nb(0);
-    constexpr bool REALISH = MODE != MODE_COMPLEX, POLAR = MODE == MODE_POLAR;
+    constexpr bool REALISH = MODE == MODE_REAL || MODE == MODE_POLAR, POLAR = MODE == MODE_POLAR, STATS = MODE == MODE_STATS;
     constexpr bool RIE = REALISH && C::ROWS_IN_EXCH;
     static_assert(!POLAR || !RIE, "the polar epilogue keeps its rows in their own buffers");
     using FFT = FrameFFT<P, false>;
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
                         for (int b0 = 0; b0 < B0; b0 += 2) {
                             float4 a = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
-                            if (p.midside) {
+                            if (MS) {
                                 const float4 o = __ldg(reinterpret_cast<const float4*>(src + p.ldx) + (b0 >> 1));
                                 a = make_float4(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain,
                                                 fmaf(ms_sign, o.z, a.z) * ms_gain, fmaf(ms_sign, o.w, a.w) * ms_gain);
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
                         for (int b0 = 0; b0 < B0; ++b0) {
                             float2 a = __ldg(reinterpret_cast<const float2*>(src) + b0);
-                            if (p.midside) {
+                            if (MS) {
                                 const float2 o = __ldg(reinterpret_cast<const float2*>(src + p.ldx) + b0);
                                 a = make_float2(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain);
                             }
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             if (k >= L) k = 2 * (L - 1) - k;
             k = k < 0 ? 0 : (k >= L ? L - 1 : k);
             float smp = valid ? __ldg(xb + k) : 0.f;
-            if (p.midside && valid) smp = fmaf(ms_sign, __ldg(xb + p.ldx + k), smp) * ms_gain;
+            if (MS && valid) smp = fmaf(ms_sign, __ldg(xb + p.ldx + k), smp) * ms_gain;
             sf[i] = smp;
         }
         gsync();
@@ -246,11 +252,11 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     int64_t b = ustart / upc;
     int uc = (int)(ustart - b * upc);
     // clip of the NEXT unit (the one being fetched); with MidSide: the LEFT row of the clip's stereo pair
-    const float* __restrict__ xclip = p.midside ? p.x + (b >> 1) * 2 * p.ldx : p.x + b * p.ldx;
+    const float* __restrict__ xclip = MS ? p.x + (b >> 1) * 2 * p.ldx : p.x + b * p.ldx;
     int ms_ch = (int)(b & 1);
     const float ms_mid_gain = p.midside == 2 ? 0.35355339059327376220f : 0.5f;      // 1/2 or 1/(2 sqrt 2) (raw.py:151-155)
     auto ms_update = [&]() {
-        if (p.midside) {
+        if (MS) {
             ms_s = ms_ch ? -1.f : 1.f;
             ms_g = ms_ch ? 0.5f : ms_mid_gain;
         }
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
     for (int f = 0; f < FPW; ++f) pend[f] = false;
     float* __restrict__ phclip = POLAR ? p.ph_out + b * p.ph_clip_stride : nullptr;
+    StatAcc acc{DBL_MAX, -DBL_MAX, 0.0, 0.0};
     if (u0 < u1) {
 #pragma unroll
         for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         float* __restrict__ const cur_ph = phclip;
         if (++uc == upc) {
             uc = 0;
-            if (p.midside) {
+            if (MS) {
                 ms_ch ^= 1;
                 if (!ms_ch) xclip += 2 * p.ldx;
                 ms_update();
@@ -401,7 +408,41 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         }
         if (RIE) gsync();    // every lane has read the last pass's operands: the buffers may take the |X| rows
 
-        if (!REALISH) {
+        if (STATS) {
+#pragma unroll
+            for (int f = 0; f < FPW; ++f) {
+                cf o1[V / 2], o2[V / 2], ex;
+                fft.untangle_fwd(v[f], o1, o2, ex);
+                // this thread's V bins of the frame (+ bin M/2 on thread 0): float partials per frame, double across frames
+                float fmn = 3.4e38f, fmx = -3.4e38f, fs = 0.f, fs2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < V / 2; ++i) {
+                    const float a1 = apply_contrast(fast_sqrt(fmaf(o1[i].x, o1[i].x, o1[i].y * o1[i].y)), p.ep.contrast, p.ep.eps);
+                    const float a2 = apply_contrast(fast_sqrt(fmaf(o2[i].x, o2[i].x, o2[i].y * o2[i].y)), p.ep.contrast, p.ep.eps);
+                    fmn = fminf(fmn, fminf(a1, a2));
+                    fmx = fmaxf(fmx, fmaxf(a1, a2));
+                    fs += a1 + a2;
+                    fs2 = fmaf(a1, a1, fmaf(a2, a2, fs2));
+                }
+                if (tid == 0) {
+                    const float ae = apply_contrast(fast_sqrt(fmaf(ex.x, ex.x, ex.y * ex.y)), p.ep.contrast, p.ep.eps);
+                    fmn = fminf(fmn, ae);
+                    fmx = fmaxf(fmx, ae);
+                    fs += ae;
+                    fs2 = fmaf(ae, ae, fs2);
+                }
+                if (tb + f < n_frames) {
+                    acc.mn = fmin(acc.mn, (double)fmn);
+                    acc.mx = fmax(acc.mx, (double)fmx);
+                    acc.s += (double)fs;
+                    acc.s2 += (double)fs2;
+                }
+            }
+            if (u + 1 < u1) {
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
+            }
+        } else if (!REALISH) {
 #pragma unroll
             for (int f = 0; f < FPW; ++f) {
                 // ---- untangle in registers ----
@@ -552,6 +593,11 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #endif
         }
     }
+    if (STATS) {
+        __syncthreads();
+        acc = stat_block_reduce(acc);
+        if (threadIdx.x == 0) p.stat_part[blockIdx.x] = acc;
+    }
 }
 
 #ifndef ACIDS_FWD_BAND_BUDGET
@@ -559,7 +605,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #endif
 static const size_t kBandSmemBudget = ACIDS_FWD_BAND_BUDGET;
 
-template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED>
+template <class P, int MODE, int PMODE, int CSEL, int BAND, bool TRANSPOSED, bool MS = false>
 static int launch_fwd(FwdParams p, cudaStream_t st) {
     using C = FwdCfg<P, MODE>;
     constexpr int THREADS = C::THREADS;
@@ -570,9 +616,9 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
 #else
     constexpr int kRowBufs = 2;
 #endif
-    if (MODE != MODE_COMPLEX) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (C::ROWS_IN_EXCH ? 0 : (size_t)kRowBufs * G * C::VSTR * sizeof(float));
+    if (MODE == MODE_REAL || MODE == MODE_POLAR) smem += (BAND == BAND_SMEM ? (size_t)p.band_smem_bytes : 0) + (C::ROWS_IN_EXCH ? 0 : (size_t)kRowBufs * G * C::VSTR * sizeof(float));
     if (MODE == MODE_POLAR) smem += (size_t)(G == 1 ? 3 : 2 * G + 3) * C::VSTR * sizeof(float);
-    auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED>;
+    auto kern = stft_fwd_kernel<P, MODE, PMODE, CSEL, BAND, TRANSPOSED, MS>;
     static PerDevice cache[kMaxDevices];
     PerDevice& pd = per_device(cache);
     size_t& reserved = pd.reserved;
@@ -593,6 +639,7 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, THREADS, smem, st>>>(p);
     ACIDS_CHECK_LAUNCH("stft_fwd");
+    if (MODE == MODE_STATS) return (int)grid;      // number of partials written (>= 1)
     return ACIDS_OK;
 }
 
@@ -607,9 +654,10 @@ static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
         case VAR_MEL_POWER_GLOBAL: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
         case VAR_MEL_ANY_SMEM: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
         case VAR_MEL_ANY_GLOBAL: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
-        case VAR_POLAR_NOBAND: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false>(p, st);
-        case VAR_POLAR_SMEM: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false>(p, st);
-        case VAR_POLAR_GLOBAL: return launch_fwd<P, MODE_POLAR, 1, -1, BAND_GLOBAL, false>(p, st);
+        case VAR_STATS: return launch_fwd<P, MODE_STATS, 1, -1, BAND_NONE, false>(p, st);
+        case VAR_POLAR_NOBAND: return p.midside ? launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false, true>(p, st) : launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false>(p, st);
+        case VAR_POLAR_SMEM: return p.midside ? launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false, true>(p, st) : launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false>(p, st);
+        case VAR_POLAR_GLOBAL: return p.midside ? launch_fwd<P, MODE_POLAR, 1, -1, BAND_GLOBAL, false, true>(p, st) : launch_fwd<P, MODE_POLAR, 1, -1, BAND_GLOBAL, false>(p, st);
     }
     set_error("stft_fwd: unknown kernel variant %d", variant);
     return ACIDS_EINVAL;

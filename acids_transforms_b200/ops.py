@@ -705,6 +705,28 @@ def stats(x, contrast=None, eps=0.0, abs_contrast: bool = False) -> torch.Tensor
     return out
 
 
+def stft_stats(x, window, n_fft, hop, contrast=None, eps=0.0) -> torch.Tensor:
+    """(min, max, mean, unbiased std) of contrast(|STFT(x)|) over every bin as a float64[4] DEVICE tensor — what
+    Magnitude.scale_data(STFT(x)) fits (spectral_repr.py:242-245), from ONE pass of the fused forward kernel: the spectrum
+    is never written."""
+    lib = _lib.load()
+    xd = _dev(x)
+    _check_stft_input(xd, n_fft)
+    xf, _ = _flat_batch(xd, 1)
+    B, L = xf.shape
+    if B == 0:
+        raise RuntimeError("min(): Expected reduction dim to be specified for input.numel() == 0.")
+    T = n_frames_centered(L, hop)
+    dev = xf.device
+    w = _dev(window).to(torch.float32).contiguous()
+    scratch = torch.empty((int(lib.acids_stats_scratch_bytes()),), dtype=torch.uint8, device=dev)
+    out = torch.empty((4,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_stft_stats, _ptr(xf), B, L, L, _ptr(w), n_fft, hop, T, _cid(contrast), float(eps), _ptr(scratch),
+                                        _ptr(out), _stream(dev))
+    return out
+
+
 def mono_mix(x):
     """Mono(mode="mix"): [..., 2, L] -> [..., L] = (l + r) / 2  (raw.py:37-39)."""
     lib = _lib.load()

@@ -6,6 +6,7 @@
 A fused stage holds the very same child modules as the chain (so buffers, `scale_data` results and
 `state_dict` entries are shared); results are identical to running the children one after the other.
 """
+import os
 from typing import Optional
 
 import torch
@@ -48,7 +49,15 @@ class FusedSTFTMagnitude(AudioTransform):
 
     @torch.jit.export
     def scale_data(self, x: torch.Tensor) -> None:
-        self.mag.scale_data(self.stft(x))
+        """Magnitude.scale_data(STFT(x)) (base.py:144-148, spectral_repr.py:242-245) as ONE pass of the forward kernel in
+        its statistics mode: min / max / sum / sum of squares of contrast(|X|) per CTA, one tiny merge, no spectrum in HBM
+        and no host synchronisation."""
+        if self.stft.track_phase:                      # the reference leaves phase_buffer behind: materialise
+            self.mag.scale_data(self.stft(x))
+            return
+        st = torch.ops.acids_b200.stft_stats(x, self.stft.window, self.stft._n_fft, self.stft._hop,
+                                             _contrast_id(self.mag.contrast_mode), self.mag._eps)
+        self.mag.norm.set_stats(st)
 
     @torch.jit.export
     def invert(self, x: torch.Tensor, inversion_mode: Optional[str] = None) -> torch.Tensor:
@@ -63,12 +72,20 @@ class FusedSTFTPolar(AudioTransform):
     invertible = True
     needs_scaling = True
 
-    def __init__(self, stft: STFT, polar, midside: Optional[MidSide] = None):
+    def __init__(self, stft: STFT, polar, midside: Optional[MidSide] = None, one_kernel: Optional[bool] = None):
         super().__init__(sr=stft.sr)
         self.stft = stft
         self.polar = polar
         self.has_midside = midside is not None
         self.midside = midside if midside is not None else MidSide(sr=stft.sr)
+        # Measured on B200 (tools/polar_debug.py): the one-kernel path is issue bound on the arctangents
+        # (25 instructions per bin on the FFT's own warps) — 1.37 ms against 1.32 ms for the three-kernel chain at n_fft 1024
+        # (512 clips) and 2.8 ms against 1.5 ms at n_fft 4096, where a CTA holds one frame and the banded projection cannot
+        # amortise a column's coefficients over several rows.  It therefore runs only on request (`one_kernel=True`, or
+        # ACIDS_B200_FUSE_POLAR=1 at construction); the default is the chain, whose results it reproduces.
+        if one_kernel is None:
+            one_kernel = os.environ.get("ACIDS_B200_FUSE_POLAR", "0") == "1"
+        self.one_kernel = bool(one_kernel)
 
     def __repr__(self):
         return "Fused(%s%r -> %r)" % ("%r -> " % self.midside if self.has_midside else "", self.stft, self.polar)
@@ -83,7 +100,7 @@ class FusedSTFTPolar(AudioTransform):
         stack = self.polar.stack
         mode = self.polar._phase_mode()
         method = self.polar._phase_method()
-        fusable = (mode == 0 or (mode == 2 and method == 0)) and stack is not None and stack == -2 and not self.stft.track_phase
+        fusable = self.one_kernel and (mode == 0 or (mode == 2 and method == 0)) and stack is not None and stack == -2 and not self.stft.track_phase
         stereo = x.ndim >= 2 and x.size(-2) == 2
         if self.has_midside and (self.midside.normalize or not stereo):
             fusable = False

@@ -248,6 +248,13 @@ ACIDS_API int64_t acids_stats_scratch_bytes(void);
 ACIDS_API int acids_stats(const float* x, int64_t n, int kind, int contrast, float eps, void* scratch,
                 double* out4, void* stream);
 
+/* The same statistics for the spectrum of a waveform WITHOUT materialising it: Magnitude.scale_data(STFT(x))
+ * (base.py:144-148 -> stft.py:101-102 -> spectral_repr.py:242-245 -> norm.py:26-38) in one pass of the fused
+ * forward kernel — min / max / sum / sum of squares of contrast(|X|) over every bin are kept per CTA and merged by a
+ * one-block kernel.  x [B, L] (row stride ldx), centre-padded framing like acids_stft_fwd; scratch / out4 as above.   */
+ACIDS_API int acids_stft_stats(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window, int n_fft,
+                     int hop, int64_t n_frames, int contrast, float eps, void* scratch, double* out4, void* stream);
+
 /* ---- raw-domain prologues: raw.py:34-49 (Mono mix), raw.py:145-180 (MidSide) -------------------
  * x [B, 2, L] -> mono [B, L] = (l + r) / 2;  mid/side [B, 2, L] (pad_mid: mid / sqrt(2)).        */
 ACIDS_API int acids_mono_mix(const float* x, int64_t B, int64_t L, float* out, void* stream);

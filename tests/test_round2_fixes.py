@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_parity, branch_cut, load_golden
+from conftest import ROOT, assert_parity, branch_cut, load_golden
 
 
 # ---------------------------------------------------------------------------------------------
@@ -166,3 +166,116 @@ def test_phase_buffer_matches_reference():
     assert any("keep_input" in str(i.message) for i in w) and mod.track_phase
     X = mod(cu(g["x"]))
     assert_parity(mod.invert(X.abs(), inversion_mode="keep_input").cpu().numpy(), g["y"], 1e-4, "keep_input after warning")
+
+
+# ---------------------------------------------------------------------------------------------
+# the libtorch-loadable op registration (csrc/torch_shim.cpp -> libacids_b200_torch.so; VERDICT r1 missing #4)
+# ---------------------------------------------------------------------------------------------
+_LOAD_WITHOUT_PACKAGE = r"""
+import sys, json
+import torch
+assert not any(m.startswith("acids_transforms_b200") for m in sys.modules)
+torch.ops.load_library(sys.argv[1])                 # what a C++ host does with dlopen before torch::jit::load
+m = torch.jit.load(sys.argv[2])
+assert not any(m_.startswith("acids_transforms_b200") for m_ in sys.modules), "the saved chain must not need the Python package"
+out = {"buffers": sorted(n for n, _ in m.named_buffers())[:3]}
+if torch.cuda.is_available() and len(sys.argv) > 3:
+    import numpy as np
+    g = np.load(sys.argv[3])
+    x = torch.from_numpy(g["x"]).cuda()
+    y = m(x)
+    t = m.forward_with_time(x, torch.zeros(x.shape[0], device="cuda"))[1]
+    xi = m.invert(y)
+    out.update(err=float((y.cpu() - torch.from_numpy(g["y"])).abs().max() / np.abs(g["y"]).max()), t1=float(t[0, 1]), inv=list(xi.shape))
+print(json.dumps(out))
+"""
+
+
+def _shim_path():
+    import os
+    from acids_transforms_b200 import _torch_ops
+    assert os.path.exists(_torch_ops.SHIM_PATH), "libacids_b200_torch.so is not built (python -m acids_transforms_b200.build)"
+    return _torch_ops.SHIM_PATH
+
+
+def test_shim_registers_every_schema_of_the_python_twin():
+    """Both registrations (C++ shim, Python fallback) must define exactly the same operator set and schemas."""
+    import subprocess, sys, json, os
+    from acids_transforms_b200 import _torch_ops
+    code = ("import sys, json, torch; sys.path.insert(0, %r); from acids_transforms_b200 import _torch_ops as t; "
+            "print(json.dumps({n: str(getattr(torch.ops.acids_b200, n).default._schema) for n in t._SCHEMAS}), t.USE_SHIM)" % ROOT)
+    outs = {}
+    for flag in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ACIDS_B200_PY_OPS=flag), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = r.stdout.strip().splitlines()[-1]
+        outs[flag] = (json.loads(line[:line.rindex("}") + 1]), line.split()[-1])
+    _shim_path()
+    assert outs["0"][1] == "True" and outs["1"][1] == "False"
+    assert outs["0"][0] == outs["1"][0]
+    assert len(outs["0"][0]) == len(_torch_ops._SCHEMAS) >= 23
+
+
+def test_saved_chain_loads_without_the_python_package(tmp_path):
+    """torch.jit.script(chain).save() -> a process that only dlopens the shim -> torch.jit.load (README.md:43-67)."""
+    import subprocess, sys, json
+    from acids_transforms_b200 import transforms as T
+    ch = T.DGT(sr=44100, n_fft=1024, hop_length=256, inversion_mode="random") + T.Magnitude(mel=True, mode="unipolar", contrast="log1p")
+    path = str(tmp_path / "chain.pt")
+    torch.jit.script(ch).save(path)
+    script = tmp_path / "load.py"
+    script.write_text(_LOAD_WITHOUT_PACKAGE)
+    r = subprocess.run([sys.executable, str(script), _shim_path(), path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])["buffers"]
+
+
+@pytest.mark.gpu
+def test_saved_chain_runs_in_a_packageless_process(tmp_path):
+    """jit.save -> jit.load in a process without acids_transforms_b200 -> forward / forward_with_time / invert on the GPU
+    through the C++ registration; the output matches the golden cfg-2 chain of the unmodified reference."""
+    import os, subprocess, sys, json
+    from acids_transforms_b200 import transforms as T
+    g = load_golden("chain_cfg2")
+    ch = (T.DGT(sr=44100, n_fft=1024, hop_length=256, inversion_mode="random") + T.Magnitude(mel=True, mode="unipolar", contrast="log1p")).cuda()
+    ch.scale_data(torch.from_numpy(g["x"]).cuda())
+    path = str(tmp_path / "chain.pt")
+    torch.jit.script(ch).save(path)
+    script = tmp_path / "load.py"
+    script.write_text(_LOAD_WITHOUT_PACKAGE)
+    r = subprocess.run([sys.executable, str(script), _shim_path(), path, os.path.join(ROOT, "tests", "golden", "chain_cfg2.npz")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["err"] <= 1e-4 and abs(out["t1"] - 256 / 44100) < 1e-7 and out["inv"] == [3, 8192]
+
+
+@pytest.mark.gpu
+def test_both_registrations_agree_bit_for_bit(tmp_path):
+    """The Python (ctypes) and the C++ registration drive the same kernels: identical outputs for the cfg-2 and cfg-4 chains."""
+    import os, subprocess, sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from acids_transforms_b200 import transforms as T, _torch_ops
+torch.manual_seed(0)
+x = torch.randn(6, 2, 20000, device="cuda")
+a = (T.Mono() + T.DGT(n_fft=1024, hop_length=256, inversion_mode="random") + T.Magnitude()).cuda()
+a.scale_data(x)
+b = (T.MidSide() + T.STFT(n_fft=4096, hop_length=1024) + T.PolarIF(magnitude_args={"mode": "bipolar", "n_fft": 4096})).cuda()
+b.scale_data(x)
+m = T.MFCC(n_fft=2048, hop_length=512, n_mels=128, n_mfcc=40).cuda()
+q = T.MuLaw().cuda()
+ya, yb = a(x), b(x)
+torch.save({"a": ya.cpu(), "b": yb.cpu(), "bi": b.invert(yb).cpu(), "m": m(x).cpu(), "q": q(x.clamp(-1, 1)).cpu(),
+            "off": a[2].norm.offset.cpu(), "shim": _torch_ops.USE_SHIM}, sys.argv[1])
+''' % ROOT
+    res = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / ("out%s.pt" % flag))
+        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, ACIDS_B200_PY_OPS=flag), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(torch.load(out))
+    assert res[0]["shim"] is True and res[1]["shim"] is False
+    for k in ("a", "b", "bi", "m", "q", "off"):
+        assert torch.equal(res[0][k], res[1][k]), k
