@@ -35,6 +35,22 @@ def _fit(ch, x):
     return ch
 
 
+def wrap_ambiguous(ref, norm, weighted=False):
+    """IF rows whose phase advance is +-pi to within rounding: the value is +0.5 or -0.5 by the last bit of the two raw
+    phases (the same frequency either way) — not comparable between two evaluations of the spectrum."""
+    v = ref * float(norm.scale) + float(norm.offset)
+    T = ref.shape[-2]
+    if weighted:
+        n = np.arange(T, dtype=np.float32)
+        a = (n - (T / 2.0 - 1.0)) / (T / 2.0)
+        w = (1.5 * T) / (T * T - 1.0) * (1.0 - a * a)
+        v = v / np.where(w == 0, 1, w)[:, None]
+    amb = np.abs(np.abs(v) - 0.5) < 1e-4
+    amb[..., 0, :] = False
+    amb[..., T - 1, :] = np.abs(np.abs(v[..., T - 1, :]) - 0.5 * np.pi) < 3e-4         # the last row is not divided by pi
+    return amb
+
+
 def assert_phase_close(a, b, X, rad_per_unit, diff, what):
     """Phase-like outputs of two evaluations of the same spectrum.  The two FFTs agree to ~3e-7 of the spectrum's peak
     (different fusion / contraction of the same arithmetic); the phase of a bin of modulus |X| then moves by up to that
@@ -74,6 +90,8 @@ def test_fused_equals_children(T, n_fft, hop, kind):
     assert_parity(host(y[..., 0, :]), host(ref[..., 0, :]), 1e-5, "magnitude slot")
     X = host(ch[0](x))
     ok = if_mask(X) if kind != "polar" else ~branch_cut(X)
+    if kind != "polar":
+        ok &= ~wrap_ambiguous(host(ref[..., 1, :]), ch[1].phase.norm, kind.endswith("weighted"))
     assert ok.mean() > 0.9
     unit = float(ch[1].phase.norm.scale) * (np.pi if kind != "polar" else 1.0)      # IF rows are phase differences / (2) pi
     assert_phase_close(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, host(ref[..., 1, :]), 0), X, unit, kind != "polar", "phase slot")
@@ -96,7 +114,7 @@ def test_fused_midside_and_options(T):
                 assert y.shape == ref.shape == (5, 2, 79, 2, 513 - (0 if keep else 1))
                 assert_parity(host(y[..., 0, :]), host(ref[..., 0, :]), 1e-5, "magnitude slot")
                 X = host(ch[1](ch[0](x)))[..., (0 if keep else 1):]
-                ok = if_mask(X)
+                ok = if_mask(X) & ~wrap_ambiguous(host(ref[..., 1, :]), ch[2].phase.norm)
                 assert_phase_close(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, host(ref[..., 1, :]), 0), X,
                                    float(ch[2].phase.norm.scale) * np.pi, True, "IF slot")
                 xi = ch.invert(y)
@@ -147,7 +165,7 @@ def test_cfg4_full_size_chain(T):
     assert y.shape == (16, 2, 173, 2, 2049)
     assert_parity(host(y[..., 0, :]), host(ref[..., 0, :]), 1e-5, "cfg4 magnitude slot")
     X = host(ch[1](ch[0](x)))
-    ok = if_mask(X)
+    ok = if_mask(X) & ~wrap_ambiguous(host(ref[..., 1, :]), ch[2].phase.norm)
     assert ok.mean() > 0.95
     assert_phase_close(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, host(ref[..., 1, :]), 0), X,
                        float(ch[2].phase.norm.scale) * np.pi, True, "cfg4 IF slot")
@@ -170,7 +188,8 @@ def test_cfg4_golden_through_the_c_abi():
     assert tuple(y.shape) == g["y"].shape
     assert_parity(host(y[..., 0, :]), g["y"][..., 0, :], 1e-4, "cfg4 golden magnitude")
     X = host(ops.stft_fwd(ops.midside(x), w, 4096, 1024))
-    ok = if_mask(X)
+    from types import SimpleNamespace
+    ok = if_mask(X) & ~wrap_ambiguous(g["y"][..., 1, :], SimpleNamespace(scale=g["ph_scale"], offset=g["ph_offset"]))
     assert_parity(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, g["y"][..., 1, :], 0), 2e-4, "cfg4 golden IF")
 
 
@@ -193,9 +212,15 @@ def test_stft_stats_equals_stats_of_the_spectrum(n_fft, hop, contrast):
     v = {"log1p": np.log1p(a), "log": np.log(np.maximum(a, 1e-6)), None: a}[contrast]
     want = np.array([v.min(), v.max(), v.mean(), v.std(ddof=1)])
     span = want[1] - want[0]
-    # min of log(|X|) is decided by the FFT's rounding noise on near-zero bins: judged against the value range
-    assert np.all(np.abs(st - want) <= 2e-5 * span + 1e-4 * np.abs(want) * (contrast != "log")), (st, want)
-    assert np.all(np.abs(st - ref) <= 2e-5 * span + 1e-4 * np.abs(ref) * (contrast != "log")), (st, ref)
+    tol = lambda r: 2e-5 * span + 1e-4 * np.abs(r) * (contrast != "log")
+    lo = 0
+    if contrast == "log":
+        # the minimum of log(|X|) is the logarithm of the bin closest to zero, i.e. of the FFT's rounding noise on it
+        # (|X| ~ 1e-5 of the peak): only bounded here — not below the clamp, within a factor e^1.5 of the other evaluations
+        lo = 1
+        assert st[0] >= np.log(1e-6) - 1e-4 and abs(st[0] - want[0]) <= 1.5 and abs(st[0] - ref[0]) <= 1.5, (st, want, ref)
+    assert np.all(np.abs(st - want)[lo:] <= tol(want)[lo:]), (st, want)
+    assert np.all(np.abs(st - ref)[lo:] <= tol(ref)[lo:]), (st, ref)
 
 
 def test_fused_chain_scale_data_is_one_pass(T):
