@@ -8,7 +8,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACIDS_B200_LIB") or os.path.join(_HERE, "libacids_b200.so")   # override: tuning builds only
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ACIDS_OK, ACIDS_EINVAL, ACIDS_ENOTSUP, ACIDS_ECUDA, ACIDS_EWORKSPACE = 0, -1, -2, -3, -4
 CONTRAST_IDS = {None: 0, "none": 0, "log1p": 1, "log": 2, "log10": 3}
@@ -53,6 +53,9 @@ _PROTOTYPES = {
     "acids_istft_ola": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "acids_irfft_frames": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     "acids_ola_stream": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int64, _P, c_float, _P, _P, _P]),
+    "acids_stream_analysis": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P]),
+    "acids_stream_synthesis": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_float, _P, _P, _P]),
+    "acids_stream_roundtrip": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P]),
     "acids_mulaw_encode": (c_int, [_P, c_int64, c_int64, c_int, c_float, c_int, c_int, _P, _P]),
     "acids_mulaw_decode": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "acids_one_hot": (c_int, [_P, c_int64, c_int, _P, _P]),

@@ -59,6 +59,25 @@ __device__ __forceinline__ void group_sync(int group) {
     }
 }
 
+// ---- mbarrier (shared-memory phase barrier): split arrive / wait, so that a warp can signal "my rows are written" and only
+// wait much later, when it needs everybody's rows (the lagged epilogue of the fused forward kernel) ----
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {      // release at CTA scope
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {      // acquire at CTA scope
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+
 // streaming (read-once / write-once) global accesses: keep them out of L1
 __device__ __forceinline__ float2 ldg_stream2(const float2* p) {
     float2 r;

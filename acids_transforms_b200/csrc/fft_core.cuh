@@ -96,6 +96,19 @@ ACIDS_HD cf mul_root(cf a) {
     return cmul(a, mk(c, INV ? s : -s));
 }
 
+// the same with a run-time slot index that is a constant after unrolling (the switch folds away)
+template <int R, bool INV>
+ACIDS_HD cf mul_root_sw(cf a, int q) {
+#define ACIDS_ROOT_CASE(Q) case Q: return mul_root<R, ((Q) < R / 2 ? (Q) : 0), INV>(a);
+    switch (q) {
+        ACIDS_ROOT_CASE(0) ACIDS_ROOT_CASE(1) ACIDS_ROOT_CASE(2) ACIDS_ROOT_CASE(3) ACIDS_ROOT_CASE(4) ACIDS_ROOT_CASE(5)
+        ACIDS_ROOT_CASE(6) ACIDS_ROOT_CASE(7) ACIDS_ROOT_CASE(8) ACIDS_ROOT_CASE(9) ACIDS_ROOT_CASE(10) ACIDS_ROOT_CASE(11)
+        ACIDS_ROOT_CASE(12) ACIDS_ROOT_CASE(13) ACIDS_ROOT_CASE(14) ACIDS_ROOT_CASE(15)
+    }
+#undef ACIDS_ROOT_CASE
+    return a;
+}
+
 // In-place radix-R DFT of a[0..R), natural-order output.  b[q] = sum_r a[r] e^{-+2 pi i r q / R}.
 template <int R, bool INV>
 struct Dft;
@@ -201,8 +214,18 @@ struct Plan {
     static constexpr int T = T_;
     static constexpr int V = M / T_;
     static constexpr int NP = (R3_ > 1) ? 4 : ((R2_ > 1) ? 3 : 2);
-    static constexpr int PADLOG = 4;
-    static constexpr int SMEM_CF = M + 2 * (M >> PADLOG) + 2;   // exchange buffer, complex slots (even: 16-byte rows)
+#ifndef ACIDS_T16_PADLOG
+#define ACIDS_T16_PADLOG 5
+#endif
+    // two pad slots every 2^PADLOG slots.  The one-exchange plan (16 threads x radix 32) stores runs of 32 slots per thread:
+    // with a pad every 32 the 128-bit stores of a quarter warp are 272 bytes apart (conflict free; every 16: 288 bytes, 2-way)
+#ifndef ACIDS_T16I_PADLOG
+#define ACIDS_T16I_PADLOG 4
+#endif
+    static constexpr int PADLOG = (N_ == 1024 && T_ == 16) ? (R0_ == 32 ? ACIDS_T16_PADLOG : ACIDS_T16I_PADLOG) : 4;
+    // exchange buffer, complex slots (even: 16-byte rows).  Two frames share a warp in the 16-thread plan and park their |X|
+    // rows in their own buffers: 2 * SMEM_CF = 16 (mod 32) floats puts the two half warps' row stores on disjoint banks
+    static constexpr int SMEM_CF = M + 2 * (M >> PADLOG) + 2 + ((N_ == 1024 && T_ == 16) ? 6 : 0);
     static_assert(R0_ * R1_ * R2_ * R3_ == M, "radices must multiply to N/2");
     static_assert(M % T_ == 0, "T must divide N/2");
     static constexpr int radix(int p) { return p == 0 ? R0_ : (p == 1 ? R1_ : (p == 2 ? R2_ : R3_)); }
@@ -227,6 +250,39 @@ struct Plan {
     static constexpr int TWN = tw_off(NP) > 0 ? tw_off(NP) : 1;
 };
 
+// Lane permutation of the paired pass.  Butterfly pi and its mirror NB - pi are taken by the same thread; with
+// pi = tid the mirrored operands of a half warp are a DESCENDING run of 16 exchange slots that straddles two pad
+// groups of the swizzle and folds back onto itself by one bank pair: every mirrored 8-byte access costs 2 wavefronts per
+// half warp instead of 1 (ncu: 16 of the 144 exchange wavefronts of a 1024-point frame).  The bank conflicts of the
+// ascending and of the mirrored accesses are two perfect matchings on the 32 lanes; their union is 2-colourable, and for
+// the 32-thread forward plan the colouring differs from (lanes 0-15 | lanes 16-31) by ONE transposition: lanes 2 and 16
+// trade their butterfly pairs and both access streams are conflict free (tests/emu/emu_fft.cpp counts the wavefronts:
+// n_fft 1024 144 -> 128 = ideal; the larger forward plans gain their first warp's share; tests/emu/emu_search.cpp is the
+// search).  The inverse plans' excess sits in the mirrored STORES of their first pass; no single transposition helps.
+#if !defined(__CUDA_ARCH__) && defined(ACIDS_EMU_SEARCH)
+static int g_pair_swap_a = 0, g_pair_swap_b = 0;
+#endif
+template <class P, int PASS>
+struct PairLane {
+#if !defined(__CUDA_ARCH__) && defined(ACIDS_EMU_SEARCH)
+    static ACIDS_HD int map(int tid) {
+        const int l = tid & 31;
+        return l == g_pair_swap_a ? (tid - l + g_pair_swap_b) : (l == g_pair_swap_b ? (tid - l + g_pair_swap_a) : tid);
+    }
+#else
+#ifdef ACIDS_PAIR_SWAP         // opt-in: measured SLOWER on B200 although the counted wavefronts drop
+    static constexpr bool SWAP = P::T >= 32 && PASS == P::NP - 1 && PASS > 0;      // the forward plans of n_fft >= 1024
+#else
+    static constexpr bool SWAP = false;
+#endif
+    static ACIDS_HD int map(int tid) {
+        if (!SWAP) return tid;
+        const int l = tid & 31;
+        return l == 2 ? tid + 14 : (l == 16 ? tid - 14 : tid);
+    }
+#endif
+};
+
 // Index helpers of the paired pass (radix R, nb = M/R butterflies, pair c of thread tid).
 template <class P, int PASS>
 struct Pairing {
@@ -234,21 +290,23 @@ struct Pairing {
     static constexpr int NB = P::nb(PASS);
     static constexpr int PC = P::bpt(PASS) / 2;   // pairs per thread
     static_assert(P::bpt(PASS) % 2 == 0, "paired pass needs an even butterfly count per thread");
-    static ACIDS_HD int ja(int tid, int c) { return tid + P::T * c; }
+    // pair index of (thread, c); 0 is the self-mirrored pair and stays on thread 0
+    static ACIDS_HD int pi(int tid, int c) { return PairLane<P, PASS>::map(tid) + P::T * c; }
+    static ACIDS_HD int ja(int tid, int c) { return pi(tid, c); }
     static ACIDS_HD int jb(int tid, int c) {
-        int pi = tid + P::T * c;
-        return pi == 0 ? NB / 2 : NB - pi;
+        int p = pi(tid, c);
+        return p == 0 ? NB / 2 : NB - p;
     }
     // k1(tid, c, s) = (s < R/2 ? klo : khi) + s * NB: two per-thread bases, the rest is an immediate
-    static ACIDS_HD int klo(int tid, int c) { return tid + P::T * c; }       // 0 for the self-mirrored pair
+    static ACIDS_HD int klo(int tid, int c) { return pi(tid, c); }       // 0 for the self-mirrored pair
     static ACIDS_HD int khi(int tid, int c) {
-        int pi = tid + P::T * c;
-        return pi != 0 ? pi : NB / 2 - (R / 2) * NB;
+        int p = pi(tid, c);
+        return p != 0 ? p : NB / 2 - (R / 2) * NB;
     }
     // bin index of untangle slot s of pair c: X[k1] and X[M - k1] come out of it
     static ACIDS_HD int k1(int tid, int c, int s) {
-        int pi = tid + P::T * c;
-        if (pi != 0) return pi + s * NB;
+        int p = pi(tid, c);
+        if (p != 0) return p + s * NB;
         return s < R / 2 ? s * NB : NB / 2 + (s - R / 2) * NB;
     }
 };
@@ -261,9 +319,22 @@ template <class P, bool INV>
 struct FrameFFT {
     static constexpr int PAIRED = INV ? 0 : P::NP - 1;
     using PR = Pairing<P, PAIRED>;
+    // COMPACT_WK: the untangle twiddle of slot s of a pair is W_N^{k1}, k1 = (s < R/2 ? klo : khi) + s NB, and W_N^{s NB} =
+    // W_{2R}^s is a compile-time 2R-th root of unity: keep W_N^{klo} and W_N^{khi} per pair (4 registers) instead of R
+    // twiddles (16 registers for the radix-8 plans) and apply the constant root with immediates (mul_root: free for s = 0 and
+    // s = R/2, two packed instructions otherwise).  Registers, not arithmetic, bound these kernels.
+#ifndef ACIDS_COMPACT_WK
+#define ACIDS_COMPACT_WK 1
+#endif
+    static constexpr bool COMPACT_WK = ACIDS_COMPACT_WK && (32 % (2 * PR::R) == 0);
     cf tw[P::TWN];        // pass twiddles (already conjugated for INV)
-    cf wk[P::V / 2];      // untangle twiddles e^{-2 pi i k1 / N} per (pair, slot); conj for INV
+    cf wk[COMPACT_WK ? 2 * PR::PC : P::V / 2];      // untangle twiddles e^{-2 pi i k1 / N} per (pair, slot); conj for INV
     int tid;
+
+    ACIDS_HD cf untangle_mul(cf a, int c, int s) const {     // a * W_N^{-+ k1(c, s)}; c, s constants after unrolling
+        if (COMPACT_WK) return cmul(mul_root_sw<(COMPACT_WK ? 2 * PR::R : 32), INV>(a, s), wk[2 * c + (s < PR::R / 2 ? 0 : 1)]);
+        return cmul(a, wk[c * PR::R + s]);
+    }
 
     template <int PASS>
     static constexpr bool tw_is_shared() { return PASS != PAIRED && P::tw_shared(PASS); }
@@ -279,10 +350,49 @@ struct FrameFFT {
         return tid + P::T * b;
     }
 
+    // MIRROR_TW (forward, paired last pass): NS * R = M, so butterfly j < NB carries the twiddles W_M^{r j}, and its mirror
+    // NB - j carries W_M^{r (NB - j)} = W_R^r * conj(W_M^{r j}).  A factor W_R^r on input r of a radix-R DFT only rotates its
+    // outputs by one bin, so the mirrored butterfly multiplies by the CONJUGATE of its partner's twiddles and relabels its
+    // outputs: one twiddle set per pair instead of two (14 registers fewer per thread for the radix-8 plans), for free.
+    // The self-mirrored pair (0, NB/2) of thread 0 keeps the set of NB/2 (W_{2R}^r, which the same rule maps onto itself)
+    // and skips the multiplication for butterfly 0.
+#ifndef ACIDS_FWD_MIRROR_TW
+#define ACIDS_FWD_MIRROR_TW 1
+#endif
+    template <int PASS>
+    static constexpr bool mirror_tw() { return ACIDS_FWD_MIRROR_TW && !INV && PASS == PAIRED && PASS > 0 && P::ns(PASS) * P::radix(PASS) == P::M; }
+
+    // POST_TW (inverse, two-pass plans with a wide last pass, i.e. the 16-thread n_fft = 1024 plan): the twiddles of pass 1
+    // (R1 - 1 = 31 per thread on the input side) are applied to the OUTPUTS of the paired pass 0 instead: output q of
+    // butterfly j is element j R0 + q, which pass 1 multiplies by W_M^{j q}.  The mirrored butterfly NB0 - j needs
+    // W_M^{(NB0 - j) q} = W_{R0}^q * conj(W_M^{j q}), and a factor W_{R0}^q on OUTPUT q of a radix-R0 DFT is a cyclic shift of
+    // its INPUTS by one: R0 - 1 = 15 twiddles per thread serve both butterflies, the shift is a register relabelling.
+    static constexpr bool POST_TW = INV && P::NP == 2 && P::N == 1024 && P::T == 16 && P::ns(1) * P::radix(1) == P::M &&
+                                    P::nb(1) == P::radix(0);
+
     template <int PASS>
     ACIDS_HD void init_pass() {
         constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = tw_is_shared<PASS>() ? 1 : P::bpt(PASS);
-        if (PASS > 0) {
+        if (POST_TW) {
+            if (PASS == 1) {
+                constexpr int R0 = P::radix(0);
+#pragma unroll
+                for (int c = 0; c < PR::PC; ++c) {
+                    const int pi = PR::pi(tid, c);
+                    const int j = pi == 0 ? PR::NB / 2 : pi;
+#pragma unroll
+                    for (int q = 1; q < R0; ++q) tw[P::tw_off(1) + c * (R0 - 1) + (q - 1)] = unit((j * q) % P::M, P::M);
+                }
+            }
+        } else if (mirror_tw<PASS>()) {
+#pragma unroll
+            for (int c = 0; c < PR::PC; ++c) {
+                const int pi = PR::pi(tid, c);
+                const int j = pi == 0 ? PR::NB / 2 : pi;
+#pragma unroll
+                for (int r = 1; r < R; ++r) tw[P::tw_off(PASS) + c * (R - 1) + (r - 1)] = cconj(unit((r * j) % (NS * R), NS * R));
+            }
+        } else if (PASS > 0) {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 int j = bfly<PASS>(b);
@@ -303,12 +413,20 @@ struct FrameFFT {
         if (P::NP > 2) init_pass<(P::NP > 2 ? 2 : 0)>();
         if (P::NP > 3) init_pass<(P::NP > 3 ? 3 : 0)>();
 #pragma unroll
-        for (int c = 0; c < PR::PC; ++c)
+        for (int c = 0; c < PR::PC; ++c) {
+            if (COMPACT_WK) {
+                // klo / khi may be negative for the self-mirrored pair (khi = NB/2 - (R/2) NB): reduce modulo N
+                const cf ul = unit((PR::klo(tid, c) + P::N) % P::N, P::N), uh = unit((PR::khi(tid, c) + P::N) % P::N, P::N);
+                wk[2 * c] = INV ? ul : cconj(ul);
+                wk[2 * c + 1] = INV ? uh : cconj(uh);
+            } else {
 #pragma unroll
-            for (int s = 0; s < PR::R; ++s) {
-                cf u = unit(PR::k1(tid, c, s), P::N);
-                wk[c * PR::R + s] = INV ? u : cconj(u);
+                for (int s = 0; s < PR::R; ++s) {
+                    cf u = unit(PR::k1(tid, c, s), P::N);
+                    wk[c * PR::R + s] = INV ? u : cconj(u);
+                }
             }
+        }
     }
 
     // element (complex index) that register v[b*R + r] of pass PASS holds BEFORE the butterfly
@@ -329,8 +447,52 @@ struct FrameFFT {
     template <int PASS>
     ACIDS_HD void butterflies(cf* v) const {
         constexpr int R = P::radix(PASS), B = P::bpt(PASS);
+        if (POST_TW) {
+            if (PASS == 0) {
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const cf* t = tw + P::tw_off(1) + (b >> 1) * (R - 1);
+                    if ((b & 1) == 0) {
+                        const bool sp = PR::pi(tid, b >> 1) == 0;       // butterfly 0: unit twiddles
+                        Dft<R, INV>::run(v + b * R);
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[b * R + q] = csel(sp, v[b * R + q], cmul(v[b * R + q], t[q - 1]));
+                    } else {
+                        const cf last = v[b * R + R - 1];                 // inputs shifted by one (the W_R^q factor on the outputs)
+#pragma unroll
+                        for (int r = R - 1; r > 0; --r) v[b * R + r] = v[b * R + r - 1];
+                        v[b * R] = last;
+                        Dft<R, INV>::run(v + b * R);
+#pragma unroll
+                        for (int q = 1; q < R; ++q) v[b * R + q] = cmul(v[b * R + q], cconj(t[q - 1]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b) Dft<R, INV>::run(v + b * R);
+            }
+            return;
+        }
 #pragma unroll
         for (int b = 0; b < B; ++b) {
+            if (mirror_tw<PASS>()) {
+                const cf* t = tw + P::tw_off(PASS) + (b >> 1) * (R - 1);
+                if ((b & 1) == 0) {
+                    const bool sp = PR::pi(tid, b >> 1) == 0;       // butterfly 0: unit twiddles
+#pragma unroll
+                    for (int r = 1; r < R; ++r) v[b * R + r] = csel(sp, v[b * R + r], cmul(v[b * R + r], t[r - 1]));
+                    Dft<R, INV>::run(v + b * R);
+                } else {
+#pragma unroll
+                    for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], cconj(t[r - 1]));
+                    Dft<R, INV>::run(v + b * R);
+                    const cf first = v[b * R];                       // outputs rotated by one bin (the W_R^r factor)
+#pragma unroll
+                    for (int q = 0; q + 1 < R; ++q) v[b * R + q] = v[b * R + q + 1];
+                    v[b * R + R - 1] = first;
+                }
+                continue;
+            }
             if (PASS > 0) {
                 constexpr int bs = tw_is_shared<PASS>() ? 0 : 1;
 #pragma unroll
@@ -393,7 +555,7 @@ struct FrameFFT {
         for (int c = 0; c < PR::PC; ++c) {
             const cf* va = v + (2 * c) * R;
             const cf* vb = v + (2 * c + 1) * R;
-            const bool sp = (tid + P::T * c) == 0;
+            const bool sp = PR::pi(tid, c) == 0;
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 cf A = va[s], Bv = vb[R - 1 - s];
@@ -407,7 +569,7 @@ struct FrameFFT {
                 }
                 cf E = A + cconj(Bv);                     // A + conj(B)
                 cf O = mul_mi(A) + mk(Bv.y, Bv.x);        // -i (A - conj(B)) = (A.y + B.y, B.x - A.x)
-                cf Pm = cmul(O, wk[c * R + s]);
+                cf Pm = untangle_mul(O, c, s);
                 cf x1 = E + Pm, x2 = cconj(E - Pm);
                 if (c == 0 && s == 0) {
                     x1.y = sp ? 0.f : x1.y;
@@ -427,7 +589,7 @@ struct FrameFFT {
 #pragma unroll
         for (int c = 0; c < PR::PC; ++c) {
             cf za[R], zb[R];
-            const bool sp = (tid + P::T * c) == 0;
+            const bool sp = PR::pi(tid, c) == 0;
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 cf A = in1[c * R + s], Bx = in2[c * R + s];
@@ -437,7 +599,7 @@ struct FrameFFT {
                 }
                 cf E2 = A + cconj(Bx);                        // A + conj(Bx)
                 cf P2 = A - cconj(Bx);                        // A - conj(Bx)
-                cf O2 = cmul(P2, wk[c * R + s]);             // conj(W^k) P2
+                cf O2 = untangle_mul(P2, c, s);             // conj(W^k) P2
                 cf iO = mul_pi(O2);
                 za[s] = E2 + iO;
                 zb[s] = cconj(E2 - iO);

@@ -107,12 +107,34 @@ struct InvCfg {
 #define ACIDS_INV_SMALL_THREADS 128
 #endif
     // n_fft = 2048 (T = 64): 128-thread CTAs at 3 per SM (168 registers); at 256 threads x 2 the 128-register budget spills
-    static constexpr int THREADS = P::T <= 32 ? ACIDS_INV_SMALL_THREADS
+#ifndef ACIDS_INV_T16_THREADS
+#define ACIDS_INV_T16_THREADS 128
+#endif
+#ifndef ACIDS_INV_T16_MINB
+#define ACIDS_INV_T16_MINB 3
+#endif
+    static constexpr int THREADS = (P::N == 1024 && P::T == 16) ? ACIDS_INV_T16_THREADS : P::T <= 32 ? ACIDS_INV_SMALL_THREADS
                                               : (P::T > 256 ? P::T : (P::T == 128 ? ACIDS_INV_T128_THREADS : (P::T == 64 ? 128 : 256)));
-    static constexpr int MINB = P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS)
+    static constexpr int MINB = (P::N == 1024 && P::T == 16) ? ACIDS_INV_T16_MINB : P::T <= 32 ? ACIDS_INV_MINB_SMALL * (128 / ACIDS_INV_SMALL_THREADS)
                                            : (P::T == 64 || P::T == 128 ? 3 : (P::T <= 256 ? 2 : 1));
     static constexpr int G = THREADS / P::T;
+    // RX (the one-exchange n_fft = 1024 plan, two frames per warp): a ring slot doubles as the exchange buffer of the frame
+    // that will be parked in it — the slots a round overwrites hold frames the previous round's gather has finished with —
+    // so 8 frames per round need 11 padded slots (51 KB) instead of 8 exchange buffers + 11 slots (81 KB): 4 CTAs per SM.
+    static constexpr bool RX = P::N == 1024 && P::T == 16;
+    static constexpr int SLOTF = RX ? 2 * P::SMEM_CF : P::N;      // floats per ring slot
+    static constexpr size_t exch_bytes() { return RX ? 0 : (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15); }
 };
+
+// plan of the overlap-add kernel of an n_fft (the per-frame kernels keep the table's plan)
+template <class P> struct OlaPlan { using type = P; };
+// ACIDS_INV1024_T16: the one-exchange plan for the n_fft = 1024 overlap-add kernel.  Measured on B200: 177
+// instead of 258 shared-memory wavefronts and 746 instead of 851 instructions per frame, but 1.29-1.53 ms against 1.11 ms —
+// 32 values per thread need 156-168 registers (12 warps / SM) and each warp issues its 32 exchange accesses back to back
+// (short-scoreboard / MIO-throttle bound at 30-38 % issue utilisation); opt-in until that is solved.
+#ifdef ACIDS_INV1024_T16
+template <> struct OlaPlan<Inv1024> { using type = Inv1024T16; };
+#endif
 
 template <class P>
 __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola_kernel(const InvParams p) {
@@ -122,10 +144,16 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     using FFT = FrameFFT<P, true>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = threadIdx.x / T, tid = threadIdx.x % T;
-    cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;
-    constexpr size_t kExch = ((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15;     // keep the ring 16-byte aligned
+    constexpr bool RX = InvCfg<P>::RX;
+    constexpr int SLOTF = InvCfg<P>::SLOTF;
+#ifndef ACIDS_INV_T16_PREFETCH
+#define ACIDS_INV_T16_PREFETCH 1
+#endif
+    constexpr bool PREFETCH = !RX || ACIDS_INV_T16_PREFETCH;      // next round's spectrum rows into registers before the gather
+    cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;      // !RX: the group's exchange buffer
+    constexpr size_t kExch = InvCfg<P>::exch_bytes();                       // keeps the ring 16-byte aligned
     float* ring = reinterpret_cast<float*>(smem_raw + kExch);
-    float2* swin = reinterpret_cast<float2*>(ring + (size_t)p.ring * N);   // synthesis window pairs with irfft's 1/N folded in
+    float2* swin = reinterpret_cast<float2*>(ring + (size_t)p.ring * SLOTF);   // synthesis window pairs with irfft's 1/N folded in
     float* inv_env = reinterpret_cast<float*>(swin + M);   // 1 / sum_i g^2[r + i hop]: the interior envelope
     // window^2 for the envelope (N is a power of two: scaling by N undoes the folded 1/N exactly)
     const float* swf = reinterpret_cast<const float*>(swin);
@@ -183,12 +211,20 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
     int q_next = ta;
     const int q_own_hi = (tb == nT) ? nT - 1 + ov : tb;
     cf i1[V / 2], i2[V / 2], ex;
-    load_spectrum<P>(fft, Xc + (int64_t)(t_start + g) * P::F, t_start + g < tb, i1, i2, ex);
+    if (PREFETCH) load_spectrum<P>(fft, Xc + (int64_t)(t_start + g) * P::F, t_start + g < tb, i1, i2, ex);
     for (int tr = t_start; tr < tb; tr += G) {
         const int t = tr + g;
         const bool valid = t < tb;
+        if (!PREFETCH) load_spectrum<P>(fft, Xc + (int64_t)t * P::F, valid, i1, i2, ex);
         cf v[V];
-        inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
+        if (RX) {
+            // the slot this frame will be parked in is its exchange buffer; the group leaves the buffer before it parks
+            s = reinterpret_cast<cf*>(ring + (size_t)wrap(base_slot + g) * SLOTF);
+            inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
+            group_sync<T, THREADS>(g);
+        } else {
+            inverse_frame<P, THREADS>(fft, i1, i2, ex, v, s, g);
+        }
         if (G == 1 && accum) {
             const int rot = (int)(((int64_t)t * hop) & (N - 1));
             const bool first = tr == t_start;        // nothing of this run is in the buffer yet: every sample opens its segment
@@ -211,7 +247,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                 }
             }
         } else if (valid) {
-            float2* slot = reinterpret_cast<float2*>(ring + (size_t)wrap(base_slot + g) * N);
+            float2* slot = reinterpret_cast<float2*>(ring + (size_t)wrap(base_slot + g) * SLOTF);
 #pragma unroll
             for (int b = 0; b < BL; ++b) {
                 // last-pass outputs sit at n = (tid + T b) + q * Ns: one base, compile-time offsets
@@ -226,7 +262,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
             }
         }
         // the next round's spectrum rows land while this round is gathered
-        if (tr + G < tb) load_spectrum<P>(fft, Xc + (int64_t)(t + G) * P::F, t + G < tb, i1, i2, ex);
+        if (PREFETCH && tr + G < tb) load_spectrum<P>(fft, Xc + (int64_t)(t + G) * P::F, t + G < tb, i1, i2, ex);
         __syncthreads();
         // gather every sample that no later frame can touch
         const int t_done = min(tr + G, tb) - 1;
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                             int slot = slot0;
 #pragma unroll
                             for (int i = 0; i < OV; ++i) {
-                                off[i] = slot * N + (OV - 1 - i) * hop;
+                                off[i] = slot * SLOTF + (OV - 1 - i) * hop;
                                 slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                             }
                             for (int r = r_lo; r < r_hi; r += 128) {
@@ -325,7 +361,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                                 int slot = slot0;
                                 for (int i = 0; i < ov; ++i) {
-                                    const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + (ov - 1 - i) * hop + r);
+                                    const float4 f = *reinterpret_cast<const float4*>(ring + slot * SLOTF + (ov - 1 - i) * hop + r);
                                     acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
                                     slot = (slot + 1 == p.ring) ? 0 : slot + 1;
                                 }
@@ -343,7 +379,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                             int slot = slot0;
                             int o2 = r + (q - t_lo) * hop;
                             for (int tt = t_lo; tt <= t_hi; ++tt, o2 -= hop) {
-                                const float4 f = *reinterpret_cast<const float4*>(ring + slot * N + o2);
+                                const float4 f = *reinterpret_cast<const float4*>(ring + slot * SLOTF + o2);
                                 acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
                                 env.x += g2(o2); env.y += g2(o2 + 1); env.z += g2(o2 + 2); env.w += g2(o2 + 3);
                                 slot = (slot + 1 == p.ring) ? 0 : slot + 1;
@@ -363,7 +399,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                         float acc = 0.f, env = 0.f;
                         int slot = slot0, off = r + (q - t_lo) * hop;
                         for (int tt = t_lo; tt <= t_hi; ++tt) {
-                            acc += ring[slot * N + off];
+                            acc += ring[slot * SLOTF + off];
                             env += g2(off);
                             off -= hop;
                             slot = (slot + 1 == p.ring) ? 0 : slot + 1;
@@ -381,7 +417,7 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
                 float acc = 0.f, env = 0.f;
                 for (int tt = t_lo; tt <= t_hi; ++tt) {
                     const int m = (int)(np - (int64_t)tt * hop);
-                    acc += ring[(size_t)wrap(base_slot + (tt - tr)) * N + m];
+                    acc += ring[(size_t)wrap(base_slot + (tt - tr)) * SLOTF + m];
                     env += g2(m);
                 }
                 const int64_t n = np - p.trim;
@@ -491,7 +527,7 @@ struct InvLaunch {
     static bool accumulates(int hop) { return G == 1 && (P::N % hop) == 0 && (hop & 3) == 0; }
     static size_t smem_ola(int ovc, int hop) {
         // exchange buffers | frame ring (or the partial sums) | window pairs | interior inverse envelope
-        return (((size_t)G * P::SMEM_CF * sizeof(cf) + 15) & ~(size_t)15) + (size_t)(accumulates(hop) ? 1 : G + ovc - 1) * P::N * sizeof(float) +
+        return InvCfg<P>::exch_bytes() + (size_t)(accumulates(hop) ? 1 : G + ovc - 1) * InvCfg<P>::SLOTF * sizeof(float) +
                (size_t)P::M * sizeof(float2) + (size_t)hop * sizeof(float);
     }
     static int ola(InvParams p, cudaStream_t st) {
@@ -575,7 +611,7 @@ static const size_t kMaxSmem = 227 * 1024;
 static int fused_fits(int n_fft, int hop, bool& fits) {
     const int ovc = (n_fft + hop - 1) / hop;
     size_t need = 0;
-    ACIDS_INV_SWITCH(n_fft, need = InvLaunch<PL>::smem_ola(ovc, hop));
+    ACIDS_INV_SWITCH(n_fft, need = InvLaunch<typename OlaPlan<PL>::type>::smem_ola(ovc, hop));
     fits = need <= kMaxSmem;
     return ACIDS_OK;
 }
@@ -625,7 +661,7 @@ extern "C" ACIDS_API int acids_istft_ola(const float* X, int64_t B, int64_t n_fr
         InvParams p{};
         p.X = reinterpret_cast<const cf*>(X); p.B = B; p.n_frames = (int)n_frames; p.hop = hop; p.window = window;
         p.out = out; p.out_len = out_len; p.trim = n_fft / 2; p.ovc = (n_fft + hop - 1) / hop;
-        ACIDS_INV_SWITCH(n_fft, return InvLaunch<PL>::ola(p, st));
+        ACIDS_INV_SWITCH(n_fft, return InvLaunch<typename OlaPlan<PL>::type>::ola(p, st));
         return ACIDS_OK;
     }
     // two-step fallback: frames to the caller's workspace, then a gather

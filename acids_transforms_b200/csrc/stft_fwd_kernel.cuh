@@ -45,11 +45,17 @@ struct FwdParams {
 #ifndef ACIDS_FWD_MINB_SMALL
 #define ACIDS_FWD_MINB_SMALL 4
 #endif
+#ifndef ACIDS_FWD_RIE
+#define ACIDS_FWD_RIE 1
+#endif
 #ifndef ACIDS_FWD_FPW_1024
 #define ACIDS_FWD_FPW_1024 1           // 2: two frames in flight per warp at 168 registers, measured SLOWER (1.35 vs 1.16 ms fused)
 #endif
 #ifndef ACIDS_FWD_THREADS_1024
-#define ACIDS_FWD_THREADS_1024 256     // 8 frames per unit: the epilogue amortises a column's metadata / coefficients over 8 rows
+#define ACIDS_FWD_THREADS_1024 256     // T = 32 plan: 8 frames per unit, the epilogue amortises a column's metadata / coefficients over 8 rows
+#endif
+#ifndef ACIDS_FWD_THREADS_1024R
+#define ACIDS_FWD_THREADS_1024R 128    // T = 16 plan: 8 frames per unit in 4 warps; 4 CTAs / SM (256 threads x 2: 1.21 vs 1.06 ms, barrier bound)
 #endif
 template <class P, int MODE>
 struct FwdCfg {
@@ -64,19 +70,25 @@ struct FwdCfg {
     // for both, and the epilogue amortises a column's metadata / coefficients / dispatch over twice the rows.  Costs
     // registers: 168 per thread, 3 CTAs / SM (n_fft = 1024: 1.17 -> see DESIGN.md section 5).
     static constexpr int FPW = P::N == 1024 ? ACIDS_FWD_FPW_1024 : 1;
-    static constexpr int THREADS = (P::N == 1024 && MODE == 1 /* MODE_REAL */) ? ACIDS_FWD_THREADS_1024
+    static constexpr int THREADS = (P::N == 1024 && MODE == 1 /* MODE_REAL */) ? (P::T == 16 ? ACIDS_FWD_THREADS_1024R : ACIDS_FWD_THREADS_1024)
                                                 : (P::T <= 32 ? 128 : (P::T > 256 ? P::T : (P::T <= 128 ? ACIDS_FWD_MID_THREADS : 256)));
     // MODE_POLAR (2), small plans: 168 registers (3 CTAs / SM) — the arctangents next to the |X| rows spill 100+ bytes at 128
     static constexpr int MINB = (FPW > 1 || (MODE == 2 && P::T <= 32)) ? 3 : (P::T <= 32 ? ACIDS_FWD_MINB_SMALL * 128 / THREADS : (P::T <= 128 ? ACIDS_FWD_MID_MINB : (P::T <= 256 ? 2 : 1)));
     // complex output: no epilogue to hide the next frame's loads behind, so they are issued a whole FFT early into a
     // second register set; that needs ~160 registers -> one CTA less per SM for the small plans
     static constexpr int MINB_COMPLEX = P::T <= 32 ? 3 : MINB;
+#ifndef ACIDS_FWD_LAG
+#define ACIDS_FWD_LAG 0      // measured slower (1.32 vs 1.15 ms on the two-exchange plan): see LAG in the kernel
+#endif
+    static constexpr bool LAG = ACIDS_FWD_LAG && MODE == 1 /* MODE_REAL */ && FPW == 1 && !(ACIDS_FWD_RIE && P::N == 1024 && P::T == 16);
     static constexpr int GT = THREADS / P::T;                   // thread groups per CTA
     static constexpr int G = GT * FPW;                          // frames per unit
     static constexpr int NF = (P::N == 1024 && G % 8 == 0) ? 8 : (G < 4 ? G : 4);   // rows per epilogue tile
     // FPW > 1: the |X| row of a frame is parked in the frame's own exchange buffer (free once the last pass has read
     // it) instead of a separate double-buffered tile: 51 KB instead of 84 KB per CTA, three CTAs fit an SM
-    static constexpr bool ROWS_IN_EXCH = FPW > 1;
+    // the 16-thread n_fft = 1024 plan: two frames per warp double the exchange and row buffers per warp; with separate
+    // double-buffered rows only 2 CTAs fit an SM (1.22 ms), with the rows parked in the exchange buffers 4 do (1.00 ms)
+    static constexpr bool ROWS_IN_EXCH = FPW > 1 || (ACIDS_FWD_RIE && P::N == 1024 && P::T == 16 && MODE == 1);
     static constexpr int VSTR = ROWS_IN_EXCH ? 2 * P::SMEM_CF : ((P::F + 3) & ~3);   // |X| row stride in shared memory (floats)
     static constexpr int VW = (P::bpt(0) % 2 == 0) ? 4 : 2;     // floats per vector load of the first pass
     static_assert(G % NF == 0, "rows per CTA must be a multiple of the row tile");
@@ -109,6 +121,11 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     constexpr bool REALISH = MODE == MODE_REAL || MODE == MODE_POLAR, POLAR = MODE == MODE_POLAR, STATS = MODE == MODE_STATS;
     constexpr bool RIE = REALISH && C::ROWS_IN_EXCH;
     static_assert(!POLAR || !RIE, "the polar epilogue keeps its rows in their own buffers");
+    // LAG: the epilogue of unit u runs AFTER the transform of unit u + 1, and the CTA barrier between "rows written" and
+    // "rows read" becomes a split mbarrier arrive / wait one whole FFT apart: nobody actually waits unless a warp falls a
+    // full unit behind (ncu before: 1.37 stall cycles per issue on the barrier, the warps of a CTA moved in lock-step).
+    constexpr bool LAG = C::LAG;
+    __shared__ uint64_t lag_full[2], lag_empty[2];
     using FFT = FrameFFT<P, false>;
     using PR = typename FFT::PR;
     constexpr int RP = PR::R, NBP = PR::NB;
@@ -147,6 +164,13 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             prows = vrows + 2 * G * VSTR;
             pcarry = G == 1 ? prows : prows + 2 * G * VSTR;
         }
+    }
+    if (LAG && threadIdx.x == 0) {
+        mbar_init(&lag_full[0], THREADS / 32);
+        mbar_init(&lag_full[1], THREADS / 32);
+        mbar_init(&lag_empty[0], THREADS / 32);
+        mbar_init(&lag_empty[1], THREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     float ph_off = 0.f, ph_inv = 1.f;
     if (POLAR) {
@@ -278,6 +302,29 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
         for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
     }
+    // the row-tile epilogue of one unit: rows `vb` (shared memory) -> banded projection -> contrast -> normalise -> `outc`
+    // halo (POLAR): the unit before the CTA's run — rows only, nothing is stored
+    auto run_epilogue = [&](const float* __restrict__ vb, float* __restrict__ outc, int unit_in_clip, bool halo) {
+        const int t0 = unit_in_clip * G;
+        const int n_valid = halo ? 0 : min(G, n_frames - t0);
+        const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
+        float* out0 = outc + (TRANSPOSED ? t0 : t0 * rs);
+        constexpr bool SPREAD = !TRANSPOSED;
+#pragma unroll 1
+        for (int g0 = 0; g0 < G; g0 += NF) {
+            if (g0 >= n_valid) break;
+            if (!TRANSPOSED && N == 1024 && rs == P::F)
+                epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, P::F, SPREAD>(p.ep.contrast, vb + g0 * VSTR, VSTR, threadIdx.x, ea,
+                                                                                      out0 + g0 * rs, rs, cs, n_valid - g0);
+            else
+                epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, 0, SPREAD>(p.ep.contrast, vb + g0 * VSTR, VSTR, threadIdx.x, ea,
+                                                                                   out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
+        }
+        return n_valid;
+    };
+    int it = 0;                       // LAG: units this CTA has transformed so far
+    float* __restrict__ lag_out = nullptr;
+    int lag_uc = 0;
     for (int64_t u = ustart; u < u1; ++u) {
         const int tb = uc * G + g * FPW;             // first frame of this group in the unit
         const int cur_uc = uc;
@@ -478,6 +525,11 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             }
         } else {
             float* __restrict__ vbuf = RIE ? vrows : vrows + buf * (G * VSTR);
+            const int t0 = cur_uc * G;
+            int n_valid = 0;
+            // LAG: this row buffer was last read by the epilogue of the unit two back; every warp ran that epilogue before
+            // its previous transform, so the wait is a formality unless a warp is a whole unit behind
+            if (LAG && it >= 2) mbar_wait(&lag_empty[buf], ((it >> 1) & 1) ^ 1);
 #pragma unroll
             for (int f = 0; f < FPW; ++f) {
                 cf o1[V / 2], o2[V / 2], ex;
@@ -539,22 +591,21 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             }
             // One barrier per unit: the rows are complete.  (Double-buffered rows: writers of this buffer two units from now
             // have passed the next barrier, i.e. every thread has left this epilogue.  RIE: see the barrier at the loop top.)
-            __syncthreads();
-            const int t0 = cur_uc * G;
-            const bool halo = POLAR && u < u0;           // the unit before the CTA's run: rows only, nothing is stored
-            const int n_valid = halo ? 0 : min(G, n_frames - t0);
-            const int rs = (int)p.out_row_stride, cs = (int)p.out_col_stride;
-            float* out0 = cur_out + (TRANSPOSED ? t0 : t0 * rs);
-            constexpr bool SPREAD = !TRANSPOSED;
-#pragma unroll 1
-            for (int g0 = 0; g0 < G; g0 += NF) {
-                if (g0 >= n_valid) break;
-                if (!TRANSPOSED && N == 1024 && rs == P::F)
-                    epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, P::F, SPREAD>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
-                                                                                          out0 + g0 * rs, rs, cs, n_valid - g0);
-                else
-                    epilogue_dispatch<THREADS, NF, CSEL, BAND, TRANSPOSED, 0, SPREAD>(p.ep.contrast, vbuf + g0 * VSTR, VSTR, threadIdx.x, ea,
-                                                                                       out0 + (TRANSPOSED ? g0 : g0 * rs), rs, cs, n_valid - g0);
+            if (LAG) {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(&lag_full[buf]);
+                if (it > 0) {
+                    mbar_wait(&lag_full[buf ^ 1], ((it - 1) >> 1) & 1);
+                    run_epilogue(vrows + (buf ^ 1) * (G * VSTR), lag_out, lag_uc, false);
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(&lag_empty[buf ^ 1]);
+                }
+                lag_out = cur_out;
+                lag_uc = cur_uc;
+                ++it;
+            } else {
+                __syncthreads();
+                n_valid = run_epilogue(vbuf, cur_out, cur_uc, POLAR && u < u0);
             }
             if (POLAR) {
                 // ---- phase epilogue: raw phase, or the forward-difference IF of spectral_repr.py:319-323 as the wrapped
@@ -592,6 +643,11 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             if (!RIE) buf ^= 1;
 #endif
         }
+    }
+    if (LAG && it > 0) {       // the last unit's epilogue
+        const int lb = (it - 1) & 1;
+        mbar_wait(&lag_full[lb], ((it - 1) >> 1) & 1);
+        run_epilogue(vrows + lb * (G * VSTR), lag_out, lag_uc, false);
     }
     if (STATS) {
         __syncthreads();
@@ -643,17 +699,37 @@ static int launch_fwd(FwdParams p, cudaStream_t st) {
     return ACIDS_OK;
 }
 
+// plan of the real-output (magnitude / mel) kernels of an n_fft: n_fft = 1024 runs them on the one-exchange plan
+template <class P> struct RealPlan { using type = P; };
+template <> struct RealPlan<Fwd1024> { using type = Fwd1024R; };
+
+// ACIDS_FWD_ONLY=<variant>: tuning builds instantiate one variant only (the full set takes minutes per plan)
+#ifndef ACIDS_FWD_ONLY
+#define ACIDS_FWD_ONLY -1
+#endif
 template <class P>
 static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
+    if (ACIDS_FWD_ONLY >= 0 && variant != ACIDS_FWD_ONLY) {
+        set_error("stft_fwd: this tuning build only holds kernel variant %d (asked for %d)", (int)ACIDS_FWD_ONLY, variant);
+        return ACIDS_ENOTSUP;
+    }
+    using PR_ = typename RealPlan<P>::type;
+    if constexpr (ACIDS_FWD_ONLY >= 0) {
+        if constexpr (ACIDS_FWD_ONLY == VAR_MAG_SMEM) return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
+        else if constexpr (ACIDS_FWD_ONLY == VAR_COMPLEX) return launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
+        else if constexpr (ACIDS_FWD_ONLY == VAR_MAG_NOBAND) return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
+        else if constexpr (ACIDS_FWD_ONLY == VAR_MEL_POWER_SMEM) return launch_fwd<PR_, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
+        else return ACIDS_ENOTSUP;
+    } else
     switch (variant) {
         case VAR_COMPLEX: return launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
-        case VAR_MAG_NOBAND: return launch_fwd<P, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
-        case VAR_MAG_SMEM: return launch_fwd<P, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
-        case VAR_MAG_GLOBAL: return launch_fwd<P, MODE_REAL, 1, -1, BAND_GLOBAL, false>(p, st);
-        case VAR_MEL_POWER_SMEM: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
-        case VAR_MEL_POWER_GLOBAL: return launch_fwd<P, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
-        case VAR_MEL_ANY_SMEM: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
-        case VAR_MEL_ANY_GLOBAL: return launch_fwd<P, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
+        case VAR_MAG_NOBAND: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
+        case VAR_MAG_SMEM: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
+        case VAR_MAG_GLOBAL: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_GLOBAL, false>(p, st);
+        case VAR_MEL_POWER_SMEM: return launch_fwd<PR_, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
+        case VAR_MEL_POWER_GLOBAL: return launch_fwd<PR_, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
+        case VAR_MEL_ANY_SMEM: return launch_fwd<PR_, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
+        case VAR_MEL_ANY_GLOBAL: return launch_fwd<PR_, MODE_REAL, 0, ACIDS_CONTRAST_NONE, BAND_GLOBAL, true>(p, st);
         case VAR_STATS: return launch_fwd<P, MODE_STATS, 1, -1, BAND_NONE, false>(p, st);
         case VAR_POLAR_NOBAND: return p.midside ? launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false, true>(p, st) : launch_fwd<P, MODE_POLAR, 1, -1, BAND_NONE, false>(p, st);
         case VAR_POLAR_SMEM: return p.midside ? launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false, true>(p, st) : launch_fwd<P, MODE_POLAR, 1, -1, BAND_SMEM, false>(p, st);

@@ -613,6 +613,80 @@ def ola_stream(frames, hop, keep, carry_in, gain) -> Tuple[torch.Tensor, torch.T
 
 
 # ------------------------------------------------------------------------------------------------
+# (4b) the block-by-block streaming step as one kernel (stream.cu)
+# ------------------------------------------------------------------------------------------------
+def _stream_state(state: torch.Tensor, B: int, keep: int, what: str) -> torch.Tensor:
+    if not (state.is_cuda and state.dtype == torch.float32 and state.is_contiguous() and state.numel() == B * keep):
+        raise RuntimeError("acids_b200: stream step: `%s` must be a contiguous float32 CUDA tensor of %d x %d samples "
+                           "(it is advanced in place)" % (what, B, keep))
+    return state
+
+
+def stream_analysis(x, window, n_fft, hop, tail, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """OverlapAdd.forward + RealtimeSTFT/DGT.forward on one block (oadd.py:70-74, stft.py:248-253): x [..., n hop] ->
+    complex64 [..., n, n_fft/2+1]; `tail` [..., n_fft - hop] (OverlapAdd.input_buffer) is advanced IN PLACE."""
+    lib = _lib.load()
+    xd = _dev(x).to(torch.float32)
+    xf, batch = _flat_batch(xd, 1)
+    B, C = xf.shape
+    if C % hop:
+        raise RuntimeError("acids_b200: stream step: the block length %d is not a multiple of hop=%d" % (C, hop))
+    n, F = C // hop, n_fft // 2 + 1
+    dev = xf.device
+    _stream_state(tail, B, n_fft - hop, "tail")
+    w = window.to(dev, torch.float32).contiguous()
+    if out is None:
+        out = torch.empty((B, n, F, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_stream_analysis, _ptr(xf), B, n, n_fft, hop, _ptr(w), _ptr(tail), _ptr(out), _stream(dev))
+    return torch.view_as_complex(out.reshape(tuple(batch) + (n, F, 2)))
+
+
+def stream_synthesis(X, inv_window, n_fft, hop, gain, carry, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RealtimeSTFT/DGT.invert + OverlapAdd.invert on one block (stft.py:259-266, oadd.py:91-104): complex64
+    [..., n, n_fft/2+1] -> [..., n hop]; `carry` [..., n_fft - hop] (OverlapAdd.output_buffer) is advanced IN PLACE."""
+    lib = _lib.load()
+    Xd = _dev(X)
+    Xr = torch.view_as_real(Xd.to(torch.complex64)).contiguous()
+    Xf, batch = _flat_batch(Xr, 3)
+    B, n, F, _ = Xf.shape
+    if F != n_fft // 2 + 1:
+        raise RuntimeError("acids_b200: stream step: %d bins do not belong to n_fft=%d" % (F, n_fft))
+    dev = Xf.device
+    _stream_state(carry, B, n_fft - hop, "carry")
+    w = inv_window.to(dev, torch.float32).contiguous()
+    if out is None:
+        out = torch.empty((B, n * hop), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_stream_synthesis, _ptr(Xf), B, n, n_fft, hop, _ptr(w), float(gain), _ptr(carry), _ptr(out), _stream(dev))
+    return out.reshape(tuple(batch) + (n * hop,))
+
+
+def stream_roundtrip(x, window, inv_window, n_fft, hop, gain, tail, carry, out: Optional[torch.Tensor] = None,
+                     spectrum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """stream_analysis followed by stream_synthesis in ONE kernel, the spectrum staying in registers (optionally also
+    written to `spectrum`, float32 [B, n, F, 2])."""
+    lib = _lib.load()
+    xd = _dev(x).to(torch.float32)
+    xf, batch = _flat_batch(xd, 1)
+    B, C = xf.shape
+    if C % hop:
+        raise RuntimeError("acids_b200: stream step: the block length %d is not a multiple of hop=%d" % (C, hop))
+    n = C // hop
+    dev = xf.device
+    _stream_state(tail, B, n_fft - hop, "tail")
+    _stream_state(carry, B, n_fft - hop, "carry")
+    w = window.to(dev, torch.float32).contiguous()
+    iw = inv_window.to(dev, torch.float32).contiguous()
+    if out is None:
+        out = torch.empty((B, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_stream_roundtrip, _ptr(xf), B, n, n_fft, hop, _ptr(w), _ptr(iw), float(gain), _ptr(tail), _ptr(carry),
+             _ptr(spectrum), _ptr(out), _stream(dev))
+    return out.reshape(tuple(batch) + (C,))
+
+
+# ------------------------------------------------------------------------------------------------
 # (5) mu-law / one-hot
 # ------------------------------------------------------------------------------------------------
 def _log1p_mu(channels: int) -> float:

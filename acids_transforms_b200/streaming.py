@@ -104,3 +104,88 @@ class GraphedStep:
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class StreamStep:
+    """The block-by-block step of an (OverlapAdd, RealtimeSTFT | RealtimeDGT) pair as ONE kernel launch per direction —
+    or one launch for the whole round trip — instead of the 7-9 kernels of the eager modules (csrc/stream.cu).
+
+        step = StreamStep(oadd, rt, batch_shape=(16,), device="cuda")
+        X = step.analysis(block)        # OverlapAdd.forward -> rt.forward          [..., n hop] -> complex [..., n, F]
+        y = step.synthesis(X)           # rt.invert -> OverlapAdd.invert            complex [..., n, F] -> [..., n hop]
+        y = step.roundtrip(block)       # both, the spectrum never leaves the registers
+
+    The carried state (`OverlapAdd.input_buffer` / `.output_buffer`, oadd.py:70-104) lives in two tensors of this object
+    at fixed addresses and is advanced in place by the kernels, so a call is capturable in a CUDA graph as is
+    (`graph=True` replays the round trip from one: the launch is then a single cudaGraphLaunch without any per-call
+    Python argument marshalling).  The synthesis half reproduces the eager kernels bit for bit, the analysis half to rounding
+    (<= 2e-6 of the peak: ptxas fuses the window into the first butterfly level differently in the two kernels).  `pull()` copies
+    the modules' current state in, `push()` hands the state back to the modules (so eager calls can continue the stream).
+    """
+
+    def __init__(self, oadd, rt, batch_shape=(), device="cuda", graph: bool = False, block: int = 0):
+        from . import ops
+        self._ops = ops
+        self.oadd, self.rt = oadd, rt
+        self.n_fft, self.hop = int(rt._n_fft), int(oadd._hop)
+        if int(oadd._n_fft) != self.n_fft:
+            raise RuntimeError("StreamStep: OverlapAdd(n_fft=%d) feeds a transform of n_fft=%d" % (oadd._n_fft, self.n_fft))
+        if self.n_fft % self.hop:
+            raise RuntimeError("StreamStep: hop=%d must divide n_fft=%d" % (self.hop, self.n_fft))
+        self.keep = self.n_fft - self.hop
+        self.batch_shape = tuple(int(b) for b in batch_shape)
+        dev = torch.device(device)
+        self.tail = torch.zeros(self.batch_shape + (self.keep,), dtype=torch.float32, device=dev)
+        self.carry = torch.zeros(self.batch_shape + (self.keep,), dtype=torch.float32, device=dev)
+        self.window = rt.window.detach()[:self.n_fft].to(dev, torch.float32).contiguous()
+        self.inv_window = rt.inv_window.detach()[:self.n_fft].to(dev, torch.float32).contiguous()
+        self.gain = float(oadd._gain)
+        self._graph = None
+        if graph:
+            if block <= 0 or block % self.hop:
+                raise RuntimeError("StreamStep(graph=True) needs the block length (a multiple of hop)")
+            self._static_in = torch.zeros(self.batch_shape + (block,), dtype=torch.float32, device=dev)
+            self._static_out = torch.empty_like(self._static_in)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._roundtrip(self._static_in, self._static_out)       # opt-in of the kernel's shared memory happens here
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.reset()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._roundtrip(self._static_in, self._static_out)
+
+    def reset(self) -> None:
+        self.tail.zero_()
+        self.carry.zero_()
+
+    def pull(self) -> None:
+        """Take over the stream where the eager modules stand."""
+        if self.oadd.input_buffer.shape == self.tail.shape:
+            self.tail.copy_(self.oadd.input_buffer)
+        if self.oadd.output_buffer.shape == self.carry.shape:
+            self.carry.copy_(self.oadd.output_buffer)
+
+    def push(self) -> None:
+        """Hand the stream back to the eager modules."""
+        self.oadd.input_buffer = self.tail.clone()
+        self.oadd.output_buffer = self.carry.clone()
+
+    def analysis(self, x: torch.Tensor) -> torch.Tensor:
+        return self._ops.stream_analysis(x, self.window, self.n_fft, self.hop, self.tail)
+
+    def synthesis(self, X: torch.Tensor) -> torch.Tensor:
+        return self._ops.stream_synthesis(X, self.inv_window, self.n_fft, self.hop, self.gain, self.carry)
+
+    def _roundtrip(self, x: torch.Tensor, out=None) -> torch.Tensor:
+        return self._ops.stream_roundtrip(x, self.window, self.inv_window, self.n_fft, self.hop, self.gain, self.tail, self.carry, out=out)
+
+    def roundtrip(self, x: torch.Tensor) -> torch.Tensor:
+        if self._graph is not None:
+            if x.shape != self._static_in.shape:
+                raise RuntimeError("StreamStep was captured for %s, got %s" % (tuple(self._static_in.shape), tuple(x.shape)))
+            self._static_in.copy_(x, non_blocking=True)
+            self._graph.replay()
+            return self._static_out
+        return self._roundtrip(x)

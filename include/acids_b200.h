@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACIDS_ABI_VERSION 2
+#define ACIDS_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ACIDS_API __attribute__((visibility("default")))
@@ -224,6 +224,27 @@ ACIDS_API int acids_irfft_frames(const float* X, int64_t rows, int n_fft, const 
  *   by `gain`.  out_len = (n-1)*hop + n_fft - keep.                                             */
 ACIDS_API int acids_ola_stream(const float* frames, int64_t B, int64_t n, int n_fft, int hop, int64_t keep,
                      const float* carry_in, float gain, float* out, float* carry_out, void* stream);
+
+/* ---- (4b) block-by-block streaming step as ONE kernel -------------------------------
+ * The reference's real-time use (README.md:4): per block of n * hop new samples per stream,
+ *   analysis :  OverlapAdd.forward (oadd.py:70-74: saved tail ++ block, framed with hop) ->
+ *               RealtimeSTFT / RealtimeDGT.forward (stft.py:248-253, dgt.py:284-289: rfft(frame * window))
+ *   synthesis:  RealtimeSTFT / RealtimeDGT.invert (stft.py:259-266, dgt.py:296-302: irfft(X) * inv_window) ->
+ *               OverlapAdd.invert (oadd.py:91-104: carried tail + rectangular overlap-add, / gain, next carry)
+ * One CTA per stream; `tail` (OverlapAdd.input_buffer) and `carry` (OverlapAdd.output_buffer), both [B, n_fft - hop],
+ * live at fixed addresses and are advanced IN PLACE, so a step is one launch and capturable in a CUDA graph as is.
+ * hop must divide n_fft, and a block must be at least as long as the carried tail (n * hop >= n_fft - hop).
+ * Synthesis is bit-identical to acids_irfft_frames + acids_ola_stream; analysis agrees with acids_stft_fwd(center=0) to
+ * rounding (<= 2e-6 of the peak; the two kernels' packed multiply-adds are contracted differently by ptxas).
+ *   x [B, n*hop], X complex64 [B, n, n_fft/2+1], out [B, n*hop].
+ * acids_stream_roundtrip is analysis followed by synthesis with the spectrum kept in registers (X_out may be NULL).     */
+ACIDS_API int acids_stream_analysis(const float* x, int64_t B, int64_t n, int n_fft, int hop, const float* window,
+                          float* tail, float* X_out, void* stream);
+ACIDS_API int acids_stream_synthesis(const float* X, int64_t B, int64_t n, int n_fft, int hop, const float* inv_window,
+                           float gain, float* carry, float* out, void* stream);
+ACIDS_API int acids_stream_roundtrip(const float* x, int64_t B, int64_t n, int n_fft, int hop, const float* window,
+                           const float* inv_window, float gain, float* tail, float* carry, float* X_out, float* out,
+                           void* stream);
 
 /* ---- (5) mu-law and one-hot ------------------------------------------------------------------
  * torchaudio mu_law_encoding / decoding (functional.py:690-700, :723-729) as used by raw.py:282-316.

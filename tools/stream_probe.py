@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import acids_transforms_b200.transforms as Tr
-from acids_transforms_b200.streaming import GraphedStep
+from acids_transforms_b200.streaming import GraphedStep, StreamStep
 
 
 def wall_us(fn, x, iters=300, warm=30):
@@ -32,6 +32,20 @@ def main():
         step = GraphedStep(graphed, lambda b: graphed.invert(graphed(b)), x)
         tag = "B%d_block%d" % (B, block)
         res[tag] = dict(eager_us=round(wall_us(lambda b: eager.invert(eager(b)), x), 1), graph_us=round(wall_us(step, x), 1))
+        # the same round trip as ONE kernel (csrc/stream.cu): called through ctypes, and replayed from a CUDA graph
+        oadd, rt = Tr.OverlapAdd(1024, 256).cuda(), Tr.RealtimeSTFT(n_fft=1024, hop_length=256).cuda()
+        one = StreamStep(oadd, rt, batch_shape=(B,))
+        oneg = StreamStep(oadd, rt, batch_shape=(B,), graph=True, block=block)
+        res[tag]["one_kernel_us"] = round(wall_us(one.roundtrip, x), 1)
+        res[tag]["one_kernel_graph_us"] = round(wall_us(oneg.roundtrip, x), 1)
+        # device time of the kernel alone
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(200):
+            oneg._graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        res[tag]["one_kernel_device_us"] = round(s.elapsed_time(e) / 200 * 1e3, 2)
     print(json.dumps(res))
 
 
