@@ -33,6 +33,7 @@ _PROTOTYPES = {
     "acids_abi_version": (c_int, []),
     "acids_last_error": (c_char_p, []),
     "acids_stft_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int64, _P, _P]),
+    "acids_midside_stft_fwd": (c_int, [_P, c_int64, c_int64, _P, c_int, c_int, c_int64, c_int, _P, _P]),
     "acids_stft_mag_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int64, Band, c_int,
                                    c_float, _P, _P, c_int, _P, c_int64, c_int64, _P]),
     "acids_stft_polar_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int64, c_int, Band, c_int, c_float,

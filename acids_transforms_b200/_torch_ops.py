@@ -26,6 +26,7 @@ else:
 
 _SCHEMAS = {
     "stft_fwd": "(Tensor x, Tensor window, int n_fft, int hop, bool center) -> Tensor",
+    "midside_stft_fwd": "(Tensor x, Tensor window, int n_fft, int hop, int midside) -> Tensor",
     "stft_mag_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, "
                     "float eps, Tensor? offset, Tensor? scale, bool drop_first) -> Tensor",
     "stft_polar_fwd": "(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, "
@@ -63,6 +64,10 @@ def _stft_fwd(x, window, n_fft: int, hop: int, center: bool):
     return ops.stft_fwd(x, window, n_fft, hop, center)
 
 
+def _midside_stft_fwd(x, window, n_fft: int, hop: int, midside: int):
+    return ops.midside_stft_fwd(x, window, n_fft, hop, midside)
+
+
 def _stft_mag_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contrast: int, eps: float, offset, scale,
                   drop_first: bool):
     return ops.stft_mag_fwd(x, window, n_fft, hop, ops.as_band(band_meta, band_coef), contrast, eps, offset, scale, drop_first)
@@ -76,9 +81,7 @@ def _stft_polar_fwd(x, window, n_fft: int, hop: int, band_meta, band_coef, contr
     if ops.fusable_phase(phase_mode, method):
         return ops.stft_polar_fwd(x, window, n_fft, hop, ops.as_band(band_meta, band_coef), contrast, eps, mag_offset, mag_scale,
                                   phase_mode, method, weighted, ph_offset, ph_scale, drop_first, midside)
-    if midside:
-        x = ops.midside(x, midside == 2, False)
-    X = ops.stft_fwd(x, window, n_fft, hop, True)
+    X = ops.midside_stft_fwd(x, window, n_fft, hop, midside) if midside else ops.stft_fwd(x, window, n_fft, hop, True)
     return _polar_fwd(X, band_meta, band_coef, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted,
                       ph_offset, ph_scale, drop_first)
 

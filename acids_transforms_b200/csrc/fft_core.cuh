@@ -326,7 +326,13 @@ struct FrameFFT {
 #ifndef ACIDS_COMPACT_WK
 #define ACIDS_COMPACT_WK 1
 #endif
-    static constexpr bool COMPACT_WK = ACIDS_COMPACT_WK && (32 % (2 * PR::R) == 0);
+    // (the n_fft = 1024 inverse runs at 168 registers / 3 CTAs either way — at 128 / 4 CTAs it is SLOWER even without spills,
+    // 1.37 vs 1.11 ms — so it keeps its full twiddle tables and saves the ~45 instructions per frame; ACIDS_INV_COMPACT=1 and
+    // ACIDS_INV_DERIVED_TW=1 switch the compact forms on for the inverse plans too)
+#ifndef ACIDS_INV_COMPACT
+#define ACIDS_INV_COMPACT 0
+#endif
+    static constexpr bool COMPACT_WK = ACIDS_COMPACT_WK && (32 % (2 * PR::R) == 0) && (!INV || ACIDS_INV_COMPACT || P::T == 16);
     cf tw[P::TWN];        // pass twiddles (already conjugated for INV)
     cf wk[COMPACT_WK ? 2 * PR::PC : P::V / 2];      // untangle twiddles e^{-2 pi i k1 / N} per (pair, slot); conj for INV
     int tid;
@@ -370,9 +376,23 @@ struct FrameFFT {
     static constexpr bool POST_TW = INV && P::NP == 2 && P::N == 1024 && P::T == 16 && P::ns(1) * P::radix(1) == P::M &&
                                     P::nb(1) == P::radix(0);
 
+    // DERIVED_TW (a non-paired last pass with two butterflies per thread whose twiddle index differs by T): butterfly b = 1
+    // carries W^{r (k + T)} = W^{r k} * W_{NS R / T}^r — its partner's twiddles times a compile-time root of unity.  One set
+    // instead of two (14 registers fewer at radix 8) for ~12 packed instructions per frame; with the compact untangle twiddles
+    // this brings the n_fft = 1024 inverse to 128 registers with 52 bytes of spills (104-144 before) — measured, not adopted.
+#ifndef ACIDS_INV_DERIVED_TW
+#define ACIDS_INV_DERIVED_TW 0
+#endif
+    template <int PASS>
+    static constexpr bool derived_tw() {
+        return ACIDS_INV_DERIVED_TW && INV && PASS > 0 && PASS == P::NP - 1 && PASS != PAIRED && !P::tw_shared(PASS) && P::bpt(PASS) == 2 &&
+               P::ns(PASS) % P::T == 0 && P::ns(PASS) / P::T >= 2 && (32 % ((P::ns(PASS) * P::radix(PASS)) / P::T)) == 0 &&
+               P::radix(PASS) - 1 < ((P::ns(PASS) * P::radix(PASS)) / P::T) / 2;
+    }
+
     template <int PASS>
     ACIDS_HD void init_pass() {
-        constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = tw_is_shared<PASS>() ? 1 : P::bpt(PASS);
+        constexpr int R = P::radix(PASS), NS = P::ns(PASS), B = (tw_is_shared<PASS>() || derived_tw<PASS>()) ? 1 : P::bpt(PASS);
         if (POST_TW) {
             if (PASS == 1) {
                 constexpr int R0 = P::radix(0);
@@ -493,7 +513,14 @@ struct FrameFFT {
                 }
                 continue;
             }
-            if (PASS > 0) {
+            if (derived_tw<PASS>()) {
+                constexpr int RO = (P::ns(PASS) * R) / P::T;       // order of the constant root: W_RO^r
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    const cf a = b == 0 ? v[b * R + r] : mul_root_sw<(derived_tw<PASS>() ? RO : 32), INV>(v[b * R + r], r);
+                    v[b * R + r] = cmul(a, tw[P::tw_off(PASS) + (r - 1)]);
+                }
+            } else if (PASS > 0) {
                 constexpr int bs = tw_is_shared<PASS>() ? 0 : 1;
 #pragma unroll
                 for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], tw[P::tw_off(PASS) + bs * b * (R - 1) + (r - 1)]);

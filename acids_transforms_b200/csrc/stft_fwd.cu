@@ -95,6 +95,20 @@ extern "C" ACIDS_API int acids_stft_fwd(const float* x, int64_t B, int64_t L, in
     return dispatch_fwd(VAR_COMPLEX, n_fft, p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" ACIDS_API int acids_midside_stft_fwd(const float* x, int64_t B, int64_t L, const float* window, int n_fft, int hop,
+                                      int64_t n_frames, int midside, float* out, void* stream) {
+    FwdParams p{};
+    ACIDS_REQUIRE(midside == 1 || midside == 2, ACIDS_EINVAL, "midside_stft_fwd: midside must be 1 (pad_mid=False) or 2 (pad_mid=True)");
+    ACIDS_REQUIRE(B % 2 == 0, ACIDS_EINVAL, "midside_stft_fwd: the MidSide prologue takes contiguous stereo pairs (B=%lld must be even)", (long long)B);
+    int rc = fill_common(p, x, B, L, L, window, n_fft, hop, 1, n_frames);
+    if (rc) return rc;
+    ACIDS_REQUIRE(out, ACIDS_EINVAL, "midside_stft_fwd: NULL output");
+    ACIDS_REQUIRE(n_frames * (n_fft / 2 + 1) < ((int64_t)1 << 30), ACIDS_ENOTSUP, "midside_stft_fwd: more than 2^30 bins per clip");
+    p.out = out;
+    p.midside = midside;
+    return dispatch_fwd(VAR_COMPLEX, n_fft, p, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" ACIDS_API int acids_stft_mag_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window, int n_fft,
                                   int hop, int center, int64_t n_frames, acids_band band, int contrast, float eps,
                                   const float* offset, const float* scale, int drop_first, float* out,

@@ -722,7 +722,8 @@ static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
         else return ACIDS_ENOTSUP;
     } else
     switch (variant) {
-        case VAR_COMPLEX: return launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
+        case VAR_COMPLEX: return p.midside ? launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false, true>(p, st)
+                                           : launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
         case VAR_MAG_NOBAND: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
         case VAR_MAG_SMEM: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
         case VAR_MAG_GLOBAL: return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_GLOBAL, false>(p, st);

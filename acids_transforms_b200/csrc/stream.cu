@@ -85,23 +85,35 @@ __global__ void __launch_bounds__(StreamCfg<PF>::THREADS, 1) stream_step_kernel(
     float* const sbuf = reinterpret_cast<float*>(reinterpret_cast<cf*>(smem_raw) + (size_t)G * PF::SMEM_CF);   // tail ++ block (analysis)
     float* const frames = sbuf + (DO_FWD ? ((p.keep + p.C + 3) & ~3) : 0);                                        // n synthesised frames
     float* const scarry = frames + (DO_INV ? (size_t)p.n * N : 0);                                                // carried tail (synthesis)
+    float* const swf = scarry + (DO_INV ? ((p.keep + 3) & ~3) : 0);                                                // analysis window
+    float* const swi = swf + (DO_FWD ? N : 0);                                                                     // synthesis window
     const int64_t b = blockIdx.x;
     const int hop = p.hop, keep = p.keep, n = p.n;
 
+    // The step is a chain of dependent latencies (a few microseconds in all), so everything that comes from global memory —
+    // the block, both carried buffers, both windows — is requested up front with asynchronous copies straight into shared
+    // memory, and the twiddle set-up (sincospi, ~2 us of ALU work) runs while they are in flight.
+    auto cp4 = [](float* dst, const float* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
+    };
+    if (DO_FWD) {
+        // OverlapAdd.forward: saved tail ++ new block; the block's last `keep` samples are the next tail (oadd.py:70-74)
+        const float* __restrict__ xb = p.x + b * p.C;
+        const float* __restrict__ tb = p.tail + b * keep;
+        for (int i = threadIdx.x; i < keep + p.C; i += THREADS) cp4(sbuf + i, i < keep ? tb + i : xb + (i - keep));
+        for (int i = threadIdx.x; i < N; i += THREADS) cp4(swf + i, p.window + i);
+    }
+    if (DO_INV) {
+        const float* __restrict__ cb = p.carry + b * keep;
+        for (int i = threadIdx.x; i < keep; i += THREADS) cp4(scarry + i, cb + i);
+        for (int i = threadIdx.x; i < N; i += THREADS) cp4(swi + i, p.inv_window + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     FF ff;
     FI fi;
     if (DO_FWD) ff.init(tid);
     if (DO_INV) fi.init(tid);
-    if (DO_FWD) {
-        // OverlapAdd.forward: saved tail ++ new block; the block's last `keep` samples are the next tail (oadd.py:70-74)
-        const float* __restrict__ xb = p.x + b * p.C;
-        float* __restrict__ tb = p.tail + b * keep;
-        for (int i = threadIdx.x; i < keep + p.C; i += THREADS) sbuf[i] = i < keep ? tb[i] : __ldg(xb + (i - keep));
-    }
-    if (DO_INV) {
-        const float* __restrict__ cb = p.carry + b * keep;
-        for (int i = threadIdx.x; i < keep; i += THREADS) scarry[i] = cb[i];
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (DO_FWD) {
         float* __restrict__ tb = p.tail + b * keep;
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(StreamCfg<PF>::THREADS, 1) stream_step_kernel(
 #pragma unroll
                 for (int r = 0; r < R0; ++r) {
                     const int e = ff.template in_index<0>(b0, r);
-                    const float2 w = make_float2(0.5f * __ldg(p.window + 2 * e), 0.5f * __ldg(p.window + 2 * e + 1));
+                    const float2 w = make_float2(0.5f * swf[2 * e], 0.5f * swf[2 * e + 1]);
                     v[b0 * R0 + r] = cmul2(mk(fr[2 * e], fr[2 * e + 1]), mk(w.x, w.y));
                 }
             forward_frame<PF, THREADS>(ff, v, s, g);
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(StreamCfg<PF>::THREADS, 1) stream_step_kernel(
 #pragma unroll
                     for (int q = 0; q < RL; ++q) {
                         const int e = tid + T * bb + q * NSL;
-                        const float2 w = make_float2(__ldg(p.inv_window + 2 * e) * (1.0f / N), __ldg(p.inv_window + 2 * e + 1) * (1.0f / N));
+                        const float2 w = make_float2(swi[2 * e] * (1.0f / N), swi[2 * e + 1] * (1.0f / N));
                         const cf y = cmul2(v[bb * RL + q], mk(w.x, w.y));
                         dst[q * NSL] = make_float2(y.x, y.y);
                     }
@@ -231,7 +243,8 @@ static int launch_stream(const StreamParams& p, int mode, cudaStream_t st) {
     const bool fwd = mode != 1, inv = mode != 0;
     size_t smem = (size_t)G * PF::SMEM_CF * sizeof(cf);
     if (fwd) smem += (size_t)((p.keep + p.C + 3) & ~3) * sizeof(float);
-    if (inv) smem += ((size_t)p.n * PF::N + p.keep) * sizeof(float);
+    if (inv) smem += ((size_t)p.n * PF::N + ((p.keep + 3) & ~3)) * sizeof(float);
+    smem += (size_t)((fwd ? 1 : 0) + (inv ? 1 : 0)) * PF::N * sizeof(float);       // the windows
     ACIDS_REQUIRE(smem <= 227 * 1024, ACIDS_ENOTSUP, "stream step: a block of %d frames of n_fft=%d needs %zu bytes of shared memory (max 232448)",
                   p.n, PF::N, smem);
     void (*kern)(const StreamParams) = mode == 0 ? stream_step_kernel<PF, PI, true, false>

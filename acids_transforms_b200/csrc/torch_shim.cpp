@@ -140,6 +140,23 @@ Tensor stft_fwd(const Tensor& x, const Tensor& window, int64_t n_fft, int64_t ho
     return ret(out.reshape(center ? with_batch(batch, {T, F}) : with_batch(batch, {F})), x);
 }
 
+// MidSide.forward -> STFT.forward in one kernel: raw.py:145-161 + stft.py:101-102
+Tensor midside_stft_fwd(const Tensor& x, const Tensor& window, int64_t n_fft, int64_t hop, int64_t ms) {
+    Tensor xd = dev(x);
+    c10::cuda::CUDAGuard guard(xd.device());
+    check_stft_input(xd, n_fft);
+    TORCH_CHECK(xd.dim() >= 2 && xd.size(-2) == 2, "acids_b200: the fused MidSide prologue needs a stereo [..., 2, L] input");
+    std::vector<int64_t> batch;
+    Tensor xf = flat(xd, 1, batch);
+    const int64_t B = xf.size(0), L = xf.size(1), T = 1 + L / hop, F = n_fft / 2 + 1;
+    Tensor w = dev(window).to(at::kFloat).contiguous();
+    Tensor out = at::empty({B, T, F}, xf.options().dtype(at::kComplexFloat));
+    if (out.numel())
+        check(acids_midside_stft_fwd(xf.data_ptr<float>(), B, L, w.data_ptr<float>(), (int)n_fft, (int)hop, T, (int)ms,
+                                     reinterpret_cast<float*>(out.data_ptr()), stream_of(xf)));
+    return ret(out.reshape(with_batch(batch, {T, F})), x);
+}
+
 // ---- (2) fused STFT + Magnitude: stft.py:101 + spectral_repr.py:215-226 ----
 Tensor stft_mag_fwd(const Tensor& x, const Tensor& window, int64_t n_fft, int64_t hop, const OptTensor& band_meta,
                     const OptTensor& band_coef, int64_t contrast, double eps, const OptTensor& offset, const OptTensor& scale,
@@ -313,8 +330,7 @@ Tensor stft_polar_fwd(const Tensor& x, const Tensor& window, int64_t n_fft, int6
                       bool drop_first, int64_t ms) {
     const bool fusable = phase_mode == ACIDS_PHASE_RAW || (phase_mode == ACIDS_PHASE_IF && method == ACIDS_IF_FORWARD);
     if (!fusable) {              // phase modes that need a scan over the frames: spectrum once, two representation kernels
-        Tensor xi = ms ? midside(x, ms == 2, false) : x;
-        return polar_fwd(stft_fwd(xi, window, n_fft, hop, true), band_meta, band_coef, contrast, eps, mag_offset, mag_scale, phase_mode,
+        return polar_fwd(ms ? midside_stft_fwd(x, window, n_fft, hop, ms) : stft_fwd(x, window, n_fft, hop, true), band_meta, band_coef, contrast, eps, mag_offset, mag_scale, phase_mode,
                          method, weighted, ph_offset, ph_scale, drop_first);
     }
     Tensor xd = dev(x);
@@ -608,6 +624,7 @@ Tensor midside(const Tensor& x, bool pad_mid, bool inverse) {
 
 TORCH_LIBRARY(acids_b200, m) {
     m.def("stft_fwd(Tensor x, Tensor window, int n_fft, int hop, bool center) -> Tensor", &stft_fwd);
+    m.def("midside_stft_fwd(Tensor x, Tensor window, int n_fft, int hop, int midside) -> Tensor", &midside_stft_fwd);
     m.def("stft_mag_fwd(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, "
           "Tensor? offset, Tensor? scale, bool drop_first) -> Tensor", &stft_mag_fwd);
     m.def("stft_polar_fwd(Tensor x, Tensor window, int n_fft, int hop, Tensor? band_meta, Tensor? band_coef, int contrast, float eps, "

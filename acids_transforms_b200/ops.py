@@ -214,6 +214,24 @@ def stft_fwd(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, center
     return _ret(out, x)
 
 
+def midside_stft_fwd(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, midside: int) -> torch.Tensor:
+    """MidSide.forward -> STFT.forward in one kernel: stereo x [..., 2, L] -> complex64 [..., 2, T, F] (raw.py:145-161,
+    stft.py:101-102); midside = 1 (pad_mid=False) or 2 (pad_mid=True).  The mid/side waveform is never written."""
+    lib = _lib.load()
+    xd = _dev(x)
+    _check_stft_input(xd, n_fft)
+    if xd.ndim < 2 or xd.shape[-2] != 2:
+        raise RuntimeError("acids_b200: the fused MidSide prologue needs a stereo [..., 2, L] input")
+    xf, batch = _flat_batch(xd, 1)
+    B, L = xf.shape
+    T, F = n_frames_centered(L, hop), n_fft // 2 + 1
+    w = _dev(window).to(torch.float32).contiguous()
+    out = torch.empty((B, T, F), dtype=torch.complex64, device=xf.device)
+    with torch.cuda.device(xf.device):
+        _run(out, lib.acids_midside_stft_fwd, _ptr(xf), B, L, _ptr(w), n_fft, hop, T, int(midside), _ptr(out), _stream(xf.device))
+    return _ret(out.reshape(tuple(batch) + (T, F)), x)
+
+
 def stft_mag_fwd(x, window, n_fft, hop, band: Optional[BandedMatrix], contrast, eps, offset, scale,
                  drop_first: bool = False, out: Optional[torch.Tensor] = None, out_slot: int = 0, out_slots: int = 1):
     """Fused STFT + Magnitude.forward: x [..., L] -> float32 [..., T, n_cols - drop]  (stft.py:101 + spectral_repr.py:215-226).

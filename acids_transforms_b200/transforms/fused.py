@@ -105,6 +105,12 @@ class FusedSTFTPolar(AudioTransform):
         if self.has_midside and (self.midside.normalize or not stereo):
             fusable = False
         if not fusable:
+            # the chain: spectrum once, then the representation kernels.  MidSide (un-normalised, on stereo input) is folded
+            # into the STFT's sample loads, so its waveform is never written (raw.py:145-161 + stft.py:101-102 in one kernel)
+            if self.has_midside and stereo and not self.midside.normalize and not self.stft.track_phase:
+                X = torch.ops.acids_b200.midside_stft_fwd(x, self.stft.window, self.stft._n_fft, self.stft._hop,
+                                                          2 if self.midside.pad_mid else 1)
+                return self.polar(X)
             return self.polar(self.stft(self._prologue(x)))
         ms = 0
         if self.has_midside:

@@ -583,7 +583,7 @@ def main():
                    "unmodified reference from oracle/_ref, eager" if kind == "reference" else "torch-CPU port of the reference chain, oracle/torch_port.py")}
 
     if rank == 0:
-        kname = "stft_fwd_kernel<Fwd1024,MODE_REAL>"
+        kname = "stft_fwd_kernel<Fwd1024R,MODE_REAL>"
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": fwd_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -94,6 +94,12 @@ typedef struct acids_band {
 ACIDS_API int acids_stft_fwd(const float* x, int64_t B, int64_t L, int64_t ldx, const float* window,
                    int n_fft, int hop, int center, int64_t n_frames, float* out, void* stream);
 
+/* The same with MidSide.forward (raw.py:145-161) folded into the sample loads: x is stereo [B/2, 2, L] (contiguous) and clip
+ * 2p + c of the output is the spectrum of channel c of (mid, side) = ((l + r) / 2 [/ sqrt 2 when midside == 2], (l - r) / 2).
+ * Replaces raw.py:145-161 -> stft.py:101-102 without writing the mid/side waveform (one kernel and 8 B/sample less).     */
+ACIDS_API int acids_midside_stft_fwd(const float* x, int64_t B, int64_t L, const float* window, int n_fft, int hop,
+                           int64_t n_frames, int midside, float* out, void* stream);
+
 /* ---- (2) fused STFT + |.| + banded mel + contrast + normalise ------------------------------
  * Replaces the chain stft.py:101-102 -> spectral_repr.py:217-225 -> norm.py:41 without
  * materialising the complex spectrum.  out float32: row (b, t) starts at

@@ -128,8 +128,13 @@ def test_fused_falls_back(T):
     x = torch.randn(3, 2, 9000, device="cuda")
     for rep in (T.Polar(phase_args={"mode": "bipolar", "unwrap": True}), T.PolarIF(phase_args={"mode": "bipolar", "method": "backward"}),
                 T.PolarIF(phase_args={"mode": "bipolar", "method": "central"})):
+        # MidSide rides in the STFT's sample loads (acids_midside_stft_fwd): mid = (l + r) * (1 / (2 sqrt 2)) there, a true
+        # division by sqrt 2 in the stand-alone kernel — one ulp of the waveform apart
         ch = _fit((T.MidSide() + T.STFT(n_fft=1024, hop_length=256) + rep).cuda(), x)
-        assert torch.equal(ch(x), ch.forward_unfused(x))
+        y, ref = ch(x), ch.forward_unfused(x)
+        assert_parity(host(y[..., 0, :]), host(ref[..., 0, :]), 1e-5, "magnitude slot, folded MidSide")
+        chp = _fit((T.MidSide(pad_mid=False) + T.STFT(n_fft=1024, hop_length=256) + rep).cuda(), x)
+        assert torch.equal(chp(x), chp.forward_unfused(x))          # without the sqrt 2 the arithmetic is the same: bit-identical
     ch = _fit((T.MidSide(normalize=True) + T.STFT(n_fft=1024, hop_length=256) + T.PolarIF()).cuda(), x)
     assert torch.equal(ch(x), ch.forward_unfused(x))
     mono = torch.randn(3, 1, 9000, device="cuda")
@@ -247,3 +252,19 @@ def test_fused_chain_scale_data_is_one_pass(T):
     sc = torch.jit.script(ch)
     sc.scale_data(x)
     assert_parity(host(sc(x)), g["y"], 1e-4, "cfg2 scripted after fused scale_data")
+
+
+def test_midside_folded_into_the_stft(T):
+    """acids_midside_stft_fwd (MidSide.forward inside the STFT's sample loads, raw.py:145-161 + stft.py:101-102) against the
+    two modules run in turn, at n_fft 1024 and 4096, both pad_mid settings, through torch.ops and through the chain plan."""
+    torch.manual_seed(9)
+    x = 0.5 * (2 * torch.rand(3, 2, 40000, device="cuda") - 1)
+    for n_fft, hop in ((1024, 256), (4096, 1024)):
+        for pad_mid in (False, True):
+            ms, st = T.MidSide(pad_mid=pad_mid).cuda(), T.STFT(n_fft=n_fft, hop_length=hop).cuda()
+            want = st(ms(x))
+            got = torch.ops.acids_b200.midside_stft_fwd(x, st.window, n_fft, hop, 2 if pad_mid else 1)
+            assert got.shape == want.shape
+            assert_parity(host(torch.view_as_real(got)), host(torch.view_as_real(want)), 1e-5, "midside+stft %d pad_mid=%s" % (n_fft, pad_mid))
+    with pytest.raises(RuntimeError):
+        torch.ops.acids_b200.midside_stft_fwd(x[:, 0], T.STFT().cuda().window, 1024, 256, 1)      # not stereo

@@ -1,6 +1,6 @@
 """Distil gpurun_out/ ncu captures into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <full.ncu-rep> [bench json ...]
+    python tools/summarize_profiles.py <round-tag> <launches.csv> <full.ncu-rep>[,<more.ncu-rep>...] [bench json ...]
 """
 import csv, json, os, subprocess, sys
 from collections import defaultdict
@@ -36,8 +36,14 @@ with open(os.path.join(OUT, "%s_launches.csv" % tag), "w") as f:
         f.write('"%s",%d,%.1f,%.2f\n' % (n, cnt[n], v, 100 * v / s))
 
 # ---- full capture: key metrics per captured launch ----
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+rr = []
+for one in rep.split(","):
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if not rr:
+        rr = part[:2]
+    idx = [part[0].index(c) if c in part[0] else -1 for c in rr[0]]
+    rr += [[row[i] if i >= 0 else "" for i in idx] for row in part[2:]]
 hh, units = rr[0], rr[1]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
@@ -52,7 +58,7 @@ stalls = [w for w in hh if "issue_stalled" in w and "per_issue_active" in w and 
 traffic = {}
 with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
     f.write("# ncu --set full summary (%s)\n\nSource: `%s` (scratch, not tracked).  One block per captured launch; byte\n"
-            "and time units as printed by ncu.  Stall columns are warps stalled per issued instruction.\n\n" % (tag, os.path.basename(rep)))
+            "and time units as printed by ncu.  Stall columns are warps stalled per issued instruction.\n\n" % (tag, rep))
     for r in rr[2:]:
         name = short(r[hh.index("Kernel Name")])
         f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % name)
@@ -75,8 +81,8 @@ with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
 # the bench kernels are the LARGEST launch of each name
 tj = {}
 for n, v in traffic.items():
-    key = "stft_fwd_kernel<Fwd1024,MODE_REAL>" if ("stft_fwd_kernel" in n and ">, 1, " in n) else \
-          "istft_ola_kernel<Inv1024>" if "istft_ola_kernel" in n else n
+    key = "stft_fwd_kernel<Fwd1024R,MODE_REAL>" if ("stft_fwd_kernel<Plan<1024" in n and ">, 1, " in n) else \
+          "istft_ola_kernel<Inv1024>" if "istft_ola_kernel<Plan<1024" in n else n
     tj[key] = max(tj.get(key, 0), max(v))
 json.dump(tj, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 for i, src in enumerate(sys.argv[4:]):
