@@ -36,15 +36,17 @@ with open(os.path.join(OUT, "%s_launches.csv" % tag), "w") as f:
         f.write('"%s",%d,%.1f,%.2f\n' % (n, cnt[n], v, 100 * v / s))
 
 # ---- full capture: key metrics per captured launch ----
-rr = []
+rr, row_units = [], []
 for one in rep.split(","):
     raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     part = list(csv.reader(raw.splitlines()))
     if not rr:
         rr = part[:2]
     idx = [part[0].index(c) if c in part[0] else -1 for c in rr[0]]
-    rr += [[row[i] if i >= 0 else "" for i in idx] for row in part[2:]]
-hh, units = rr[0], rr[1]
+    for row in part[2:]:
+        rr.append([row[i] if i >= 0 else "" for i in idx])
+        row_units.append([part[1][i] if i >= 0 else "" for i in idx])      # units are per report (Mbyte here, Gbyte there)
+hh = rr[0]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -59,7 +61,7 @@ traffic = {}
 with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
     f.write("# ncu --set full summary (%s)\n\nSource: `%s` (scratch, not tracked).  One block per captured launch; byte\n"
             "and time units as printed by ncu.  Stall columns are warps stalled per issued instruction.\n\n" % (tag, rep))
-    for r in rr[2:]:
+    for r, units in zip(rr[2:], row_units):
         name = short(r[hh.index("Kernel Name")])
         f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % name)
         vals = {}
