@@ -46,6 +46,8 @@ _PROTOTYPES = {
     "acids_phase_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int64, c_int64, _P]),
     "acids_polar_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, c_float, _P, _P, c_int, c_int, c_int, _P, _P, c_int,
                                 _P, c_int64, c_int64, _P, c_int64, c_int64, _P]),
+    "acids_polar_rows_fwd": (c_int, [_P, c_int64, c_int64, c_int, Band, c_int, c_float, _P, _P, c_int, c_int, c_int, _P, _P, c_int,
+                                     _P, c_int64, _P, c_int64, _P]),
     "acids_phase_inv": (c_int, [_P, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "acids_phase_inv_polar": (c_int, [_P, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "acids_polar_to_complex": (c_int, [_P, _P, c_int64, _P, _P]),

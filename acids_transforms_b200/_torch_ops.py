@@ -117,6 +117,9 @@ def _polar_fwd(X, band_meta, band_coef, contrast: int, eps: float, mag_offset, m
     if band is None and Xd.ndim >= 2:       # no mel bank: both halves from one read of the spectrum
         return ops.polar_fwd(X, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted, ph_offset, ph_scale, drop_first)
     F = Xd.shape[-1]
+    if band is not None and Xd.ndim >= 2 and ops.polar_rows_pays(phase_mode, F):
+        # mel bank + raw phase: one row-tile kernel, one read of the spectrum
+        return ops.polar_rows_fwd(X, band, contrast, eps, mag_offset, mag_scale, phase_mode, method, weighted, ph_offset, ph_scale, drop_first)
     n_mag = (band.n_out if band is not None else F) - int(drop_first)
     n_ph = F - int(drop_first)
     if n_mag != n_ph:

@@ -96,6 +96,136 @@ __global__ void __launch_bounds__(NT) mag_epilogue_kernel(const MagParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Polar / PolarIF on a spectrum WITH a mel bank, one read of X (spectral_repr.py:431-440): the magnitude half needs whole
+// rows (banded projection), the IF half the previous frame's phase.  Row-tile kernel derived from mag_epilogue_kernel<PF>:
+// while a lane holds X for its share of a row it parks |X| in the magnitude tile AND the raw phase in a second tile; the
+// CTA then projects the magnitude rows and emits the phase rows — raw, or the forward-difference IF as the wrapped
+// difference of two consecutive raw phases (the arithmetic of the fused STFT -> Polar epilogue).  A CTA owns a CONTIGUOUS
+// run of row tiles, so the phase row preceding a tile is the last row of the previous tile, kept in a ring of ROWS + 1
+// phase rows; only the first tile of a run recomputes it from the spectrum (one extra row per CTA).
+// 8 B read + 8 B written per bin instead of 16 + 8 for the two kernels it replaces.
+// ---------------------------------------------------------------------------------------------
+struct PolarRowsParams {
+    const float2* X;
+    int64_t rows;            // B * n_frames
+    int n_frames, n_bins;
+    EpiParams ep;
+    const float* offset_ptr;
+    const float* scale_ptr;
+    float* out;              // magnitude rows: row r at out + r * out_row_stride
+    int64_t out_row_stride;
+    float* ph_out;           // phase rows: row r at ph_out + r * ph_row_stride
+    int64_t ph_row_stride;
+    const float* ph_offset_ptr;
+    const float* ph_scale_ptr;
+    int ph_mode, ph_weighted;
+};
+
+template <int BAND, int ROWS, int NT>
+__global__ void __launch_bounds__(NT) polar_rows_kernel(const PolarRowsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WPR = (NT / 32) / ROWS;              // warps per row
+    constexpr int NF = ROWS < 4 ? ROWS : 4;
+    constexpr int U = 17;                              // 32 * WPR * U >= n_bins (checked by the launcher)
+    constexpr int RING = ROWS + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wrow = warp / WPR, wsub = warp % WPR;
+    const int stride = (p.n_bins + 3) & ~3;
+    float* val = reinterpret_cast<float*>(smem_raw);
+    float* phs = val + (size_t)ROWS * stride;          // ring of ROWS + 1 raw-phase rows
+    unsigned char* bandmem = reinterpret_cast<unsigned char*>(phs + (size_t)RING * stride);
+    int32_t* smeta = reinterpret_cast<int32_t*>(bandmem);
+    float* scoef = reinterpret_cast<float*>(bandmem + p.ep.band_bytes_meta);
+    if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
+    const EpiArgs ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef,
+                                     p.offset_ptr, p.scale_ptr);
+    const float ph_off = p.ph_offset_ptr ? __ldg(p.ph_offset_ptr) : 0.f;
+    const float ph_inv = p.ph_scale_ptr ? 1.0f / __ldg(p.ph_scale_ptr) : 1.0f;
+    const bool ph_if = p.ph_mode == ACIDS_PHASE_IF;
+    const int T = p.n_frames;
+    const int rs = (int)p.out_row_stride;
+    const int df = p.ep.drop_first, n_keep = p.n_bins - df;
+    // contiguous run of row tiles
+    const int64_t tiles = (p.rows + ROWS - 1) / ROWS;
+    const int64_t i0 = tiles * blockIdx.x / gridDim.x, i1 = tiles * (blockIdx.x + 1) / gridDim.x;
+    if (i0 >= i1) return;
+    int64_t r0 = i0 * ROWS;
+    int t_first = (int)(r0 % T);                        // frame index of the tile's first row (advanced incrementally)
+    int base = 0;                                       // ring slot of the row preceding the tile
+    if (ph_if && t_first != 0) {
+        // the phase of the row before the run (same clip): recomputed once per CTA
+        const float2* __restrict__ row = p.X + (r0 - 1) * p.n_bins;
+        for (int k = threadIdx.x; k < p.n_bins; k += NT) {
+            const float2 a = __ldg(row + k);
+            phs[k] = fast_atan2f(a.y, a.x);
+        }
+    }
+    __syncthreads();
+    const int kl = lane + 32 * wsub;                    // this lane's bins: kl + 32 * WPR * j
+    float2 a[U];
+    auto issue = [&](int64_t rr0) {
+        const int64_t r = rr0 + wrow;
+        const float2* __restrict__ row = p.X + r * p.n_bins + kl;
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            a[j] = (r < p.rows && kl + 32 * WPR * j < p.n_bins) ? ldg_stream2(row + 32 * WPR * j) : make_float2(0.f, 0.f);
+    };
+    issue(r0);
+    for (int64_t i = i0; i < i1; ++i, r0 += ROWS) {
+        {
+            int slot = base + 1 + wrow;
+            if (slot >= RING) slot -= RING;
+            float* __restrict__ vrow = val + wrow * stride;
+            float* __restrict__ prow = phs + slot * stride;
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+                if (kl + 32 * WPR * j < p.n_bins) {
+                    vrow[kl + 32 * WPR * j] = fast_sqrt(a[j].x * a[j].x + a[j].y * a[j].y);
+                    prow[kl + 32 * WPR * j] = fast_atan2f(a[j].y, a[j].x);
+                }
+        }
+        __syncthreads();
+        if (i + 1 < i1) issue(r0 + ROWS);
+        const int n_valid = (int)min((int64_t)ROWS, p.rows - r0);
+        // magnitude rows: banded projection -> contrast -> normalise
+#pragma unroll 1
+        for (int g0 = 0; g0 < ROWS && g0 < n_valid; g0 += NF)
+            epilogue_dispatch<NT, NF, -1, BAND, false>(p.ep.contrast, val + g0 * stride, stride, threadIdx.x, ea,
+                                                       p.out + (r0 + g0) * p.out_row_stride, rs, 1, n_valid - g0);
+        // phase rows (spectral_repr.py:270-278 raw; :319-323 + :352-356 forward-difference IF, weighting, normalisation)
+        int t = t_first;
+#pragma unroll 1
+        for (int g0 = 0; g0 < n_valid; ++g0) {
+            int sc = base + 1 + g0, sp = base + g0;
+            if (sc >= RING) sc -= RING;
+            if (sp >= RING) sp -= RING;
+            const float* __restrict__ cur = phs + sc * stride + df;
+            const float* __restrict__ prv = phs + sp * stride + df;
+            float* __restrict__ o = p.ph_out + (r0 + g0) * p.ph_row_stride;
+            const bool diff = ph_if && t > 0;
+            const float s_pi = (ph_if && t < T - 1) ? ACIDS_INV_PI_F : 1.f;
+            const float wgt = p.ph_weighted ? if_weight(t, T) : 1.f;
+            for (int k = threadIdx.x; k < n_keep; k += NT) {
+                float v = cur[k];
+                if (diff) {
+                    const float d = v - prv[k];
+                    v = (d + unwrap_correction(d)) * 0.5f;
+                }
+                v = v * s_pi;
+                if (p.ph_weighted) v *= wgt;
+                stg_stream1(o + k, (v - ph_off) * ph_inv);
+            }
+            if (++t == T) t = 0;
+        }
+        t_first += ROWS;
+        while (t_first >= T) t_first -= T;
+        base += ROWS;
+        if (base >= RING) base -= RING;
+        __syncthreads();
+    }
+}
+
 // Magnitude.invert: m = contrast^-1(y * scale + offset) [zero padded] @ inverse band
 struct MagInvParams {
     const float* y;
@@ -597,6 +727,65 @@ extern "C" ACIDS_API int acids_polar_fwd(const float* X, int64_t B, int64_t n_fr
     const int64_t cols = B * n_bins;
     pick_phase_kernel(mode, if_method, p.weighted, contrast)<<<(unsigned)((cols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("polar_fwd");
+    return ACIDS_OK;
+}
+
+extern "C" ACIDS_API int acids_polar_rows_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, acids_band band, int contrast,
+                                    float eps, const float* mag_offset, const float* mag_scale, int phase_mode, int if_method,
+                                    int weighted, const float* ph_offset, const float* ph_scale, int drop_first, float* mag_out,
+                                    int64_t mag_row_stride, float* ph_out, int64_t ph_row_stride, void* stream) {
+    ACIDS_REQUIRE(X && mag_out && ph_out, ACIDS_EINVAL, "polar_rows_fwd: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 1 && n_frames < (1LL << 31) && n_bins > 0 && n_bins < 65536, ACIDS_EINVAL, "polar_rows_fwd: bad sizes");
+    ACIDS_REQUIRE(contrast >= 0 && contrast <= 3, ACIDS_EINVAL, "unknown contrast id %d", contrast);
+    ACIDS_REQUIRE(drop_first == 0 || drop_first == 1, ACIDS_EINVAL, "drop_first must be 0 or 1");
+    // the phase modes that need no scan over the frames; everything else stays on acids_mag_epilogue + acids_phase_fwd
+    ACIDS_REQUIRE(phase_mode == ACIDS_PHASE_RAW || (phase_mode == ACIDS_PHASE_IF && if_method == ACIDS_IF_FORWARD), ACIDS_ENOTSUP,
+                  "polar_rows_fwd: only the raw phase and the forward-difference IF are fused (mode %d, method %d)", phase_mode, if_method);
+    ACIDS_REQUIRE(n_bins <= 4352, ACIDS_ENOTSUP, "polar_rows_fwd: rows of %d bins do not fit the row-tile kernel (max 4352)", n_bins);
+    int rc = check_band(band);
+    if (rc) return rc;
+    if (B == 0) return ACIDS_OK;
+    PolarRowsParams p{};
+    p.X = reinterpret_cast<const float2*>(X); p.rows = B * n_frames; p.n_frames = (int)n_frames; p.n_bins = n_bins;
+    // (rows per iteration, threads): a lane's share of a row must fit the 17 prefetch registers.  Rows of 1089 .. 2176 bins run
+    // 2-row tiles in 256-thread CTAs (3 CTAs / SM) rather than mag_epilogue's 4 rows x 512 threads: the arctangents make a
+    // 512-thread CTA need 128 registers, i.e. ONE CTA per SM whose phases (stage, project, emit) cannot overlap (1.22 vs ... ms)
+#ifndef ACIDS_POLAR_ROWS_MID
+#define ACIDS_POLAR_ROWS_MID 2
+#endif
+    const int threads = (n_bins > 2176 || (n_bins > 1088 && ACIDS_POLAR_ROWS_MID == 4)) ? 512 : 256;
+    const int rows_per_iter = n_bins <= 544 ? 8 : (n_bins <= 1088 ? 4 : (n_bins <= 2176 ? ACIDS_POLAR_ROWS_MID : 2));
+    const size_t stride = (size_t)((n_bins + 3) & ~3);
+    const size_t rows_bytes = (size_t)(2 * rows_per_iter + 1) * stride * sizeof(float);
+    rc = fill_epilogue(p.ep, band, n_bins, contrast, eps, drop_first, rows_bytes <= 80 * 1024 ? 40 * 1024 : 24 * 1024);
+    if (rc) return rc;
+    ACIDS_REQUIRE(p.ep.n_cols == n_bins, ACIDS_EINVAL, "stack expects each tensor to be equal size, but got [%d] and [%d] bins",
+                  p.ep.n_cols - drop_first, n_bins - drop_first);
+    p.offset_ptr = mag_offset; p.scale_ptr = mag_scale; p.out = mag_out; p.out_row_stride = mag_row_stride;
+    p.ph_out = ph_out; p.ph_row_stride = ph_row_stride; p.ph_offset_ptr = ph_offset; p.ph_scale_ptr = ph_scale;
+    p.ph_mode = phase_mode; p.ph_weighted = phase_mode == ACIDS_PHASE_IF ? weighted : 0;
+    const size_t smem = rows_bytes + p.ep.band_bytes_meta + p.ep.band_bytes_coef;
+    const int bsel = !band.meta ? BAND_NONE : (p.ep.band_bytes_meta > 0 ? BAND_SMEM : BAND_GLOBAL);
+    void (*kern)(const PolarRowsParams) = nullptr;
+#define ACIDS_PRK(R, NT)                                                                                      \
+    kern = bsel == BAND_NONE ? polar_rows_kernel<BAND_NONE, R, NT>                                            \
+                             : (bsel == BAND_SMEM ? polar_rows_kernel<BAND_SMEM, R, NT> : polar_rows_kernel<BAND_GLOBAL, R, NT>)
+    if (rows_per_iter == 8) { ACIDS_PRK(8, 256); }
+    else if (threads == 256 && rows_per_iter == 4) { ACIDS_PRK(4, 256); }
+    else if (threads == 256) { ACIDS_PRK(2, 256); }
+    else if (rows_per_iter == 4) { ACIDS_PRK(4, 512); }
+    else { ACIDS_PRK(2, 512); }
+#undef ACIDS_PRK
+    ACIDS_REQUIRE(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)) == cudaSuccess,
+                  ACIDS_ECUDA, "polar_rows_fwd: cannot reserve %zu B of shared memory", smem);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem);
+    if (nb < 1) nb = 1;
+    const int64_t tiles = (p.rows + rows_per_iter - 1) / rows_per_iter;
+    int64_t grid = (int64_t)num_sms() * nb;
+    if (grid > tiles) grid = tiles;
+    kern<<<(unsigned)grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    ACIDS_CHECK_LAUNCH("polar_rows_fwd");
     return ACIDS_OK;
 }
 

@@ -315,8 +315,19 @@ Tensor polar_fwd(const Tensor& X, const OptTensor& band_meta, const OptTensor& b
         const int64_t n_mag = band.b.n_out - (drop_first ? 1 : 0);
         TORCH_CHECK(n_mag == n_ph, "stack expects each tensor to be equal size, but got [", n_mag, "] and [", n_ph, "] bins");
         out = at::empty({B, T, 2, n_ph}, f32(Xf));
-        mag_epilogue_into(Xf.reshape({B * T, F}), band, contrast, eps, mag_offset, mag_scale, drop_first, out, 0, 2);
-        phase_fwd_into(Xf, phase_mode, method, weighted, ph_offset, ph_scale, drop_first, out, 1, 2);
+        // where the row-tile kernel pays on B200 (ops.polar_rows_pays): raw phase, rows of 545 .. 4352 bins
+        if (phase_mode == ACIDS_PHASE_RAW && F > 544 && F <= 4352) {
+            // mel bank + raw phase: one row-tile kernel, one read of the spectrum
+            OptTensor mo = scalar(mag_offset, Xf.device()), ms = scalar(mag_scale, Xf.device());
+            OptTensor po = scalar(ph_offset, Xf.device()), ps = scalar(ph_scale, Xf.device());
+            if (out.numel())
+                check(acids_polar_rows_fwd(reinterpret_cast<const float*>(Xf.data_ptr()), B, T, (int)F, band.b, (int)contrast, (float)eps, fptr(mo),
+                                           fptr(ms), (int)phase_mode, (int)method, weighted ? 1 : 0, fptr(po), fptr(ps), drop_first ? 1 : 0,
+                                           out.data_ptr<float>(), 2 * n_ph, out.data_ptr<float>() + n_ph, 2 * n_ph, stream_of(Xf)));
+        } else {
+            mag_epilogue_into(Xf.reshape({B * T, F}), band, contrast, eps, mag_offset, mag_scale, drop_first, out, 0, 2);
+            phase_fwd_into(Xf, phase_mode, method, weighted, ph_offset, ph_scale, drop_first, out, 1, 2);
+        }
     }
     return ret(out.reshape(with_batch(batch, {T, 2, n_ph})), X);
 }

@@ -458,6 +458,45 @@ def polar_fwd(X, contrast, eps, mag_offset, mag_scale, phase_mode: int, method="
     return _ret(out.reshape(tuple(batch) + (T, 2, n_keep)), X)
 
 
+POLAR_ROWS_MAX_BINS = 4352
+
+
+def polar_rows_pays(phase_mode: int, n_bins: int) -> bool:
+    """Where acids_polar_rows_fwd beats acids_mag_epilogue + acids_phase_fwd on B200 (tools/polar_rows_probe.py):
+    the raw phase on rows of more than 544 bins (1.83 vs 2.04 ms at n_fft 1024 ... 0.46 vs 0.48 ms at 8192).  Both halves are
+    issue bound, not memory bound, so the forward-difference IF — an extra pass over the tile — is 3-13 % SLOWER fused
+    (0.96 vs 0.89 ms at n_fft 4096) and keeps the two kernels; the entry point supports it and the tests cover it."""
+    return phase_mode == PHASE_RAW and 544 < n_bins <= POLAR_ROWS_MAX_BINS
+
+
+def polar_rows_fwd(X, band: Optional[BandedMatrix], contrast, eps, mag_offset, mag_scale, phase_mode: int, method="forward",
+                   weighted=False, ph_offset=None, ph_scale=None, drop_first=False):
+    """Magnitude.forward (with its mel bank) and Phase / forward-difference IF of X [..., T, F] from ONE read of the spectrum,
+    stacked -> float32 [..., T, 2, F - drop]  (spectral_repr.py:431-440); raw phase or IF `forward` only (`fusable_phase`)."""
+    lib = _lib.load()
+    Xd = _as_complex64(_dev(X)).resolve_conj()
+    if Xd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] spectrum)")
+    Xf, batch = _flat_batch(Xd, 2)
+    B, T, F = Xf.shape
+    if band is not None and band.n_in != F:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (B * T, F, band.n_in, band.n_out))
+    n_keep = F - int(drop_first)
+    n_mag = (band.n_out if band is not None else F) - int(drop_first)
+    if n_mag != n_keep:
+        raise RuntimeError("stack expects each tensor to be equal size, but got [%d] and [%d] bins" % (n_mag, n_keep))
+    dev = Xf.device
+    out = torch.empty((B, T, 2, n_keep), dtype=torch.float32, device=dev)
+    flat = out.view(-1)
+    mo, ms = _scalar(mag_offset, dev), _scalar(mag_scale, dev)
+    po, ps = _scalar(ph_offset, dev), _scalar(ph_scale, dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_polar_rows_fwd, _ptr(Xf), B, T, F, _band(band, dev), _cid(contrast), float(eps), _ptr(mo), _ptr(ms),
+             int(phase_mode), _mid(method), int(bool(weighted)), _ptr(po), _ptr(ps), int(drop_first), _ptr(flat), 2 * n_keep,
+             _ptr(flat[n_keep:]), 2 * n_keep, _stream(dev))
+    return _ret(out.reshape(tuple(batch) + (T, 2, n_keep)), X)
+
+
 def phase_inv(y, mode: int, method="forward", offset=None, scale=None, pad_last=False):
     """Phase.invert / IF.invert: y [..., T, n_in] -> phase [..., T, n_in + pad]  (spectral_repr.py:46-53, :359-375)."""
     lib = _lib.load()

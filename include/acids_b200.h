@@ -176,6 +176,16 @@ ACIDS_API int acids_phase_fwd(const float* X, int64_t B, int64_t n_frames, int n
                     int drop_first, float* out, int64_t out_clip_stride, int64_t out_row_stride,
                     void* stream);
 
+/* Polar / PolarIF on an existing spectrum WITH a mel bank, one read of X (spectral_repr.py:431-440: magnitude(x), phase(x),
+ * stack): row-tile kernel, the magnitude rows go through the banded projection while the raw phase of the same rows is
+ * kept in a second shared-memory tile; phase_mode ACIDS_PHASE_RAW, or ACIDS_PHASE_IF with ACIDS_IF_FORWARD (the wrapped
+ * difference of consecutive raw phases); other modes and rows longer than 4352 bins return ACIDS_ENOTSUP (use
+ * acids_mag_epilogue + acids_phase_fwd).  Row (b, t) of both outputs is at base + (b * n_frames + t) * row_stride.     */
+ACIDS_API int acids_polar_rows_fwd(const float* X, int64_t B, int64_t n_frames, int n_bins, acids_band band, int contrast,
+                         float eps, const float* mag_offset, const float* mag_scale, int phase_mode, int if_method,
+                         int weighted, const float* ph_offset, const float* ph_scale, int drop_first, float* mag_out,
+                         int64_t mag_row_stride, float* ph_out, int64_t ph_row_stride, void* stream);
+
 /* SpectralRepresentation.forward for Polar / PolarIF without a mel bank (spectral_repr.py:434-440: magnitude(x),
  * phase(x), stack): acids_mag_epilogue (band-less) and acids_phase_fwd from ONE read of the spectrum.  mag_out /
  * ph_out rows like (2); both may point into the same stacked tensor.                                       */

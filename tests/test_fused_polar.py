@@ -268,3 +268,51 @@ def test_midside_folded_into_the_stft(T):
             assert_parity(host(torch.view_as_real(got)), host(torch.view_as_real(want)), 1e-5, "midside+stft %d pad_mid=%s" % (n_fft, pad_mid))
     with pytest.raises(RuntimeError):
         torch.ops.acids_b200.midside_stft_fwd(x[:, 0], T.STFT().cuda().window, 1024, 256, 1)      # not stereo
+
+
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (512, 128), (1024, 256), (2048, 512), (4096, 1024), (8192, 2048)])
+@pytest.mark.parametrize("kind", ["polar", "polarif", "polarif_weighted", "polarif_drop"])
+def test_polar_rows_against_the_two_kernels(T, n_fft, hop, kind):
+    """acids_polar_rows_fwd (mel bank + raw phase / forward IF from ONE read of the spectrum; what Polar.forward runs on long rows)
+    against acids_mag_epilogue + acids_phase_fwd writing the two slots.  Enough clips that the persistent grid hands most
+    CTAs a run starting inside a clip (the recomputed carry row), odd frame counts so that row tiles straddle clips."""
+    from acids_transforms_b200 import ops
+    torch.manual_seed(n_fft + len(kind))
+    B, L = (300, 5 * n_fft + 3 * hop) if n_fft <= 1024 else (37, 5 * n_fft + hop)
+    x = torch.randn(B, L, device="cuda")
+    keep = kind != "polarif_drop"
+    margs = {"mode": "bipolar", "n_fft": n_fft}
+    if kind == "polar":
+        rep = T.Polar(magnitude_args=margs, keep_nyquist=keep).cuda()
+    else:
+        rep = T.PolarIF(magnitude_args=margs, phase_args={"mode": "bipolar", "weighted": kind.endswith("weighted")}, keep_nyquist=keep).cuda()
+    st = T.STFT(n_fft=n_fft, hop_length=hop).cuda()
+    X = st(x)
+    rep.scale_data(X[:8])
+    mag, ph = rep.magnitude, rep.phase
+
+    def rows(Xi):      # the entry point itself: the modules only dispatch to it where it is the faster path (ops.polar_rows_pays)
+        return ops.polar_rows_fwd(Xi, ops.as_band(mag.band_meta(), mag.band_coef()), mag.contrast_mode, mag._eps, mag.norm.get_offset(),
+                                  mag.norm.get_scale(), rep._phase_mode(), rep._phase_method(), rep._phase_weighted(), ph.norm.get_offset(),
+                                  ph.norm.get_scale(), not keep)
+
+    y = rows(X)
+    assert (kind == "polar" and n_fft >= 2048) == (type(rep).__name__ == "Polar" and ops.polar_rows_pays(rep._phase_mode(), n_fft // 2 + 1))
+    Fk = n_fft // 2 + 1 - (0 if keep else 1)
+    ref = torch.empty((B, X.shape[1], 2, Fk), device="cuda")
+    ops.mag_epilogue(X, ops.as_band(mag.band_meta(), mag.band_coef()), mag.contrast_mode, mag._eps, mag.norm.get_offset(), mag.norm.get_scale(),
+                     not keep, out=ref, out_slot=0, out_slots=2)
+    ops.phase_fwd(X, rep._phase_mode(), rep._phase_method(), rep._phase_weighted(), ph.norm.get_offset(), ph.norm.get_scale(), not keep,
+                  out=ref, out_slot=1, out_slots=2)
+    assert y.shape == ref.shape
+    assert_parity(host(y[..., 0, :]), host(ref[..., 0, :]), 1e-6, "magnitude slot")
+    Xh = host(X)[..., (0 if keep else 1):]
+    if kind == "polar":
+        assert torch.equal(y[..., 1, :], ref[..., 1, :])                  # the same arctangent of the same bins
+        return
+    ok = if_mask(Xh) & ~wrap_ambiguous(host(ref[..., 1, :]), ph.norm, kind.endswith("weighted"))
+    assert ok.mean() > 0.9
+    assert_phase_close(np.where(ok, host(y[..., 1, :]), 0), np.where(ok, host(ref[..., 1, :]), 0), Xh, float(ph.norm.scale) * np.pi, True, "IF slot")
+    # position independence: a clip alone (its run starts at frame 0) equals the clip inside the batch, bit for bit
+    for b in (1, B // 2, B - 1):
+        assert torch.equal(rows(X[b:b + 1])[0], y[b])

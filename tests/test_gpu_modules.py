@@ -103,8 +103,11 @@ def test_polar_modules(T):
         assert_parity(np.where(ok, y[..., 1, :], 0), np.where(ok, g[tag + "_y"][..., 1, :], 0), REL, tag + " phase")
         p.magnitude.norm.offset, p.magnitude.norm.scale = cu(g[tag + "_mag_offset"]), cu(g[tag + "_mag_scale"])
         assert_parity(host(p.invert(cu(g[tag + "_y"]))), g[tag + "_inv"], REL, tag + " invert")
-        # the generic stack path (two kernels + torch.stack) equals the in-place stacked write
-        assert torch.equal(p._stacked_forward(X), p(X))
+        # the generic stack path (Magnitude kernel, Phase / IF kernel, torch.stack) against what p(X) runs (the same two kernels
+        # writing their slots, or the one-read row-tile kernel where it is faster)
+        ys, yp = host(p._stacked_forward(X)), host(p(X))
+        assert_parity(yp[..., 0, :], ys[..., 0, :], 1e-6, tag + " stacked mag")
+        assert_parity(np.where(ok, yp[..., 1, :], 0), np.where(ok, ys[..., 1, :], 0), REL, tag + " stacked phase")
 
 
 def test_mfcc_module(T):
