@@ -254,6 +254,9 @@ __device__ __forceinline__ float contrast_gain(int contrast) {
     return 1.0f;
 }
 
+#ifndef ACIDS_EPI_SNAKE
+#define ACIDS_EPI_SNAKE 1
+#endif
 // ---- the row-tile epilogue --------------------------------------------------------------------------------------
 // `val` (shared memory) holds the non-negative inputs (|X| or |X|^p) of NF consecutive rows, val_stride floats
 // apart.  NT threads produce output columns tid, tid + NT, ... of every row:
@@ -375,10 +378,7 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
                                               float* __restrict__ out0, int row_step, int col_step, int n_valid) {
     // out0: element (row 0, first output column) of the tile; rows are row_step floats apart, columns col_step
     // (TRANSPOSED: rows are adjacent, row_step is ignored; otherwise columns are adjacent, col_step is ignored)
-    // one running pointer per thread (row 0 of its current column) plus loop-invariant row offsets: the column loop
-    // carries no address arithmetic beyond one pointer increment
-    float* __restrict__ o = out0 + (TRANSPOSED ? (int64_t)tid * col_step : (int64_t)tid);
-    const int64_t o_step = TRANSPOSED ? (int64_t)NT * col_step : (int64_t)NT;
+    // one pointer per column (row 0) plus loop-invariant row offsets
     int64_t roff[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) roff[f] = TRANSPOSED ? (int64_t)f : (RS > 0 ? (int64_t)f * RS : (int64_t)f * row_step);
@@ -387,7 +387,15 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
         const int rem = ep.n_out % NT;
         if (rem * NF <= NT) n_main = ep.n_out - rem;
     }
-    for (int mo = tid; mo < n_main; mo += NT, o += o_step) {
+    // Odd sweeps hand the 32-column groups to the warps in REVERSE order: a bank whose tap count grows with the column index
+    // (mel: 1 ... 7 taps over the 16 groups of the 513-column bank) then gives every warp a similar total instead of loading
+    // the last warp with the widest group of every sweep (fused cfg-2 kernel 0.999 -> 0.982 ms).  ACIDS_EPI_SNAKE=0: plain order.
+    int sweep = 0;
+    for (int mo0 = tid; mo0 < n_main; mo0 += NT, ++sweep) {
+        int mo = mo0;
+        if (ACIDS_EPI_SNAKE && !TRANSPOSED && (sweep & 1) && (mo0 - tid) + NT <= n_main)       // full sweeps only
+            mo = (mo0 - tid) + 32 * (NT / 32 - 1 - (tid >> 5)) + (tid & 31);
+        float* __restrict__ o = out0 + (TRANSPOSED ? (int64_t)mo * col_step : (int64_t)mo);
         const int m = mo + ep.drop_first;
         float a[NF];
         if (BAND != BAND_NONE) {

@@ -499,8 +499,15 @@ struct FrameFFT {
                 const cf* t = tw + P::tw_off(PASS) + (b >> 1) * (R - 1);
                 if ((b & 1) == 0) {
                     const bool sp = PR::pi(tid, b >> 1) == 0;       // butterfly 0: unit twiddles
+#ifdef ACIDS_FWD_PRED_SP      // tuning experiment: predicated multiply instead of multiply + select
+                    if (!sp) {
+#pragma unroll
+                        for (int r = 1; r < R; ++r) v[b * R + r] = cmul(v[b * R + r], t[r - 1]);
+                    }
+#else
 #pragma unroll
                     for (int r = 1; r < R; ++r) v[b * R + r] = csel(sp, v[b * R + r], cmul(v[b * R + r], t[r - 1]));
+#endif
                     Dft<R, INV>::run(v + b * R);
                 } else {
 #pragma unroll
