@@ -208,6 +208,8 @@ struct EpiParams {
     int drop_first;
     int band_bytes_meta;     // bytes of meta / coef to stage in shared memory (0: read from global memory)
     int band_bytes_coef;
+    int coef_floats;         // coefficients actually present in `coef` (band_bytes_coef may reserve more, see split_reserve)
+    int split_reserve;       // the shared-memory coefficient area was enlarged for the tap-split layout (transposed launches)
 };
 
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -277,6 +279,7 @@ struct EpiArgs {
     float gain;              // contrast_gain / scale
     float bias;              // -offset / scale
     float eps;
+    int split;               // BAND_SMEM, transposed output: tap-split layout (epilogue_split), see stage_band_split
 };
 
 // K taps of one column for NF rows: the K coefficients are loaded once and reused for every row
@@ -367,6 +370,60 @@ __device__ __forceinline__ float band_single(const float* __restrict__ vrow, con
     return acc;
 }
 
+// ---- tap-split epilogue for wide bands (the 1025 -> 128 MFCC mel bank: 4 / 10 / 23 / 55 taps over its four 32-column groups) ----
+// With one column per lane a warp's work is its group's tap count, and the warp holding the widest group sets the pace of the
+// CTA (ncu, cfg 3: 1.9 barrier-stall cycles per issue).  Here a warp takes 8 columns at a time and FOUR lanes share a column,
+// each a quarter of its taps; two shuffle-adds combine the partial sums (fixed order: deterministic).  Every warp then
+// walks ceil(cnt / 4) taps of every group.  The coefficients are re-packed once per CTA so that the 32 lanes of a step read
+// 32 consecutive floats; rec.y of a column holds (taps << 16 | float offset of its group's split block).
+// Measured on B200 (cfg 3, 512 x 10 s): 1.773 ms against 1.644 ms for one column per lane — with three CTAs per SM the
+// other CTAs fill the SM while a CTA's wide-group warp finishes, so the imbalance costs less than the shuffles and index
+// arithmetic of the split.  Correct (the whole GPU suite passes with it on) but opt-in: -DACIDS_EPI_SPLIT=1.
+#ifndef ACIDS_EPI_SPLIT
+#define ACIDS_EPI_SPLIT 0
+#endif
+#ifndef ACIDS_SPLIT_MIN_TAPS
+#define ACIDS_SPLIT_MIN_TAPS 12
+#endif
+template <int NT, int NF, int CONTRAST>
+__device__ __forceinline__ void epilogue_split(const float* __restrict__ val, int val_stride, int tid, const EpiArgs& ep,
+                                               float* __restrict__ out0, int col_step, int n_valid) {
+    constexpr int NW = NT / 32;
+    const int lane = tid & 31, warp = tid >> 5, j = lane & 7, q = lane >> 3;
+    const int n_chunks = (ep.n_out + 7) >> 3;
+    for (int c = warp; c < n_chunks; c += NW) {
+        const int col = 8 * c + j;
+        const int colc = min(col, ep.n_out - 1) + ep.drop_first;
+        const int2 rec = reinterpret_cast<const int2*>(ep.meta)[colc];
+        const int cnt = (int)((unsigned)rec.y >> 16);
+        const int kq = (cnt + 3) >> 2;
+        const float* __restrict__ cs = ep.coef + (rec.y & 0xffff) + (c & 3) * kq * 32 + lane;       // chunk c & 3 of its group (drop_first == 0)
+        const float* __restrict__ v = val + rec.x;
+        const int u0 = q * kq, ulast = cnt - 1;
+        float acc[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+        for (int up = 0; up < kq; ++up) {
+            const float w = cs[up * 32];                       // zero beyond the column's taps
+            const int u = min(u0 + up, ulast);                  // keep the (unused) read inside the window
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] = fmaf(v[f * val_stride + u], w, acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 8);
+            acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 16);
+        }
+        // the four lanes of a column share out its rows
+        if (col < ep.n_out) {
+            float* __restrict__ o = out0 + (int64_t)col * col_step;
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                if ((f & 3) == q && f < n_valid) stg_stream1(o + f, fmaf(contrast_core<CONTRAST>(acc[f], ep.eps), ep.gain, ep.bias));
+        }
+    }
+}
+
 // FULL: all NF rows exist (no row predicates); otherwise rows f >= n_valid are skipped.
 // RS > 0: the output row step is known at compile time (the common contiguous [.., T, F] output): the NF stores of a
 // column are one pointer plus immediates instead of NF 64-bit additions.
@@ -379,6 +436,12 @@ __device__ __forceinline__ void epilogue_tile(const float* __restrict__ val, int
     // out0: element (row 0, first output column) of the tile; rows are row_step floats apart, columns col_step
     // (TRANSPOSED: rows are adjacent, row_step is ignored; otherwise columns are adjacent, col_step is ignored)
     // one pointer per column (row 0) plus loop-invariant row offsets
+    if constexpr (TRANSPOSED && BAND == BAND_SMEM) {
+        if (ep.split) {
+            epilogue_split<NT, NF, CONTRAST>(val, val_stride, tid, ep, out0, col_step, FULL ? NF : n_valid);
+            return;
+        }
+    }
     int64_t roff[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) roff[f] = TRANSPOSED ? (int64_t)f : (RS > 0 ? (int64_t)f * RS : (int64_t)f * row_step);
@@ -453,7 +516,36 @@ __device__ __forceinline__ void stage_band(const EpiParams& ep, int32_t* srec, f
         const int cnt = __ldg(ep.meta + 2 * (m >> 5)), base = __ldg(ep.meta + 2 * (m >> 5) + 1);
         reinterpret_cast<int2*>(srec)[m] = make_int2(__ldg(ep.meta + 2 * n_groups + m), (cnt << 16) | ((base << 5) + (m & 31)));
     }
-    for (int i = threadIdx.x; i < ep.band_bytes_coef / 4; i += blockDim.x) scoef[i] = __ldg(ep.coef + i);
+    for (int i = threadIdx.x; i < ep.coef_floats; i += blockDim.x) scoef[i] = __ldg(ep.coef + i);
+}
+
+// does the bank want the tap-split epilogue?  (uniform over the CTA; only where the launcher reserved the room)
+__device__ __forceinline__ bool band_wants_split(const EpiParams& ep) {
+    if (!ACIDS_EPI_SPLIT || !ep.split_reserve || ep.drop_first != 0) return false;
+    const int n_groups = (ep.n_cols + 31) >> 5;
+    int mx = 0;
+    for (int g = 0; g < n_groups; ++g) mx = max(mx, __ldg(ep.meta + 2 * g));
+    return mx >= ACIDS_SPLIT_MIN_TAPS;
+}
+
+// the same, tap-split layout (epilogue_split): records carry (taps << 16 | offset of the group's split block); the block of
+// group g holds, for each of its four 8-column chunks k and each step u', the 32 lanes' coefficients
+//   lane (q = lane >> 3, j = lane & 7) -> coefficient q * kq + u' of column 32 g + 8 k + j   (zero beyond the column's taps)
+__device__ __forceinline__ void stage_band_split(const EpiParams& ep, int32_t* srec, float* scoef) {
+    const int n_groups = (ep.n_cols + 31) >> 5;
+    int gbase = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int cnt = __ldg(ep.meta + 2 * g), base = __ldg(ep.meta + 2 * g + 1);
+        const int kq = (cnt + 3) >> 2, block = 4 * kq * 32;
+        for (int m = 32 * g + threadIdx.x; m < min(32 * g + 32, ep.n_cols); m += blockDim.x)
+            reinterpret_cast<int2*>(srec)[m] = make_int2(__ldg(ep.meta + 2 * n_groups + m), (cnt << 16) | gbase);
+        for (int i = threadIdx.x; i < block; i += blockDim.x) {
+            const int k = i / (kq * 32), r = i - k * kq * 32, up = r >> 5, ln = r & 31;
+            const int u = (ln >> 3) * kq + up;
+            scoef[gbase + i] = u < cnt ? __ldg(ep.coef + (((base + u) << 5) + 8 * k + (ln & 7))) : 0.f;
+        }
+        gbase += block;
+    }
 }
 
 __device__ __forceinline__ EpiArgs make_epi_args(const EpiParams& ep, const int32_t* meta, const float* coef, const float* offset,
@@ -471,6 +563,7 @@ __device__ __forceinline__ EpiArgs make_epi_args(const EpiParams& ep, const int3
     a.gain = inv * contrast_gain(ep.contrast);
     a.bias = -off * inv;
     a.eps = ep.eps;
+    a.split = 0;
     return a;
 }
 
@@ -480,6 +573,8 @@ static inline void band_smem_plan(const acids_band& band, int64_t coef_floats, s
     if (!band.meta) return;
     // in shared memory: one 8-byte record per column + the coefficients (indexable with 16 bits, see EpiArgs)
     const size_t need = (size_t)band.n_out * 8 + (size_t)coef_floats * 4;
+    ep.coef_floats = (int)coef_floats;
+    ep.split_reserve = 0;
     if (need <= budget && coef_floats < 65536 && band.n_out < 65536) {
         ep.band_bytes_meta = band.n_out * 8;
         ep.band_bytes_coef = (int)(coef_floats * 4);

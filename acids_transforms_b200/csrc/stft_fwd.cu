@@ -140,6 +140,16 @@ extern "C" ACIDS_API int acids_melspec_fwd(const float* x, int64_t B, int64_t L,
     ACIDS_REQUIRE(out, ACIDS_EINVAL, "melspec_fwd: NULL output");
     ACIDS_REQUIRE((int64_t)mel.n_out * n_frames < ((int64_t)1 << 31), ACIDS_ENOTSUP, "melspec_fwd: more than 2^31 output elements per clip");
     p.offset_ptr = offset; p.scale_ptr = scale;
+    // the tap-split epilogue (common.cuh: epilogue_split) re-packs the coefficients with every group's tap count rounded up to a
+    // multiple of 4: reserve 3 x 32 floats per group on top of the coefficients when the bank lives in shared memory
+    if (ACIDS_EPI_SPLIT && p.ep.band_bytes_meta > 0) {
+        const int n_groups = (mel.n_out + 31) / 32;
+        const size_t grown = (size_t)p.ep.band_bytes_coef + (size_t)n_groups * 96 * sizeof(float);
+        if ((size_t)p.ep.band_bytes_meta + grown <= kBandSmemBudget + 4096 && grown / 4 < 65536) {
+            p.ep.band_bytes_coef = (int)grown;
+            p.ep.split_reserve = 1;
+        }
+    }
     // frequency-major output [B, n_mels, n_frames] like torchaudio (mel.py:70)
     p.out = out; p.out_clip_stride = (int64_t)mel.n_out * n_frames; p.out_row_stride = 1; p.out_col_stride = n_frames;
     p.power = power;

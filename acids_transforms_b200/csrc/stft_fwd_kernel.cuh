@@ -150,9 +150,15 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
         unsigned char* bandmem = smem_raw + C::exch_bytes() + C::win_bytes();
         int32_t* smeta = reinterpret_cast<int32_t*>(bandmem);
         float* scoef = reinterpret_cast<float*>(bandmem + p.ep.band_bytes_meta);
-        if (BAND == BAND_SMEM) stage_band(p.ep, smeta, scoef);
+        bool split = false;
+        if (BAND == BAND_SMEM) {
+            split = TRANSPOSED && band_wants_split(p.ep);
+            if (split) stage_band_split(p.ep, smeta, scoef);
+            else stage_band(p.ep, smeta, scoef);
+        }
         ea = make_epi_args(p.ep, BAND == BAND_SMEM ? smeta : p.ep.meta, BAND == BAND_SMEM ? scoef : p.ep.coef, p.offset_ptr,
                            p.scale_ptr);
+        ea.split = split ? 1 : 0;
         // |X| rows of a unit: in the frames' exchange buffers (RIE), or double buffered so that the next unit's FFT never
         // waits for the slowest epilogue thread
         vrows = RIE ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(bandmem + (BAND == BAND_SMEM ? p.band_smem_bytes : 0));
