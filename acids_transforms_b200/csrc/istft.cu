@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(InvCfg<P>::THREADS, InvCfg<P>::MINB) istft_ola
 #ifndef ACIDS_INV_T16_PREFETCH
 #define ACIDS_INV_T16_PREFETCH 1
 #endif
-    constexpr bool PREFETCH = !RX || ACIDS_INV_T16_PREFETCH;      // next round's spectrum rows into registers before the gather
+#ifndef ACIDS_INV_PREFETCH
+#define ACIDS_INV_PREFETCH 1
+#endif
+    constexpr bool PREFETCH = RX ? ACIDS_INV_T16_PREFETCH : ACIDS_INV_PREFETCH;      // next round's spectrum rows into registers before the gather
     cf* s = reinterpret_cast<cf*>(smem_raw) + (size_t)g * P::SMEM_CF;      // !RX: the group's exchange buffer
     constexpr size_t kExch = InvCfg<P>::exch_bytes();                       // keeps the ring 16-byte aligned
     float* ring = reinterpret_cast<float*>(smem_raw + kExch);
