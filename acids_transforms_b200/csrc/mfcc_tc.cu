@@ -74,18 +74,24 @@ struct Params {
     float* out;              // [B, n_mfcc, T]
 };
 
-constexpr int THREADS = 512;      // 16 warps: operand fill and dB conversion are the bulk of the work
+constexpr int THREADS = 256;      // 8 warps; two CTAs per SM (112 KB each), so one CTA's drain overlaps the other's operand fill
+constexpr int KC = 32;            // mel bands per pipeline stage: the A operand is filled and multiplied in K chunks of 32
 
-__global__ void __launch_bounds__(THREADS, 1) mfcc_dct_tc_kernel(const Params p) {
+// Round 2: the kernel was one CTA per SM walking fill(128 KB) -> MMA -> drain strictly in turn (tensor pipe 8.6 % active, the
+// SM idle during every barrier).  Now the A operand lives in a ring of two 32-band chunk buffers (2 x 32 KB for hi + lo): while
+// the tensor core multiplies chunk c (12 tcgen05.mma, committed to the chunk buffer's mbarrier) the warps convert and store
+// chunk c + 1; the accumulator in TMEM sums over the chunks.  112 KB of shared memory per CTA instead of 180 KB -> two CTAs
+// per SM, whose fill and drain phases interleave.
+__global__ void __launch_bounds__(THREADS, 2) mfcc_dct_tc_kernel(const Params p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int K = p.K;
-    const uint32_t a_bytes = (uint32_t)TM * K * 4, b_bytes = (uint32_t)NP * K * 4;
-    unsigned char* a_hi = smem;
-    unsigned char* a_lo = a_hi + a_bytes;
-    unsigned char* b_hi = a_lo + a_bytes;
+    const uint32_t a_chunk = (uint32_t)TM * KC * 4, b_bytes = (uint32_t)NP * K * 4;
+    unsigned char* a_hi = smem;                         // [2 stages][TM x KC]
+    unsigned char* a_lo = a_hi + 2 * a_chunk;
+    unsigned char* b_hi = a_lo + 2 * a_chunk;
     unsigned char* b_lo = b_hi + b_bytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + b_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + b_bytes);      // [0], [1]: chunk buffer free again; [2]: accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) {
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1) mfcc_dct_tc_kernel(const Params p)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1) : "memory");
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + i)), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // B operand: row n = coefficient, column k = mel band: DCT^T, zero rows for n >= n_mfcc
@@ -105,45 +111,82 @@ __global__ void __launch_bounds__(THREADS, 1) mfcc_dct_tc_kernel(const Params p)
         *reinterpret_cast<float*>(b_hi + off) = hi;
         *reinterpret_cast<float*>(b_lo + off) = lo;
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t idesc = make_idesc();
-    const uint32_t sbo = (uint32_t)(K >> 2) * 128;
-    uint32_t phase = 0;
-    const int cores_k = K >> 2;                       // core matrices along K
-    const int n_cores = (TM / 8) * cores_k;           // 8 frames x 4 mel bands each
+    const uint32_t sbo_a = (uint32_t)(KC >> 2) * 128, sbo_b = (uint32_t)(K >> 2) * 128;
+    const int n_chunks = (K + KC - 1) / KC;           // K is a multiple of 8: the last chunk may hold 8, 16 or 24 bands
+    uint32_t ph_buf[2] = {0, 0}, ph_done = 0;         // mbarrier phases
+    uint32_t used[2] = {0, 0};                        // has the stage's mbarrier an outstanding commit?
+    auto wait = [&](uint64_t* bar, uint32_t parity) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(parity)
+                : "memory");
+        }
+    };
 
     const int64_t tiles_per_clip = (p.T + TM - 1) / TM;
-    for (int64_t tile = blockIdx.x; tile < p.B * tiles_per_clip; tile += gridDim.x) {
+    const int64_t n_tiles = p.B * tiles_per_clip;
+    int stage = 0;
+    constexpr int cores_k = KC >> 2;                      // 8 core matrices along K per chunk
+    constexpr int steps = (TM / 32) * cores_k;            // 32
+    constexpr int NW = THREADS / 32, U = 4;               // 4 steps (16 independent loads) in flight per warp
+    static_assert(steps == NW * U, "one pass of the warps covers a chunk");
+    // raw mel values of chunk kc of a tile, in fill order: per step a warp takes 32 frames x 4 bands (four coalesced 128-byte
+    // loads along the frame axis).  Issued one chunk AHEAD of their use (ncu on the first pipelined version: 4.6 long-scoreboard
+    // stall cycles per issue — the loads of a chunk were only issued after the previous chunk's barrier).
+    auto load_chunk = [&](int64_t tile, int kc, float (&v)[U][4]) {
+        const int64_t b = tile / tiles_per_clip;
+        const int64_t t0 = (tile - b * tiles_per_clip) * TM;
+        const float* src = p.mel + b * (int64_t)K * p.T;
+        const int kw = min(KC, K - kc * KC);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = warp + u * NW;
+            const int fb = c / cores_k, kb = c - fb * cores_k;      // frame block (32 frames), band block (4 bands)
+            const int64_t t = t0 + fb * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[u][j] = (t < p.T && kb * 4 < kw) ? __ldg(src + (int64_t)(kc * KC + kb * 4 + j) * p.T + t) : 1.0f;
+        }
+    };
+    float v[U][4];
+    if ((int64_t)blockIdx.x < n_tiles) load_chunk(blockIdx.x, 0, v);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t b = tile / tiles_per_clip;
         const int64_t t0 = (tile - b * tiles_per_clip) * TM;
         float floor_db = -FLT_MAX;
         if (p.top_db >= 0.f) floor_db = 10.0f * log10f(fmaxf(__ldg(p.gmax + b / p.clips_per_group), 1e-10f)) - p.top_db;
-        // A operand: row = frame, column = mel band.  Per step a warp takes 32 frames x 4 bands: four coalesced 128-byte
-        // loads along the frame axis; a lane then holds one 16-byte row of a core matrix (its frame, 4 bands), so the
-        // hi and lo parts go out as two conflict-free 128-bit shared-memory stores.
-        // dB through lg2.approx (2^-22 relative: 1e-5 dB, four orders below the parity budget on values of +-100 dB).
-        const float* src = p.mel + b * (int64_t)K * p.T;
-        const int steps = (TM / 32) * cores_k;
-        constexpr int NW = THREADS / 32, U = 4;      // U steps in flight per warp: 16 independent loads before the first use
-        for (int c0 = warp; c0 < steps; c0 += NW * U) {
-            float v[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int c = c0 + u * NW;
-                const int fb = c / cores_k, kc = c - fb * cores_k;      // frame block (32 frames), band block (4 bands)
-                const int64_t t = t0 + fb * 32 + lane;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[u][j] = (c < steps && t < p.T) ? __ldg(src + (int64_t)(kc * 4 + j) * p.T + t) : 1.0f;
+        for (int kc = 0; kc < n_chunks; ++kc, stage ^= 1) {
+            // the MMAs that read this stage two chunks ago must have completed before it is overwritten
+            if (used[stage]) {
+                wait(mbar + stage, ph_buf[stage]);
+                ph_buf[stage] ^= 1;
+                used[stage] = 0;
             }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // A chunk: row = frame, column = mel band kc * 32 + (0..31).  A lane holds one 16-byte row of a core matrix (its
+            // frame, 4 bands), so the hi and lo parts go out as two conflict-free 128-bit shared-memory stores.
+            // dB through lg2.approx (2^-22 relative: 1e-5 dB, four orders below the parity budget on values of +-100 dB).
+            unsigned char* ah = a_hi + stage * a_chunk;
+            unsigned char* al = a_lo + stage * a_chunk;
+            const int kw = min(KC, K - kc * KC);                  // bands in this chunk
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int c = c0 + u * NW;
-                if (c >= steps) break;
-                const int fb = c / cores_k, kc = c - fb * cores_k;
+                const int c = warp + u * NW;
+                const int fb = c / cores_k, kb = c - fb * cores_k;
                 const int r = fb * 32 + lane;
+                if (kb * 4 >= kw) continue;                       // beyond the last band: never read by the MMAs below
                 const bool live = t0 + r < p.T;
                 float4 hi, lo;
                 float* hp = &hi.x;
@@ -153,51 +196,44 @@ __global__ void __launch_bounds__(THREADS, 1) mfcc_dct_tc_kernel(const Params p)
                     const float d = live ? fmaxf(3.01029995663981195f * fast_lg2(fmaxf(v[u][j], 1e-10f)), floor_db) : 0.f;   // 10 log10(x), functional.py:390-404
                     split_tf32(d, hp[j], lp[j]);
                 }
-                const uint32_t off = (uint32_t)((r >> 3) * cores_k + kc) * 128 + (uint32_t)(r & 7) * 16;      // == op_offset(r, 4 kc, K)
-                *reinterpret_cast<float4*>(a_hi + off) = hi;
-                *reinterpret_cast<float4*>(a_lo + off) = lo;
+                const uint32_t off = (uint32_t)((r >> 3) * cores_k + kb) * 128 + (uint32_t)(r & 7) * 16;      // == op_offset(r, 4 kb, KC)
+                *reinterpret_cast<float4*>(ah + off) = hi;
+                *reinterpret_cast<float4*>(al + off) = lo;
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (warp == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-                uint32_t acc = 0;
-                for (int ks = 0; ks < K / 8; ++ks) {              // one MMA consumes K = 8 (two core matrices of 4 TF32)
-                    const uint32_t ko = (uint32_t)ks * 256;
-                    mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, acc);
-                    acc = 1;
-                    mma_tf32(tmem_d, make_desc(sa_lo + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, 1);
-                    mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_lo + ko, 128, sbo), idesc, 1);
+            // the next chunk's (or the next tile's first chunk's) loads go out now and land behind the barrier and the MMA issue
+            if (kc + 1 < n_chunks) load_chunk(tile, kc + 1, v);
+            else if (tile + gridDim.x < n_tiles) load_chunk(tile + gridDim.x, 0, v);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa_hi = smem_u32(ah), sa_lo = smem_u32(al);
+                    const uint32_t sb_hi = smem_u32(b_hi) + (uint32_t)kc * (KC >> 2) * 128, sb_lo = smem_u32(b_lo) + (uint32_t)kc * (KC >> 2) * 128;
+                    for (int ks = 0; ks < kw / 8; ++ks) {              // one MMA consumes K = 8 (two core matrices of 4 TF32)
+                        const uint32_t ko = (uint32_t)ks * 256;
+                        mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo_a), make_desc(sb_hi + ko, 128, sbo_b), idesc, (kc | ks) ? 1u : 0u);
+                        mma_tf32(tmem_d, make_desc(sa_lo + ko, 128, sbo_a), make_desc(sb_hi + ko, 128, sbo_b), idesc, 1);
+                        mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo_a), make_desc(sb_lo + ko, 128, sbo_b), idesc, 1);
+                    }
+                    // the stage is free again when these MMAs have read it; the last chunk also signals the finished accumulator
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + stage)) : "memory");
+                    if (kc == n_chunks - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 2)) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+                __syncwarp();
             }
-            __syncwarp();
+            used[stage] = 1;
         }
         // wait for the accumulator
-        {
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t"
-                    "}\n"
-                    : "=r"(done)
-                    : "r"(smem_u32(mbar)), "r"(phase)
-                    : "memory");
-            }
-            phase ^= 1;
-        }
+        wait(mbar + 2, ph_done);
+        ph_done ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: a warp reads the TMEM lane quadrant (warp % 4) = 32 frames; the warp group (warp / 4) picks the
-        // 16-column chunk of coefficients.  Stores are coalesced along frames ([n_mfcc, T] frequency-major).
-        const int quad = warp & 3, chunk = warp >> 2;
-        if (chunk * 16 < NP) {
+        // epilogue: a warp reads the TMEM lane quadrant (warp % 4) = 32 frames; warps 0-3 take coefficient chunks 0 and 2,
+        // warps 4-7 chunk 1 (16 columns each).  Stores are coalesced along frames ([n_mfcc, T] frequency-major).
+        const int quad = warp & 3;
+        for (int chunk = warp >> 2; chunk * 16 < NP; chunk += THREADS / 128) {
             uint32_t r[16];
             const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chunk * 16);
             asm volatile(
@@ -215,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1) mfcc_dct_tc_kernel(const Params p)
                     if (chunk * 16 + n < p.n_mfcc) o[(int64_t)n * p.T] = __uint_as_float(r[n]);
             }
         }
-        // the next tile overwrites the operands and the accumulator
+        // the next tile's first MMA overwrites the accumulator: everybody has read it
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -233,11 +269,11 @@ using namespace acids;
 int acids_mfcc_dct_tc_launch(const float* mel, int64_t B, int n_mels, int64_t n_frames, const float* dct, int n_mfcc, float top_db,
                              int64_t clips_per_group, const float* group_max, float* out, cudaStream_t st) {
     tc::Params p{mel, B, n_mels, n_frames, dct, n_mfcc, top_db, group_max, clips_per_group > 0 ? clips_per_group : 1, out};
-    const size_t smem = (size_t)2 * tc::TM * n_mels * 4 + (size_t)2 * tc::NP * n_mels * 4 + 64;
+    const size_t smem = (size_t)4 * tc::TM * tc::KC * 4 + (size_t)2 * tc::NP * n_mels * 4 + 64;
     ACIDS_REQUIRE(cudaFuncSetAttribute(tc::mfcc_dct_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
                   ACIDS_ECUDA, "mfcc_dct_tc: cannot reserve %zu B of shared memory", smem);
     int64_t grid = B * ((n_frames + tc::TM - 1) / tc::TM);
-    if (grid > num_sms()) grid = num_sms();
+    if (grid > 2 * (int64_t)num_sms()) grid = 2 * (int64_t)num_sms();
     tc::mfcc_dct_tc_kernel<<<(unsigned)grid, tc::THREADS, smem, st>>>(p);
     ACIDS_CHECK_LAUNCH("mfcc_dct_tc");
     return ACIDS_OK;
