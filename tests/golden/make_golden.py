@@ -290,6 +290,16 @@ def main():
     mag = d(x)[0].abs()
     save("pghi_128_32", x=x, mag=mag, phase=d.pghi(mag.clone(), 1e-2), gamma=d.gamma, eps=d.eps, y=d.invert(mag.clone()[None]))
 
+    # ---- PGHI at the DEFAULT sizes (DGT(): n_fft 1024, hop 256), the reference's default inversion of a magnitude ----
+    g = torch.Generator().manual_seed(106)
+    n = torch.arange(8192, dtype=torch.float64)
+    x = (0.5 * torch.sin(2 * math.pi * 440.0 * n / SR) + 0.25 * torch.sin(2 * math.pi * 3520.0 * n / SR)
+         + 0.1 * torch.sin(2 * math.pi * 9000.0 * n / SR)).float()[None]
+    x = x + 0.05 * (2 * torch.rand(x.shape, generator=g) - 1)
+    d = T.DGT()
+    mag = d(x)[0].abs()
+    save("pghi_1024_256", x=x, mag=mag, phase=d.pghi(mag.clone(), 1e-2), gamma=d.gamma, eps=d.eps, y=d.invert(mag.clone()[None]))
+
 
 if __name__ == "__main__":
     main()

@@ -247,7 +247,12 @@ def test_phaseless_inversion(T):
     assert float((ph.cpu() - torch.from_numpy(g["phase"])).abs().max()) < 1e-3      # phases reach hundreds of radians
     y = d.invert(mag[None])
     assert_parity(host(y), g["y"], 2e-3, "pghi inverse")        # exp(i phase) of a phase known to ~1e-5 rad
+    # the same at the reference's default sizes (DGT(): n_fft 1024, hop 256), pinned on the reference's own phase and waveform
+    g = load_golden("pghi_1024_256")
     d = T.DGT().cuda()
+    mag = cu(g["mag"])
+    assert float((d.pghi(mag, 1e-2).cpu() - torch.from_numpy(g["phase"])).abs().max()) < 1e-3
+    assert_parity(host(d.invert(mag[None])), g["y"], 2e-3, "pghi inverse, default sizes")
     X = d(x)
     yp = d.invert(X.abs())                                                  # default mode, default sizes
     conv = float(((d(yp).abs() - X[:, :33].abs()).norm() / X.abs().norm()))

