@@ -203,6 +203,15 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     // zero-filling their registers they re-read an interior frame of the same clip when there is one.
     const int t_safe = (p.pad + p.hop - 1) / p.hop;
     const bool has_safe = t_safe < n_frames && t_safe * p.hop - p.pad + N <= L;
+    // MS_DEFER (MidSide + the early prefetch of the complex kernels): combining the two channels where they are loaded would
+    // consume the loads at once and expose a full memory latency per frame (ncu, cfg 4: 26 % of all stall samples on that one
+    // FFMA).  Instead the early fetch loads the first channel raw and only PREFETCHES the second into L1; ms_finish() loads it
+    // (an L1 hit by then) and forms mid / side right before the frame is used.
+    constexpr bool MS_DEFER = MS && MODE == MODE_COMPLEX && T <= 128 && FPW == 1;
+    bool fin_on = false;                 // the prefetched frame still needs ms_finish
+    const float* __restrict__ fin_x = nullptr;
+    int fin_t = 0;
+    float fin_s = 1.f, fin_g = 1.f;
     auto fetch_fast = [&](cf* v, const float* __restrict__ xb, int t, float ms_sign, float ms_gain) -> bool {
         const bool valid = t < n_frames;
         if (!valid && has_safe) t = t_safe;
@@ -225,7 +234,9 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
                         for (int b0 = 0; b0 < B0; b0 += 2) {
                             float4 a = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
-                            if (MS) {
+                            if (MS_DEFER) {
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(src + p.ldx) + (b0 >> 1)));
+                            } else if (MS) {
                                 const float4 o = __ldg(reinterpret_cast<const float4*>(src + p.ldx) + (b0 >> 1));
                                 a = make_float4(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain,
                                                 fmaf(ms_sign, o.z, a.z) * ms_gain, fmaf(ms_sign, o.w, a.w) * ms_gain);
@@ -237,7 +248,9 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
 #pragma unroll
                         for (int b0 = 0; b0 < B0; ++b0) {
                             float2 a = __ldg(reinterpret_cast<const float2*>(src) + b0);
-                            if (MS) {
+                            if (MS_DEFER) {
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float2*>(src + p.ldx) + b0));
+                            } else if (MS) {
                                 const float2 o = __ldg(reinterpret_cast<const float2*>(src + p.ldx) + b0);
                                 a = make_float2(fmaf(ms_sign, o.x, a.x) * ms_gain, fmaf(ms_sign, o.y, a.y) * ms_gain);
                             }
@@ -245,12 +258,43 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
                         }
                     }
                 }
+                if (MS_DEFER) {
+                    fin_on = true;
+                    fin_x = xb;
+                    fin_t = t;
+                    fin_s = ms_sign;
+                    fin_g = ms_gain;
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[i] = mk(0.f, 0.f);
             }
         }
         return stage;
+    };
+    // second half of a deferred MidSide fetch: v holds the first channel's raw samples of frame fin_t
+    auto ms_finish = [&](cf* v) {
+        if (!MS_DEFER || !fin_on) return;
+        fin_on = false;
+        const int s0i = fin_t * p.hop - p.pad;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+            const float* __restrict__ src = fin_x + p.ldx + s0i + 2 * (tid * B0 + r * NB0);
+            if (VW == 4) {
+#pragma unroll
+                for (int b0 = 0; b0 < B0; b0 += 2) {
+                    const float4 o = __ldg(reinterpret_cast<const float4*>(src) + (b0 >> 1));
+                    v[b0 * R0 + r] = mk(fmaf(fin_s, o.x, v[b0 * R0 + r].x) * fin_g, fmaf(fin_s, o.y, v[b0 * R0 + r].y) * fin_g);
+                    v[(b0 + 1) * R0 + r] = mk(fmaf(fin_s, o.z, v[(b0 + 1) * R0 + r].x) * fin_g, fmaf(fin_s, o.w, v[(b0 + 1) * R0 + r].y) * fin_g);
+                }
+            } else {
+#pragma unroll
+                for (int b0 = 0; b0 < B0; ++b0) {
+                    const float2 o = __ldg(reinterpret_cast<const float2*>(src) + b0);
+                    v[b0 * R0 + r] = mk(fmaf(fin_s, o.x, v[b0 * R0 + r].x) * fin_g, fmaf(fin_s, o.y, v[b0 * R0 + r].y) * fin_g);
+                }
+            }
+        }
     };
     auto fetch_staged = [&](cf* v, cf* s, const float* __restrict__ xb, int t, float ms_sign, float ms_gain) {
         const bool valid = t < n_frames;
@@ -307,6 +351,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
     if (u0 < u1) {
 #pragma unroll
         for (int f = 0; f < FPW; ++f) fetch(v[f], s0 + f * P::SMEM_CF, xclip, uc * G + g * FPW + f);
+        ms_finish(v[0]);
     }
     // the row-tile epilogue of one unit: rows `vb` (shared memory) -> banded projection -> contrast -> normalise -> `outc`
     // halo (POLAR): the unit before the CTA's run — rows only, nothing is stored
@@ -523,6 +568,7 @@ __global__ void __launch_bounds__(FwdCfg<P, MODE>::THREADS, MODE == MODE_COMPLEX
             if (EARLY) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[0][i] = nv[EARLY ? i : 0];
+                ms_finish(v[0]);
             } else {
                 if (u + 1 < u1) {
 #pragma unroll
