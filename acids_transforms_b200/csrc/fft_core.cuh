@@ -222,7 +222,11 @@ struct Plan {
 #ifndef ACIDS_T16I_PADLOG
 #define ACIDS_T16I_PADLOG 4
 #endif
-    static constexpr int PADLOG = (N_ == 1024 && T_ == 16) ? (R0_ == 32 ? ACIDS_T16_PADLOG : ACIDS_T16I_PADLOG) : 4;
+#ifndef ACIDS_INV4096_PADLOG
+#define ACIDS_INV4096_PADLOG 5      // pad every 32 slots: 640 instead of 704 exchange wavefronts per frame (ideal 512), 0.664 -> 0.644 ms at cfg 4
+#endif
+    static constexpr int PADLOG = (N_ == 1024 && T_ == 16) ? (R0_ == 32 ? ACIDS_T16_PADLOG : ACIDS_T16I_PADLOG)
+                                                           : ((N_ == 4096 && R0_ == 8) ? ACIDS_INV4096_PADLOG : 4);
     // exchange buffer, complex slots (even: 16-byte rows).  Two frames share a warp in the 16-thread plan and park their |X|
     // rows in their own buffers: 2 * SMEM_CF = 16 (mod 32) floats puts the two half warps' row stores on disjoint banks
     static constexpr int SMEM_CF = M + 2 * (M >> PADLOG) + 2 + ((N_ == 1024 && T_ == 16) ? 6 : 0);
