@@ -231,10 +231,12 @@ def test_fused_chain_golden(ops, name, window):
     assert_parity(host(y2), g["y"], REL, name + " unfused")
 
 
-@pytest.mark.parametrize("n_fft,hop", [(128, 32), (512, 128), (2048, 512), (4096, 1024), (8192, 2048)])
+@pytest.mark.parametrize("n_fft,hop", [(128, 32), (512, 128), (1024, 256), (1024, 100), (1024, 1024), (2048, 512), (4096, 1024), (8192, 2048)])
 def test_fused_magnitude_oracle(ops, n_fft, hop):
     """Small plans (many frames per CTA, several row tiles per unit) up to a bank that does not fit in shared memory
-    (n_fft = 8192: banded matrix read from global memory)."""
+    (n_fft = 8192: banded matrix read from global memory).  The clip length is odd, so every row but the first is unaligned
+    and its frames go through the staged path — at n_fft = 1024 that is the one-exchange plan with the rows parked in the
+    exchange buffers (hop 100: unaligned frame starts as well; hop = n_fft: no overlap)."""
     x = synth(3, 6 * n_fft + 17, n_fft)
     w = O.periodic_window("hann", n_fft)
     fwd, _ = O.magnitude_banks(44100, n_fft)
