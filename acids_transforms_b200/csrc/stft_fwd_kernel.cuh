@@ -768,7 +768,8 @@ static int launch_any(int variant, const FwdParams& p, cudaStream_t st) {
     using PR_ = typename RealPlan<P>::type;
     if constexpr (ACIDS_FWD_ONLY >= 0) {
         if constexpr (ACIDS_FWD_ONLY == VAR_MAG_SMEM) return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_SMEM, false>(p, st);
-        else if constexpr (ACIDS_FWD_ONLY == VAR_COMPLEX) return launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
+        else if constexpr (ACIDS_FWD_ONLY == VAR_COMPLEX) return p.midside ? launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false, true>(p, st)
+                                                                           : launch_fwd<P, MODE_COMPLEX, 1, ACIDS_CONTRAST_NONE, BAND_NONE, false>(p, st);
         else if constexpr (ACIDS_FWD_ONLY == VAR_MAG_NOBAND) return launch_fwd<PR_, MODE_REAL, 1, -1, BAND_NONE, false>(p, st);
         else if constexpr (ACIDS_FWD_ONLY == VAR_MEL_POWER_SMEM) return launch_fwd<PR_, MODE_REAL, 2, ACIDS_CONTRAST_NONE, BAND_SMEM, true>(p, st);
         else return ACIDS_ENOTSUP;
