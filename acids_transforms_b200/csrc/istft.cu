@@ -9,6 +9,7 @@
 // ascending t like torch.istft's col2im.  Nothing is scattered, no atomics, no global scratch.
 //
 // HBM traffic per frame: (n_fft/2+1)*8 B in, hop*4 B out.
+#include <stdlib.h>
 #include "common.cuh"
 #include "plans.cuh"
 #include <type_traits>
@@ -561,6 +562,9 @@ struct InvLaunch {
         const int64_t total_units = p.B * (((int64_t)p.n_frames + G - 1) / G);
         if (total_units == 0) return ACIDS_OK;
         int64_t grid = (int64_t)num_sms() * ctas_per_sm;
+#ifdef ACIDS_INV_GRID_ENV      // tuning experiment: cap the persistent grid from the environment (CTAs per SM)
+        if (const char* e = getenv("ACIDS_INV_CTAS_PER_SM")) grid = (int64_t)num_sms() * atoi(e);
+#endif
         const int64_t min_units = 4 * ((p.ovc + G - 1) / G) + 1;
         if (grid > total_units / min_units) grid = total_units / min_units;
         if (grid < 1) grid = 1;
