@@ -59,6 +59,8 @@ _PROTOTYPES = {
     "acids_stream_analysis": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "acids_stream_synthesis": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_float, _P, _P, _P]),
     "acids_stream_roundtrip": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P]),
+    "acids_pghi_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
+    "acids_pghi": (c_int, [_P, c_int64, c_int64, c_int, c_float, c_int, c_int, ctypes.c_double, c_float, _P, c_int64, _P, _P]),
     "acids_mulaw_encode": (c_int, [_P, c_int64, c_int64, c_int, c_float, c_int, c_int, _P, _P]),
     "acids_mulaw_decode": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "acids_one_hot": (c_int, [_P, c_int64, c_int, _P, _P]),

@@ -744,6 +744,27 @@ def stream_roundtrip(x, window, inv_window, n_fft, hop, gain, tail, carry, out: 
 
 
 # ------------------------------------------------------------------------------------------------
+# (4c) phase-gradient heap integration (pghi.cu)
+# ------------------------------------------------------------------------------------------------
+def pghi(mag, gamma: float, n_fft: int, hop: int, tol: float, eps: float) -> torch.Tensor:
+    """DGT.pghi (dgt.py:156-236) for a batch: mag [..., T, F] -> phase [..., T, F]; one CTA per clip."""
+    lib = _lib.load()
+    md = _dev(mag).to(torch.float32)
+    if md.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] magnitude)")
+    mf, batch = _flat_batch(md, 2)
+    B, T, F = mf.shape
+    dev = mf.device
+    out = torch.empty((B, T, F), dtype=torch.float32, device=dev)
+    nbytes = int(lib.acids_pghi_workspace_bytes(B, T, F))
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_pghi, _ptr(mf), B, T, F, float(gamma), int(n_fft), int(hop), float(tol), float(eps), _ptr(ws), nbytes,
+             _ptr(out), _stream(dev))
+    return _ret(out.reshape(tuple(batch) + (T, F)), mag)
+
+
+# ------------------------------------------------------------------------------------------------
 # (5) mu-law / one-hot
 # ------------------------------------------------------------------------------------------------
 def _log1p_mu(channels: int) -> float:

@@ -77,17 +77,21 @@ class DGT(STFT):
 
     @torch.jit.unused
     def pghi(self, mag: torch.Tensor, tolerance: float = 1.e-4) -> torch.Tensor:
-        """Phase of one [T, F] magnitude by heap integration (dgt.py:156-162), computed on the host."""
+        """Phase of a [..., T, F] magnitude by heap integration (dgt.py:156-162): the CUDA kernel (csrc/pghi.cu, one CTA per
+        clip, the reference's visiting and operation order) for device tensors; host tensors keep the numpy + heapq
+        restatement (transforms/pghi.py), which is also what pins the kernel in the tests."""
+        if mag.is_cuda:
+            from .. import ops
+            return ops.pghi(mag, float(self.gamma), self._n_fft, self._hop, float(tolerance), float(self.eps))
+        if mag.dim() > 2:
+            return torch.stack([self.pghi(m, tolerance) for m in mag])
         return _pghi.pghi(mag, float(self.gamma), self._n_fft, self._hop, float(tolerance), float(self.eps))
 
     @torch.jit.unused
     def _pghi_istft(self, x: torch.Tensor) -> torch.Tensor:
-        # dgt.py:136-143: one flood fill per clip, then mag * exp(i phase) -> ISTFT with the dual window
-        tol = float(self.tolerance)
-        if x.dim() == 3:
-            phase = torch.stack([self.pghi(x[n], tol) for n in range(x.size(0))])
-        else:
-            phase = self.pghi(x, tol)
+        # dgt.py:136-143: one flood fill per clip (all clips of a device batch in one launch), then mag * exp(i phase) -> ISTFT
+        # with the dual window
+        phase = self.pghi(x, float(self.tolerance))
         return self._istft(torch.ops.acids_b200.polar_to_complex(x.contiguous(), phase.to(x.device)))
 
     def test_inversion(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -1,4 +1,5 @@
-"""Phase-gradient heap integration (PGHI) — host-side glue, not a kernel.
+"""Phase-gradient heap integration (PGHI) — the host restatement (the whole-spectrogram variant also runs on the GPU:
+csrc/pghi.cu via ops.pghi, which DGT.pghi uses for device tensors and which the tests pin against this module).
 
 Průša, Balazs, Søndergaard, "A Noniterative Method for Reconstruction of Phase from STFT Magnitude"
 (IEEE/ACM TASLP 2017), as parameterised by the reference (acids_transforms/transforms/dgt.py:156-236 for

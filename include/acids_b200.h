@@ -262,6 +262,14 @@ ACIDS_API int acids_stream_roundtrip(const float* x, int64_t B, int64_t n, int n
                            const float* inv_window, float gain, float* tail, float* carry, float* X_out, float* out,
                            void* stream);
 
+/* ---- (4c) phase-gradient heap integration (PGHI): DGT.pghi, dgt.py:156-236 — the reference's default inversion of a magnitude ----
+ * mag float32 [B, n_frames, n_bins] (clamped at eps inside) -> phase float32 of the same shape.  One CTA per clip: log-magnitude,
+ * threshold tol * max and every region's arg-max seed in parallel, the priority-queue flood fill by one thread in the
+ * reference's visiting order ((-|X|, t, k) keys) and float32 operation order.  workspace: acids_pghi_workspace_bytes().     */
+ACIDS_API int64_t acids_pghi_workspace_bytes(int64_t B, int64_t n_frames, int n_bins);
+ACIDS_API int acids_pghi(const float* mag, int64_t B, int64_t n_frames, int n_bins, float gamma, int n_fft, int hop, double tol,
+               float eps, void* workspace, int64_t workspace_bytes, float* phase, void* stream);
+
 /* ---- (5) mu-law and one-hot ------------------------------------------------------------------
  * torchaudio mu_law_encoding / decoding (functional.py:690-700, :723-729) as used by raw.py:282-316.
  * log1p_mu = float32 log1p(channels-1) evaluated by the caller the way the reference does (host).

@@ -382,3 +382,37 @@ def test_griffin_lim_iteration_matches_torch_sample_by_sample(T):
     assert got.shape == want.shape
     # six iterations of a contraction started identically: rounding differences stay at the 1e-5 level
     assert_parity(host(got), host(want), 1e-3, "griffin-lim after %d iterations" % n_iter)
+
+
+def test_pghi_kernel_matches_reference_and_host(T):
+    """csrc/pghi.cu (one CTA per clip) against the reference's own phases (both golden fixtures) and against the host
+    restatement (transforms/pghi.py) on a batch of noisy magnitudes with several disconnected regions: the visiting order is
+    identical by construction, the values differ by the rounding of logf only."""
+    from acids_transforms_b200 import ops
+    from acids_transforms_b200.transforms import pghi as P
+    for name, n_fft, hop in (("pghi_128_32", 128, 32), ("pghi_1024_256", 1024, 256)):
+        g = load_golden(name)
+        ph = ops.pghi(cu(g["mag"]), float(g["gamma"]), n_fft, hop, 1e-2, float(g["eps"]))
+        ref = torch.from_numpy(g["phase"])
+        assert ph.shape == ref.shape
+        assert float((ph.cpu() - ref).abs().max()) < 1e-3, name
+        assert bool(((ph.cpu() != 0) == (ref != 0)).all()), name + ": the same bins are visited"
+    # a batch: speech-like bursts separated by silence (several regions per clip), different per clip
+    torch.manual_seed(31)
+    d = T.DGT(n_fft=256, hop_length=64).cuda()
+    x = torch.zeros(5, 6000, device="cuda")
+    for b in range(5):
+        for s0 in range(300 + 97 * b, 5600, 1400):
+            n = torch.arange(500, device="cuda")
+            x[b, s0:s0 + 500] = torch.sin(2 * math.pi * (300.0 + 211 * b) * n / 44100) * torch.hann_window(500, device="cuda") \
+                + 0.02 * torch.randn(500, device="cuda")
+    mag = d(x).abs()
+    got = d.pghi(mag, 1e-2)
+    assert got.shape == mag.shape
+    for b in range(5):
+        want = P.pghi(mag[b].cpu(), float(d.gamma), 256, 64, 1e-2, float(d.eps))
+        assert bool(((got[b].cpu() != 0) == (want != 0)).all()), "clip %d: visited set" % b
+        assert float((got[b].cpu() - want).abs().max()) < 2e-3, "clip %d" % b
+    # the module's default inversion runs on it end to end
+    y = d.invert(mag)
+    assert y.shape[0] == 5 and bool(torch.isfinite(y).all())
