@@ -26,54 +26,49 @@ struct PghiParams {
     float abstol;
     float* logm;           // workspace [B, T, F]: log(max(mag, abstol))
     float* s;              // workspace [B, T, F]: magnitudes still to visit (abstol = visited / too quiet)
-    float* hkey;           // workspace [B, T * F]: heap keys (-|X|)
-    int* hidx;             // workspace [B, T * F]: heap payload (linear bin index)
+    float* hkey;           // workspace [B, T * F] x 8 bytes: the heap (64-bit keys, see Heap)
     float* phase;          // out [B, T, F]
 };
 
+// Binary min-heap of 64-bit keys: (0xFFFFFFFF - bits(|X|)) << 32 | linear bin index.  |X| > 0, so its bit pattern orders like
+// its value: ascending keys are descending magnitudes, ties by ascending (t, k) — the order of the reference's tuples
+// (-|X|, t, k) — with ONE load and ONE compare per entry (the walk is a single thread's dependent chain: instructions count).
 struct Heap {
-    float* key;
-    int* idx;
+    unsigned long long* a;
     int n;
-    __device__ __forceinline__ static bool less(float ka, int ia, float kb, int ib) { return ka < kb || (ka == kb && ia < ib); }
-    __device__ void push(float k, int i) {
+    __device__ __forceinline__ static unsigned long long make(float mag, int i) {
+        return ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(mag)) << 32) | (unsigned)i;
+    }
+    __device__ void push(unsigned long long k) {
         int c = n++;
         while (c > 0) {
             const int pnt = (c - 1) >> 1;
-            const float pk = key[pnt];
-            const int pi = idx[pnt];
-            if (!less(k, i, pk, pi)) break;
-            key[c] = pk;
-            idx[c] = pi;
+            const unsigned long long pk = a[pnt];
+            if (!(k < pk)) break;
+            a[c] = pk;
             c = pnt;
         }
-        key[c] = k;
-        idx[c] = i;
+        a[c] = k;
     }
     __device__ int pop() {
-        const int top = idx[0];
+        const int top = (int)(unsigned)a[0];
         --n;
         if (n > 0) {
-            const float k = key[n];
-            const int i = idx[n];
+            const unsigned long long k = a[n];
             int c = 0;
             for (;;) {
                 int l = 2 * c + 1;
                 if (l >= n) break;
-                float lk = key[l];
-                int li = idx[l];
+                unsigned long long lk = a[l];
                 if (l + 1 < n) {
-                    const float rk = key[l + 1];
-                    const int ri = idx[l + 1];
-                    if (less(rk, ri, lk, li)) { ++l; lk = rk; li = ri; }
+                    const unsigned long long rk = a[l + 1];
+                    if (rk < lk) { ++l; lk = rk; }
                 }
-                if (!less(lk, li, k, i)) break;
-                key[c] = lk;
-                idx[c] = li;
+                if (!(lk < k)) break;
+                a[c] = lk;
                 c = l;
             }
-            key[c] = k;
-            idx[c] = i;
+            a[c] = k;
         }
         return top;
     }
@@ -123,7 +118,7 @@ __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
         return __fadd_rn(__fmul_rn(-p.fmul, d), 3.14159265358979323846f);
     };
 
-    Heap h{p.hkey + b * n, p.hidx + b * n, 0};
+    Heap h{reinterpret_cast<unsigned long long*>(p.hkey) + b * n, 0};
     for (;;) {
         // ---- seed: the loudest unvisited bin, FIRST index on ties like np.argmax ----
         float bv = -1.f;
@@ -153,7 +148,7 @@ __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
         if (threadIdx.x == 0) {
             // ---- the flood fill of this region (dgt.py:186-224) ----
             h.n = 0;
-            h.push(-top, seed);
+            h.push(Heap::make(top, seed));
             s[seed] = abstol;
             while (h.n > 0) {
                 const int i = h.pop();
@@ -161,22 +156,22 @@ __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
                 const float ph = phase[i];
                 if (t + 1 < T && s[i + F] > abstol) {
                     phase[i + F] = __fadd_rn(ph, __fmul_rn(__fadd_rn(fgrad(t, k), fgrad(t + 1, k)), 0.5f));
-                    h.push(-s[i + F], i + F);
+                    h.push(Heap::make(s[i + F], i + F));
                     s[i + F] = abstol;
                 }
                 if (t > 0 && s[i - F] > abstol) {
                     phase[i - F] = __fsub_rn(ph, __fmul_rn(__fadd_rn(fgrad(t, k), fgrad(t - 1, k)), 0.5f));
-                    h.push(-s[i - F], i - F);
+                    h.push(Heap::make(s[i - F], i - F));
                     s[i - F] = abstol;
                 }
                 if (k + 1 < F && s[i + 1] > abstol) {
                     phase[i + 1] = __fadd_rn(ph, __fmul_rn(__fadd_rn(tgrad(t, k), tgrad(t, k + 1)), 0.5f));
-                    h.push(-s[i + 1], i + 1);
+                    h.push(Heap::make(s[i + 1], i + 1));
                     s[i + 1] = abstol;
                 }
                 if (k > 0 && s[i - 1] > abstol) {
                     phase[i - 1] = __fsub_rn(ph, __fmul_rn(__fadd_rn(tgrad(t, k), tgrad(t, k - 1)), 0.5f));
-                    h.push(-s[i - 1], i - 1);
+                    h.push(Heap::make(s[i - 1], i - 1));
                     s[i - 1] = abstol;
                 }
             }
@@ -210,7 +205,7 @@ extern "C" ACIDS_API int acids_pghi(const float* mag, int64_t B, int64_t n_frame
     p.kstep = (float)(2.0 * 3.14159265358979323846 * (double)hop / (double)n_fft);
     p.tol = tol; p.abstol = eps;
     float* w = static_cast<float*>(workspace);
-    p.logm = w; p.s = w + n; p.hkey = w + 2 * n; p.hidx = reinterpret_cast<int*>(w + 3 * n);
+    p.logm = w; p.s = w + n; p.hkey = w + 2 * n;       // 2 n floats = n 64-bit heap entries (8-byte aligned: n floats each before)
     p.phase = phase;
     pghi_kernel<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("pghi");
