@@ -764,6 +764,29 @@ def pghi(mag, gamma: float, n_fft: int, hop: int, tol: float, eps: float) -> tor
     return _ret(out.reshape(tuple(batch) + (T, F)), mag)
 
 
+def rt_pghi(mag, hist_mag, hist_phase, gamma: float, n_fft: int, hop: int, tol: float, eps: float, noise=None) -> torch.Tensor:
+    """RealtimeDGT.pghi (dgt.py:338-452): mag [..., n, F] new frames, hist_mag [..., 2, F], hist_phase [..., F] ->
+    phase [..., n, F]; one CTA per stream, heap in shared memory.  `noise` [..., n, F]: the phase of the bins below the
+    tolerance (None: zeros)."""
+    lib = _lib.load()
+    md = _dev(mag).to(torch.float32)
+    if md.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] magnitude)")
+    mf, batch = _flat_batch(md, 2)
+    B, n, F = mf.shape
+    dev = mf.device
+    hm = hist_mag.to(dev, torch.float32).reshape(B, 2, F).contiguous()
+    hp = hist_phase.to(dev, torch.float32).reshape(B, F).contiguous()
+    nz = None if noise is None else noise.to(dev, torch.float32).reshape(B, n, F).contiguous()
+    out = torch.empty((B, n, F), dtype=torch.float32, device=dev)
+    nbytes = int(lib.acids_rt_pghi_workspace_bytes(B, n, F))
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _run(out, lib.acids_rt_pghi, _ptr(mf), _ptr(hm), _ptr(hp), _ptr(nz) if nz is not None else None, B, n, F, float(gamma),
+             int(n_fft), int(hop), float(tol), float(eps), _ptr(ws), nbytes, _ptr(out), _stream(dev))
+    return _ret(out.reshape(tuple(batch) + (n, F)), mag)
+
+
 # ------------------------------------------------------------------------------------------------
 # (5) mu-law / one-hot
 # ------------------------------------------------------------------------------------------------

@@ -2,10 +2,11 @@
 canonical dual as synthesis window (acids_transforms/transforms/dgt.py:24-123, :238-302).
 
 The analysis / complex-inverse path is the same pair of kernels as STFT.  Phase-gradient heap
-integration (PGHI, dgt.py:156-236, :338-466) is a sequential priority-queue flood fill that
-SURVEY.md §8 keeps off the GPU hot path (row N4): the phase is reconstructed on the host
-(transforms/pghi.py, numpy + heapq), recombined with the magnitude and inverted by the CUDA kernels.
-Like the reference's, it is eager-only (the reference scripts a TorchScript heap; here scripted modules
+integration (PGHI, dgt.py:156-236, :338-466) is a sequential priority-queue
+flood fill per clip: device tensors go through csrc/pghi.cu (one CTA per clip or stream, the
+reference's visiting order and float32 operation order), host tensors through the numpy + heapq
+restatement (transforms/pghi.py) that also pins the kernels in the tests; the phase is recombined
+with the magnitude and inverted by the CUDA kernels.  Like the reference's, it is eager-only (the reference scripts a TorchScript heap; here scripted modules
 support every other inversion mode and raise for "pghi").
 """
 import math
@@ -188,9 +189,25 @@ class RealtimeDGT(DGT):
         flat = x.reshape(-1, x.size(-2), n_bins)
         hist_mag = self.hgi_mag_buffer.reshape(-1, 2, n_bins)
         hist_phase = self.hgi_phase_buffer.reshape(-1, n_bins)
-        ph = _pghi.rt_pghi(flat, hist_mag, hist_phase, float(self.gamma), self._n_fft, self._hop, float(self.tolerance),
-                           float(self.eps))
+        if flat.is_cuda:
+            # csrc/pghi.cu rt_pghi_kernel: one CTA per stream, no trip to the host (the three scalar buffers are read back
+            # once per value, not once per block); quiet bins take a normal random phase
+            from .. import ops
+            gamma, tol, eps = self._pghi_scalars()
+            ph = ops.rt_pghi(flat, hist_mag, hist_phase, gamma, self._n_fft, self._hop, tol, eps, noise=torch.randn_like(flat))
+        else:
+            ph = _pghi.rt_pghi(flat, hist_mag, hist_phase, float(self.gamma), self._n_fft, self._hop, float(self.tolerance),
+                               float(self.eps))
         return ph.reshape(x.shape)
+
+    def _pghi_scalars(self):
+        """(gamma, tolerance, eps) as Python floats, re-read from the device buffers only when one of them changed."""
+        bufs = (self.gamma, self.tolerance, self.eps)
+        key = tuple((b.data_ptr(), b._version) for b in bufs)
+        if getattr(self, "_pghi_scalar_key", None) != key:
+            self._pghi_scalar_val = tuple(float(v) for v in torch.stack([b.reshape(()).float() for b in bufs]).cpu())
+            self._pghi_scalar_key = key
+        return self._pghi_scalar_val
 
     def _update_hgi_buffers(self, mag: torch.Tensor, phase: torch.Tensor) -> None:
         # dgt.py:329-336, on (|x|, angle(x)) of x = mag * exp(i phase): the angle is the phase wrapped to (-pi, pi]

@@ -15,8 +15,11 @@ Reference quirks that are reproduced because they shape the output (each is visi
     stencil (3 y[t+1] - 4 y[t] + y[t-1]) / 2 (dgt.py:380), the gradient rows are indexed two frames late
     (the extra zero rows of dgt.py:393-395), bin 0 is never reached from bin 1 (`> 0` at dgt.py:434), and
     low-magnitude bins get a normal random phase.
-One deliberate deviation: the reference's real-time stencil reads one row of uninitialised memory (`torch.empty`,
-dgt.py:373) for the newest frame; here that row replicates the newest frame.
+One deliberate deviation: the reference's real-time stencil reads rows of uninitialised memory (`torch.empty`,
+dgt.py:373) on either side of the block.  The row after the newest frame only feeds a gradient row that is never indexed
+(the two-frame lag above); the row BEFORE the first history frame feeds the gradient the first two new frames integrate,
+so the reference's phases depend on what the allocator returned.  Here both rows replicate their neighbour; the golden
+fixture `rtpghi_128_32` was generated with zero memory there and pins this restatement with `row_before="zeros"`.
 """
 import heapq
 import math
@@ -93,14 +96,18 @@ def pghi(mag: torch.Tensor, gamma: float, n_fft: int, hop: int, tol: float, eps:
 # ---------------------------------------------------------------------------------------------
 # frame-by-frame variant (RealtimeDGT.pghi, dgt.py:338-466)
 # ---------------------------------------------------------------------------------------------
-def rt_phase_gradients(mag: np.ndarray, gamma: float, n_fft: int, hop: int) -> Tuple[np.ndarray, np.ndarray]:
-    """mag [T, F] is already clamped and includes the two history frames (dgt.py:364-384)."""
+def rt_phase_gradients(mag: np.ndarray, gamma: float, n_fft: int, hop: int, row_before: str = "edge") -> Tuple[np.ndarray, np.ndarray]:
+    """mag [T, F] is already clamped and includes the two history frames (dgt.py:364-384).  `row_before`: what the stencil
+    sees before the first history frame — "edge" (the product: that frame replicated) or "zeros" (what the reference reads
+    when its `torch.empty` row happens to be zero memory; used to pin this restatement on the golden fixture)."""
     fmul = np.float32(gamma / (hop * n_fft))
     y = np.log(mag).astype(np.float32)
     yb = np.pad(y, ((0, 0), (1, 1)), mode="edge")
     d_bins = (yb[:, 2:] - yb[:, :-2]) / np.float32(2)
     # (3 y[t+1] - 4 y[t] + y[t-1]) / 2 with the rows outside the block replicated (see module docstring)
     yt = np.pad(y, ((1, 1), (0, 0)), mode="edge")
+    if row_before == "zeros":
+        yt[0] = 0
     d_frames = (np.float32(3) * yt[2:] - np.float32(4) * yt[1:-1] + yt[:-2]) / np.float32(2)
     k = np.arange(n_fft // 2 + 1, dtype=np.float32)[None, :]
     fgrad = d_bins / fmul + np.float32(2 * math.pi * hop / n_fft) * k
@@ -109,7 +116,7 @@ def rt_phase_gradients(mag: np.ndarray, gamma: float, n_fft: int, hop: int) -> T
 
 
 def rt_heap_integrate(mag: np.ndarray, prev_phase: np.ndarray, tgrad: np.ndarray, fgrad: np.ndarray, tol: float, eps: float,
-                      rng: np.random.Generator) -> np.ndarray:
+                      rng: np.random.Generator, noise: Optional[np.ndarray] = None) -> np.ndarray:
     """One clip: rows 0-1 of mag are the history frames, row 1 has the known phase `prev_phase` (dgt.py:386-452).
     Every new frame is seeded from the previous frame's audible bins and from its own loudest bin."""
     s = mag.astype(np.float32).copy()
@@ -118,7 +125,7 @@ def rt_heap_integrate(mag: np.ndarray, prev_phase: np.ndarray, tgrad: np.ndarray
     phase = np.zeros_like(s)
     phase[1] = prev_phase
     quiet = ~(s[2:] > abstol)
-    phase[2:][quiet] = rng.standard_normal(int(quiet.sum())).astype(np.float32)
+    phase[2:][quiet] = rng.standard_normal(int(quiet.sum())).astype(np.float32) if noise is None else noise[quiet]
     # the reference prepends two zero rows to gradients that already cover the history frames
     zeros = np.zeros((2, n_f), np.float32)
     tg = np.concatenate([zeros, tgrad], 0)
@@ -157,14 +164,17 @@ def rt_heap_integrate(mag: np.ndarray, prev_phase: np.ndarray, tgrad: np.ndarray
 
 
 def rt_pghi(mag: torch.Tensor, hist_mag: torch.Tensor, hist_phase: torch.Tensor, gamma: float, n_fft: int, hop: int,
-            tol: float, eps: float, generator: Optional[np.random.Generator] = None) -> torch.Tensor:
-    """mag [B, n, F] new frames, hist_mag [B, 2, F], hist_phase [B, F] -> phase [B, n, F]."""
+            tol: float, eps: float, generator: Optional[np.random.Generator] = None, row_before: str = "edge",
+            noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mag [B, n, F] new frames, hist_mag [B, 2, F], hist_phase [B, F] -> phase [B, n, F].  Bins below the tolerance take
+    `noise` [B, n, F] when given, else draws of `generator`."""
     rng = generator or np.random.default_rng()
     m = torch.cat([hist_mag.to(mag.device, mag.dtype), mag], -2).detach().to("cpu", torch.float32).numpy()
     m = np.maximum(m, np.float32(eps))
     hp = hist_phase.detach().to("cpu", torch.float32).numpy()
+    nz = None if noise is None else noise.detach().to("cpu", torch.float32).numpy()
     out = []
     for i in range(m.shape[0]):
-        tgrad, fgrad = rt_phase_gradients(m[i], gamma, n_fft, hop)
-        out.append(rt_heap_integrate(m[i], hp[i], tgrad, fgrad, tol, eps, rng))
+        tgrad, fgrad = rt_phase_gradients(m[i], gamma, n_fft, hop, row_before)
+        out.append(rt_heap_integrate(m[i], hp[i], tgrad, fgrad, tol, eps, rng, None if nz is None else nz[i]))
     return torch.from_numpy(np.stack(out)).to(mag.device)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACIDS_ABI_VERSION 3
+#define ACIDS_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ACIDS_API __attribute__((visibility("default")))
@@ -269,6 +269,17 @@ ACIDS_API int acids_stream_roundtrip(const float* x, int64_t B, int64_t n, int n
 ACIDS_API int64_t acids_pghi_workspace_bytes(int64_t B, int64_t n_frames, int n_bins);
 ACIDS_API int acids_pghi(const float* mag, int64_t B, int64_t n_frames, int n_bins, float gamma, int n_fft, int hop, double tol,
                float eps, void* workspace, int64_t workspace_bytes, float* phase, void* stream);
+
+/* Frame-by-frame variant (RealtimeDGT.pghi, dgt.py:338-452): phase of n_frames NEW frames per stream, continued from the two
+ * remembered frames hist_mag [B, 2, n_bins] and the phase hist_phase [B, n_bins] of the newer one.  Every new frame is filled
+ * from the previous frame's audible bins (steps along time) and its own loudest bin (steps along bins); the heap and the
+ * frame's rows live in shared memory, one CTA per stream.  noise [B, n_frames, n_bins] (may be NULL: zeros) is what bins
+ * below max(tol * max, eps) receive (the reference draws randn).  The stencil row before the first remembered frame
+ * replicates it (the reference reads uninitialised memory there).  workspace: acids_rt_pghi_workspace_bytes().          */
+ACIDS_API int64_t acids_rt_pghi_workspace_bytes(int64_t B, int64_t n_frames, int n_bins);
+ACIDS_API int acids_rt_pghi(const float* mag, const float* hist_mag, const float* hist_phase, const float* noise, int64_t B,
+                  int64_t n_frames, int n_bins, float gamma, int n_fft, int hop, float tol, float eps, void* workspace,
+                  int64_t workspace_bytes, float* phase, void* stream);
 
 /* ---- (5) mu-law and one-hot ------------------------------------------------------------------
  * torchaudio mu_law_encoding / decoding (functional.py:690-700, :723-729) as used by raw.py:282-316.

@@ -416,3 +416,56 @@ def test_pghi_kernel_matches_reference_and_host(T):
     # the module's default inversion runs on it end to end
     y = d.invert(mag)
     assert y.shape[0] == 5 and bool(torch.isfinite(y).all())
+
+
+def test_rt_pghi_kernel_matches_reference_and_host(T):
+    """csrc/pghi.cu rt_pghi_kernel (one CTA per stream, heap in shared memory) against the host restatement that
+    tests/test_host_api.py pins on the reference's RealtimeDGT.pghi: the golden blocks through their history, then batches of
+    noisy magnitudes with quiet bins (explicit noise), disconnected regions and silent frames, at two transform sizes."""
+    from acids_transforms_b200 import ops
+    from acids_transforms_b200.transforms import pghi as P
+    g = load_golden("rtpghi_128_32")
+    mag = torch.from_numpy(g["mag"])
+    gamma, tol, eps = float(g["gamma"].reshape(-1)[0]), float(g["tol"]), float(g["eps"].reshape(-1)[0])
+    for i, (a, b) in enumerate(g["blocks"]):
+        hm, hp = torch.from_numpy(g["hist_mag"][i]), torch.from_numpy(g["hist_phase"][i])
+        got = ops.rt_pghi(mag[:, a:b].cuda(), hm.cuda(), hp.cuda(), gamma, 128, 32, tol, eps).cpu()
+        want = P.rt_pghi(mag[:, a:b], hm, hp, gamma, 128, 32, tol, eps)
+        assert float((got - want).abs().max()) < 1e-3, (a, b)
+        assert float((got - torch.from_numpy(g["phase"][:, a:b])).abs().max()) < 0.05       # the reference, up to its empty row
+    gen = torch.Generator().manual_seed(31)
+    # n_fft 8192 / 16384: too many keys to sort in shared memory, the binary heap instead (in shared / global memory)
+    for n_fft, hop, n, B, tol in ((256, 64, 5, 6, 1e-2), (1024, 256, 1, 4, 1e-2), (1024, 256, 3, 3, 1e-6), (4096, 1024, 2, 3, 1e-3),
+                                  (8192, 2048, 2, 3, 1e-3), (16384, 4096, 1, 3, 1e-3)):
+        F = n_fft // 2 + 1
+        m = torch.rand((B, n + 2, F), generator=gen) ** 4
+        m[:, :, F // 3:F // 3 + 6] = 1e-9                   # a silent band: two regions per frame
+        m[0, 3 if n > 1 else 2] = 1e-9                      # a silent frame
+        if B > 2:
+            m[2, :2] = 0.0                                  # a stream that starts from the reset history
+        hm, mg = m[:, :2].contiguous(), m[:, 2:].contiguous()
+        hp = 6.0 * torch.rand((B, F), generator=gen) - 3.0
+        nz = torch.randn((B, n, F), generator=gen)
+        d = T.RealtimeDGT(n_fft=n_fft, hop_length=hop)
+        gm = float(d.gamma)
+        got = ops.rt_pghi(mg.cuda(), hm.cuda(), hp.cuda(), gm, n_fft, hop, tol, float(d.eps), noise=nz.cuda()).cpu()
+        want = P.rt_pghi(mg, hm, hp, gm, n_fft, hop, tol, float(d.eps), noise=nz)
+        err = float((got - want).abs().max())
+        assert err < 2e-3 * max(1.0, float(want.abs().max()) / 1000.0), (n_fft, n, err)
+
+
+def test_realtime_dgt_pghi_stays_on_the_device(T):
+    """RealtimeDGT.invert(magnitude) in its default mode: the CUDA module (rt_pghi_kernel) against the same module fed host
+    tensors (numpy + heapq), block after block through the remembered frames; a tolerance below every bin keeps the random
+    phase out of the comparison."""
+    g = load_golden("rtpghi_128_32")
+    mag = torch.from_numpy(g["mag"])
+    dev_m, host_m = T.RealtimeDGT(n_fft=128, hop_length=32, batch_size=2).cuda(), T.RealtimeDGT(n_fft=128, hop_length=32, batch_size=2)
+    for m in (dev_m, host_m):
+        m.tolerance.fill_(1e-6)
+    for a, b in g["blocks"]:
+        y_dev = dev_m.invert(mag[:, a:b].cuda())
+        y_host = host_m.invert(mag[:, a:b])
+        assert y_dev.is_cuda and tuple(y_dev.shape) == (2, b - a, 128)
+        assert_parity(y_dev.cpu(), y_host.cpu(), 2e-3, "RealtimeDGT pghi block %d:%d" % (a, b))
+        assert float((dev_m.hgi_phase_buffer.cpu() - host_m.hgi_phase_buffer.cpu()).abs().max()) < 2e-3

@@ -261,3 +261,27 @@ def test_pghi_matches_reference_golden():
     mag = torch.from_numpy(g["mag"])[None, :8]
     out = P.rt_pghi(mag, torch.zeros(1, 2, 65), torch.zeros(1, 65), 12.0, 128, 32, 1e-2, float(g["eps"]), rng)
     assert tuple(out.shape) == (1, 8, 65) and bool(torch.isfinite(out).all())
+
+
+def test_rt_pghi_matches_reference_golden():
+    """The frame-by-frame PGHI (RealtimeDGT.pghi, dgt.py:338-452) pinned on the reference's own output for three consecutive
+    blocks (3, 1 and 4 frames) through its two-frame history.  The reference's stencil reads a `torch.empty` row before the
+    first remembered frame; the fixture was generated with zero memory there (tests/golden/make_golden.py), which
+    `row_before="zeros"` restates — everything else (visiting order, lagged gradient rows, float32 operation order) must agree
+    to float32 rounding of phases that reach thousands of radians."""
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from acids_transforms_b200.transforms import pghi as P
+    g = load_golden("rtpghi_128_32")
+    assert bool(g["audible"].all())          # no bin takes the (unpinnable) random phase
+    mag = torch.from_numpy(g["mag"])
+    gamma, tol, eps = float(g["gamma"].reshape(-1)[0]), float(g["tol"]), float(g["eps"].reshape(-1)[0])
+    for i, (a, b) in enumerate(g["blocks"]):
+        args = (mag[:, a:b], torch.from_numpy(g["hist_mag"][i]), torch.from_numpy(g["hist_phase"][i]), gamma, 128, 32, tol, eps)
+        ph = P.rt_pghi(*args, row_before="zeros").numpy()
+        ref = g["phase"][:, a:b]
+        assert float(np.abs(ph - ref).max()) < 2.5e-4 * max(1.0, float(np.abs(ref).max()) / 1000.0), (a, b)
+        # the product replicates the first remembered frame instead: same walk, a bounded offset on the first two frames' step
+        edge = P.rt_pghi(*args).numpy()
+        assert float(np.abs(edge - ref).max()) < 0.05

@@ -19,3 +19,28 @@ for B in (1, 16, 256):
 t0 = time.perf_counter(); want = P.pghi(mag[0].cpu(), float(d.gamma), 1024, 256, 1e-2, float(d.eps)); t1 = time.perf_counter()
 print("host numpy + heapq, 1 clip: %.3f s" % (t1 - t0))
 print("max |gpu - host| on clip 0: %.2e rad; visited %.1f %% of the bins" % (float((ph[0].cpu() - want).abs().max()), 100 * float((want != 0).float().mean())))
+
+# ---- frame-by-frame variant: RealtimeDGT.invert(magnitude) in its default mode, one frame per call ----
+if "--rt" in sys.argv or True:
+    for B in (1, 16, 256):
+        rt_dev = Tr.RealtimeDGT(n_fft=1024, hop_length=256, batch_size=B).cuda()
+        rt_host = Tr.RealtimeDGT(n_fft=1024, hop_length=256, batch_size=B)
+        blocks = [mag[:B, 100 + i:101 + i].contiguous() for i in range(12)]
+        for blk in blocks[:2]:
+            rt_dev.invert(blk)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for blk in blocks[2:]:
+            y = rt_dev.invert(blk)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        line = "RealtimeDGT.invert (pghi), %3d streams, one frame per call: device %.3f ms per call" % (B, 1e3 * (t1 - t0) / 10)
+        if B <= 16:
+            hb = [b.cpu() for b in blocks]
+            rt_host.invert(hb[0]); rt_host.invert(hb[1])
+            t0 = time.perf_counter()
+            for blk in hb[2:6]:
+                rt_host.invert(blk)
+            t1 = time.perf_counter()
+            line += "; host restatement %.1f ms per call" % (1e3 * (t1 - t0) / 4)
+        print(line)
