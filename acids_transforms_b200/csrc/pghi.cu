@@ -26,7 +26,7 @@ struct PghiParams {
     float abstol;
     float* logm;           // workspace [B, T, F]: log(max(mag, abstol))
     float* s;              // workspace [B, T, F]: magnitudes still to visit (abstol = visited / too quiet)
-    float* hkey;           // workspace [B, T * F] x 8 bytes: the heap (64-bit keys, see Heap)
+    float* hkey;           // workspace, 64-byte aligned: B heaps of pghi_heap_stride(T F) 64-bit keys (see Heap8)
     float* phase;          // out [B, T, F]
 };
 
@@ -74,6 +74,71 @@ struct Heap {
     }
 };
 
+// The whole-spectrogram walk keeps hundreds of thousands of entries in GLOBAL memory, where every level of a sift is a trip to
+// L2: an 8-ary heap has a third of the binary heap's levels (6 instead of 18 at 354 k entries), and the eight children of a
+// node are one aligned 64-byte line fetched by four independent 16-byte loads.  Node i lives at a[7 + i], so the children
+// 8 i + 1 ... 8 i + 8 start at a[8 (i + 1)].  The pop order only depends on the keys, not on the heap's shape.
+struct Heap8 {
+    // (Keeping the top four levels — 585 nodes, 4.7 KB — in shared memory was measured: 0.65 s against 0.47 s per clip; the
+    // address-space select on every access costs more than the L1-resident top of the heap saves.)
+    unsigned long long* a;      // global, 64-byte aligned; node i at a[7 + i]
+    int n;
+    __device__ __forceinline__ unsigned long long& at(int i) { return a[7 + i]; }
+    __device__ __forceinline__ void push(unsigned long long k) {
+        int c = n++;
+        while (c > 0) {
+            const int pnt = (c - 1) >> 3;
+            const unsigned long long pk = at(pnt);
+            if (!(k < pk)) break;
+            at(c) = pk;
+            c = pnt;
+        }
+        at(c) = k;
+    }
+    __device__ __forceinline__ int peek() const { return (int)(unsigned)a[7]; }
+    __device__ __forceinline__ void drop() {          // removes the root (peek() first)
+        --n;
+        if (n > 0) {
+            const unsigned long long k = at(n);
+            int c = 0;
+            for (;;) {
+                const int l = 8 * c + 1;
+                if (l >= n) break;
+                unsigned long long v[8];
+                const unsigned long long* ch = a + 7 + l;
+                if (l + 8 <= n) {
+                    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(ch);
+                    const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                    v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y; v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = l + j < n ? ch[j] : ~0ull;
+                }
+                // smallest of the eight (keys are distinct), as a tree
+                const bool b01 = v[1] < v[0], b23 = v[3] < v[2], b45 = v[5] < v[4], b67 = v[7] < v[6];
+                const unsigned long long m01 = b01 ? v[1] : v[0], m23 = b23 ? v[3] : v[2], m45 = b45 ? v[5] : v[4], m67 = b67 ? v[7] : v[6];
+                const int i01 = b01 ? 1 : 0, i23 = b23 ? 3 : 2, i45 = b45 ? 5 : 4, i67 = b67 ? 7 : 6;
+                const bool b03 = m23 < m01, b47 = m67 < m45;
+                const unsigned long long m03 = b03 ? m23 : m01, m47 = b47 ? m67 : m45;
+                const int i03 = b03 ? i23 : i01, i47 = b47 ? i67 : i45;
+                const bool b07 = m47 < m03;
+                const unsigned long long mk = b07 ? m47 : m03;
+                if (!(mk < k)) break;
+                at(c) = mk;
+                c = l + (b07 ? i47 : i03);
+            }
+            at(c) = k;
+        }
+    }
+    __device__ __forceinline__ int pop() {
+        const int top = peek();
+        drop();
+        return top;
+    }
+};
+
+static __host__ __device__ __forceinline__ int64_t pghi_heap_stride(int64_t n) { return ((n + 15) & ~(int64_t)7) + 8; }   // entries per clip, a multiple of 8
+
 __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
     const int64_t b = blockIdx.x;
     const int T = p.T, F = p.F, n = T * F;
@@ -107,18 +172,9 @@ __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
 
     // gradients on demand, each a chain of single rounded float32 operations in the reference's order:
     //   fgrad = ((y[k+1] - y[k-1]) / 2) / fmul + (2 pi hop / n_fft) k      tgrad = -fmul ((y[t+1] - y[t-1]) / 2) + pi
-    // with replicated edges (np.pad(..., mode="edge"))
-    auto fgrad = [&](int t, int k) {
-        const float* row = logm + t * F;
-        const float d = __fmul_rn(__fsub_rn(row[min(k + 1, F - 1)], row[max(k - 1, 0)]), 0.5f);
-        return __fadd_rn(__fdiv_rn(d, p.fmul), __fmul_rn(p.kstep, (float)k));
-    };
-    auto tgrad = [&](int t, int k) {
-        const float d = __fmul_rn(__fsub_rn(logm[min(t + 1, T - 1) * F + k], logm[max(t - 1, 0) * F + k]), 0.5f);
-        return __fadd_rn(__fmul_rn(-p.fmul, d), 3.14159265358979323846f);
-    };
+    // with replicated edges (np.pad(..., mode="edge")); see the walk
 
-    Heap h{reinterpret_cast<unsigned long long*>(p.hkey) + b * n, 0};
+    Heap8 h{reinterpret_cast<unsigned long long*>(p.hkey) + b * pghi_heap_stride(n), 0};
     for (;;) {
         // ---- seed: the loudest unvisited bin, FIRST index on ties like np.argmax ----
         float bv = -1.f;
@@ -151,27 +207,45 @@ __global__ void __launch_bounds__(256) pghi_kernel(const PghiParams p) {
             h.push(Heap::make(top, seed));
             s[seed] = abstol;
             while (h.n > 0) {
-                const int i = h.pop();
+                const int i = h.peek();
                 const int t = i / F, k = i - t * F;
+                // every load of this step first — the four neighbours' magnitudes, the bin's phase and the 3 x 3 patch of
+                // log-magnitudes the six gradients read (edges replicated like np.pad(mode="edge")) — so that they are in
+                // flight while the heap sifts; the arithmetic below is the reference's, one rounded float32 operation per step
+                const bool hn = t + 1 < T, hp = t > 0, hr = k + 1 < F, hl = k > 0;
+                const int tn = min(t + 1, T - 1) * F, tp = max(t - 1, 0) * F, t0 = t * F, kr = min(k + 1, F - 1), kl = max(k - 1, 0);
+                const float sn = hn ? s[i + F] : 0.f, sp = hp ? s[i - F] : 0.f, sr = hr ? s[i + 1] : 0.f, sl = hl ? s[i - 1] : 0.f;
                 const float ph = phase[i];
-                if (t + 1 < T && s[i + F] > abstol) {
-                    phase[i + F] = __fadd_rn(ph, __fmul_rn(__fadd_rn(fgrad(t, k), fgrad(t + 1, k)), 0.5f));
-                    h.push(Heap::make(s[i + F], i + F));
+                const float y0l = logm[t0 + kl], y0r = logm[t0 + kr];
+                const float ynl = logm[tn + kl], ynk = logm[tn + k], ynr = logm[tn + kr];
+                const float ypl = logm[tp + kl], ypk = logm[tp + k], ypr = logm[tp + kr];
+                h.drop();
+                auto fgv = [&](float right, float left) {        // fgrad of a row at bin k
+                    return __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(right, left), 0.5f), p.fmul), __fmul_rn(p.kstep, (float)k));
+                };
+                auto tgv = [&](float next, float prev) {         // tgrad of a column between frames t - 1 and t + 1
+                    return __fadd_rn(__fmul_rn(-p.fmul, __fmul_rn(__fsub_rn(next, prev), 0.5f)), 3.14159265358979323846f);
+                };
+                const float f0 = fgv(y0r, y0l), t0g = tgv(ynk, ypk);
+                if (hn && sn > abstol) {
+                    phase[i + F] = __fadd_rn(ph, __fmul_rn(__fadd_rn(f0, fgv(ynr, ynl)), 0.5f));
+                    h.push(Heap::make(sn, i + F));
                     s[i + F] = abstol;
                 }
-                if (t > 0 && s[i - F] > abstol) {
-                    phase[i - F] = __fsub_rn(ph, __fmul_rn(__fadd_rn(fgrad(t, k), fgrad(t - 1, k)), 0.5f));
-                    h.push(Heap::make(s[i - F], i - F));
+                if (hp && sp > abstol) {
+                    phase[i - F] = __fsub_rn(ph, __fmul_rn(__fadd_rn(f0, fgv(ypr, ypl)), 0.5f));
+                    h.push(Heap::make(sp, i - F));
                     s[i - F] = abstol;
                 }
-                if (k + 1 < F && s[i + 1] > abstol) {
-                    phase[i + 1] = __fadd_rn(ph, __fmul_rn(__fadd_rn(tgrad(t, k), tgrad(t, k + 1)), 0.5f));
-                    h.push(Heap::make(s[i + 1], i + 1));
+                if (hr && sr > abstol) {
+                    // tgrad(t, k + 1): the column to the right, kstep-free
+                    phase[i + 1] = __fadd_rn(ph, __fmul_rn(__fadd_rn(t0g, tgv(ynr, ypr)), 0.5f));
+                    h.push(Heap::make(sr, i + 1));
                     s[i + 1] = abstol;
                 }
-                if (k > 0 && s[i - 1] > abstol) {
-                    phase[i - 1] = __fsub_rn(ph, __fmul_rn(__fadd_rn(tgrad(t, k), tgrad(t, k - 1)), 0.5f));
-                    h.push(Heap::make(s[i - 1], i - 1));
+                if (hl && sl > abstol) {
+                    phase[i - 1] = __fsub_rn(ph, __fmul_rn(__fadd_rn(t0g, tgv(ynl, ypl)), 0.5f));
+                    h.push(Heap::make(sl, i - 1));
                     s[i - 1] = abstol;
                 }
             }
@@ -461,7 +535,8 @@ using namespace acids;
 
 extern "C" ACIDS_API int64_t acids_pghi_workspace_bytes(int64_t B, int64_t n_frames, int n_bins) {
     if (B < 0 || n_frames < 0 || n_bins < 0) return 0;
-    return B * n_frames * n_bins * 16;          // log|X|, |X| to visit (4 bytes each) and one 8-byte heap entry per bin
+    // log|X| and |X| to visit (4 bytes per bin each), 64 bytes of alignment, one 8-byte heap entry per bin + the heap's slack
+    return B * n_frames * n_bins * 8 + 64 + B * pghi_heap_stride(n_frames * (int64_t)n_bins) * 8;
 }
 
 extern "C" ACIDS_API int acids_pghi(const float* mag, int64_t B, int64_t n_frames, int n_bins, float gamma, int n_fft, int hop,
@@ -480,7 +555,8 @@ extern "C" ACIDS_API int acids_pghi(const float* mag, int64_t B, int64_t n_frame
     p.kstep = (float)(2.0 * 3.14159265358979323846 * (double)hop / (double)n_fft);
     p.tol = tol; p.abstol = eps;
     float* w = static_cast<float*>(workspace);
-    p.logm = w; p.s = w + n; p.hkey = w + 2 * n;       // 2 n floats = n 64-bit heap entries (8-byte aligned: n floats each before)
+    p.logm = w; p.s = w + n;
+    p.hkey = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(w + 2 * n) + 63) & ~(uintptr_t)63);      // the heaps' 64-byte lines
     p.phase = phase;
     pghi_kernel<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ACIDS_CHECK_LAUNCH("pghi");

@@ -69,12 +69,21 @@ struct Band {
     Tensor meta, coef;
     acids_band b{nullptr, nullptr, 0, 0, 0};
 };
+// Identity of a tensor's buffer for the two host-side caches below.  A raw data pointer is not one: the caching allocator hands
+// a freed bank's address to the next bank of the same size (the metadata of a 513 -> 128 and of a 1025 -> 128 bank are equally
+// long).  The StorageImpl's address is, as long as somebody holds a weak reference to it — which every cache entry does; a weak
+// reference keeps the small StorageImpl object alive, not the device memory.
+using WeakStorage = c10::weak_intrusive_ptr<c10::StorageImpl>;
+using BufferId = std::tuple<const void*, int64_t, int64_t, int64_t>;       // StorageImpl, offset, numel, version
+BufferId buffer_id(const Tensor& t) {
+    return std::make_tuple((const void*)t.storage().unsafeGetStorageImpl(), (int64_t)t.storage_offset(), (int64_t)t.numel(), (int64_t)t._version());
+}
 Band band_of(const OptTensor& meta, const OptTensor& coef, at::Device d) {
     Band r;
     if (!meta.has_value() || !coef.has_value()) return r;
     static std::mutex mu;
-    static std::map<std::tuple<const void*, int64_t, int64_t>, std::pair<int, int>> cache;      // -> (n_out, n_in)
-    const auto key = std::make_tuple((const void*)meta->data_ptr(), (int64_t)meta->numel(), (int64_t)meta->_version());
+    static std::map<BufferId, std::tuple<int, int, WeakStorage>> cache;      // -> (n_out, n_in, what pins the identity)
+    const auto key = buffer_id(*meta);
     std::pair<int, int> dims;
     {
         std::lock_guard<std::mutex> lock(mu);
@@ -87,9 +96,9 @@ Band band_of(const OptTensor& meta, const OptTensor& coef, at::Device d) {
             TORCH_CHECK(n_out >= 0, "acids_b200: malformed banded-matrix metadata");
             const int n_in = meta->numel() >= 2 ? meta->select(0, meta->numel() - 2).item<int>() : -1;
             if (cache.size() > 64) cache.clear();
-            it = cache.emplace(key, std::make_pair((int)n_out, n_in)).first;
+            it = cache.emplace(key, std::make_tuple((int)n_out, n_in, meta->storage().getWeakStorageImpl())).first;
         }
-        dims = it->second;
+        dims = std::make_pair(std::get<0>(it->second), std::get<1>(it->second));
     }
     r.meta = meta->to(d, at::kInt).contiguous();
     r.coef = coef->to(d, at::kFloat).contiguous();
@@ -453,12 +462,12 @@ Tensor griffinlim_update(const Tensor& rebuilt, const Tensor& tprev, const Tenso
 bool envelope_ok(const Tensor& window, int64_t n_fft, int64_t hop, int64_t n_frames) {
     const int64_t t_eff = std::min<int64_t>(n_frames, 2 * ((n_fft + hop - 1) / hop) + 2);
     static std::mutex mu;
-    static std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int64_t>, bool> cache;
-    const auto key = std::make_tuple((const void*)window.data_ptr(), (int64_t)window._version(), n_fft, hop, t_eff);
+    static std::map<std::tuple<BufferId, int64_t, int64_t, int64_t>, std::pair<bool, WeakStorage>> cache;
+    const auto key = std::make_tuple(buffer_id(window), n_fft, hop, t_eff);
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
-        if (it != cache.end()) return it->second;
+        if (it != cache.end()) return it->second.first;
     }
     Tensor w = window.detach().to(at::kCPU, at::kDouble).slice(0, 0, n_fft).contiguous();
     const double* wp = w.data_ptr<double>();
@@ -470,7 +479,7 @@ bool envelope_ok(const Tensor& window, int64_t n_fft, int64_t hop, int64_t n_fra
     for (int64_t i = n_fft / 2; i < length - n_fft / 2; ++i) ok = ok && std::fabs(env[i]) > 1e-11;
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() > 256) cache.clear();
-    cache[key] = ok;
+    cache.emplace(key, std::make_pair(ok, window.storage().getWeakStorageImpl()));
     return ok;
 }
 

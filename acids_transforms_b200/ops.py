@@ -139,16 +139,18 @@ _BAND_CACHE = {}
 
 
 def as_band(meta: Optional[torch.Tensor], coef: Optional[torch.Tensor]) -> Optional[BandedMatrix]:
-    """BandedMatrix view of a (meta, coef) buffer pair, cached on the buffers' identity/version."""
+    """BandedMatrix view of a (meta, coef) buffer pair, cached on the buffers' identity/version.  An entry keeps its two
+    tensors alive: a freed bank's addresses could otherwise be handed to a different bank with the same key (the metadata of
+    a 513 -> 128 and of a 1025 -> 128 bank have the same size)."""
     if meta is None or coef is None:
         return None
-    key = (meta.data_ptr(), coef.data_ptr(), meta._version, coef._version, meta.numel())
-    b = _BAND_CACHE.get(key)
-    if b is None:
+    key = (meta.data_ptr(), coef.data_ptr(), meta._version, coef._version, meta.numel(), coef.numel())
+    hit = _BAND_CACHE.get(key)
+    if hit is None:
         if len(_BAND_CACHE) > 64:
             _BAND_CACHE.clear()
-        b = _BAND_CACHE[key] = BandedMatrix.from_tensors(meta, coef)
-    return b
+        hit = _BAND_CACHE[key] = (BandedMatrix.from_tensors(meta, coef), meta, coef)
+    return hit[0]
 
 
 def _band(b: Optional[BandedMatrix], device) -> Band:
@@ -597,9 +599,9 @@ def istft_envelope_ok(window: torch.Tensor, n_fft: int, hop: int, n_frames: int)
     """
     t_eff = min(int(n_frames), 2 * ((n_fft + hop - 1) // hop) + 2)
     key = (window.data_ptr(), window._version, str(window.device), int(n_fft), int(hop), t_eff)
-    ok = _ENVELOPE_CACHE.get(key)
-    if ok is not None:
-        return ok
+    hit = _ENVELOPE_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
     w2 = window.detach().to("cpu", torch.float64)[:n_fft].numpy() ** 2
     length = n_fft + hop * (t_eff - 1)
     env = np.zeros(length, np.float64)
@@ -609,7 +611,7 @@ def istft_envelope_ok(window: torch.Tensor, n_fft: int, hop: int, n_frames: int)
     ok = core.size == 0 or bool(np.abs(core).min() > 1e-11)
     if len(_ENVELOPE_CACHE) > 256:
         _ENVELOPE_CACHE.clear()
-    _ENVELOPE_CACHE[key] = ok
+    _ENVELOPE_CACHE[key] = (ok, window)      # the entry keeps the buffer alive: its address cannot be handed to another window
     return ok
 
 

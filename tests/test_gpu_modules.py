@@ -469,3 +469,20 @@ def test_realtime_dgt_pghi_stays_on_the_device(T):
         assert y_dev.is_cuda and tuple(y_dev.shape) == (2, b - a, 128)
         assert_parity(y_dev.cpu(), y_host.cpu(), 2e-3, "RealtimeDGT pghi block %d:%d" % (a, b))
         assert float((dev_m.hgi_phase_buffer.cpu() - host_m.hgi_phase_buffer.cpu()).abs().max()) < 2e-3
+
+
+def test_bank_caches_survive_address_reuse(T):
+    """The host-side caches (a bank's dimensions, a window's overlap-add verdict) are keyed on buffer identity; a freed bank's
+    device address is handed to the next bank of the same size by the caching allocator — the metadata of a 513 -> 128 and of a
+    1025 -> 128 mel bank are equally long — and must not resurrect the old entry (the shape check then rejects the call)."""
+    x = torch.randn(2, 16384, device="cuda")
+    for n_fft in (2048, 1024, 2048, 1024, 512, 1024):
+        m = T.MFCC(n_fft=n_fft, hop_length=n_fft // 4).cuda()
+        y = m(x)
+        assert tuple(y.shape[-2:]) == (128, 1 + 16384 // (n_fft // 4))
+        del m, y
+    for n_fft in (1024, 512, 1024, 512):
+        st = T.STFT(n_fft=n_fft, hop_length=n_fft // 4).cuda()
+        X = st(x)
+        assert_parity(host(st.invert(X)), host(x)[..., :(X.shape[-2] - 1) * (n_fft // 4)], 1e-3, "round trip, n_fft %d" % n_fft)
+        del st, X
