@@ -444,22 +444,28 @@ __global__ void __launch_bounds__(32) rt_pghi_kernel(const RtPghiParams p) {
                     while ((r = q.pop()) >= 0) {
                         const unsigned lo = (unsigned)hs[r];
                         const int k = (int)(lo & 0xFFFFu);
+                        const int kr = min(k + 1, F - 1), kl = max(k - 1, 0);
+                        // every load of the step before its first store: independent shared-memory reads in flight together
+                        // instead of a chain through the branches (a lane's walk is latency, not bandwidth)
+                        const float sk = s_row[k], sr = s_row[kr], sl = s_row[kl];
+                        const float pc = ph_cur[k], pp = ph_prev[k], ek = e_row[k];
+                        const float fk = f_row[k], fr = f_row[kr], fl = f_row[kl];
+                        const int rk = rank_of[F + k], rr = rank_of[F + kr], rl = rank_of[F + kl];
                         if (!(lo >> 16)) {                       // a bin of frame f - 1: the step along time
-                            if (s_row[k] > abstol) {
-                                ph_cur[k] = __fadd_rn(ph_prev[k], e_row[k]);
-                                q.push(rank_of[F + k]);
+                            if (sk > abstol) {
+                                ph_cur[k] = __fadd_rn(pp, ek);
+                                q.push(rk);
                                 s_row[k] = abstol;
                             }
                         } else {                                 // a bin of frame f: its two neighbours
-                            const float ph = ph_cur[k], fk = f_row[k];
-                            if (k + 1 < F && s_row[k + 1] > abstol) {
-                                ph_cur[k + 1] = __fadd_rn(ph, __fmul_rn(0.5f, __fadd_rn(fk, f_row[k + 1])));
-                                q.push(rank_of[F + k + 1]);
+                            if (k + 1 < F && sr > abstol) {
+                                ph_cur[k + 1] = __fadd_rn(pc, __fmul_rn(0.5f, __fadd_rn(fk, fr)));
+                                q.push(rr);
                                 s_row[k + 1] = abstol;
                             }
-                            if (k - 1 > 0 && s_row[k - 1] > abstol) {
-                                ph_cur[k - 1] = __fsub_rn(ph, __fmul_rn(0.5f, __fadd_rn(fk, f_row[k - 1])));
-                                q.push(rank_of[F + k - 1]);
+                            if (k - 1 > 0 && sl > abstol) {
+                                ph_cur[k - 1] = __fsub_rn(pc, __fmul_rn(0.5f, __fadd_rn(fk, fl)));
+                                q.push(rl);
                                 s_row[k - 1] = abstol;
                             }
                         }

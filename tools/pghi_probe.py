@@ -44,3 +44,19 @@ if "--rt" in sys.argv or True:
             t1 = time.perf_counter()
             line += "; host restatement %.1f ms per call" % (1e3 * (t1 - t0) / 4)
         print(line)
+
+# ---- the frame-by-frame kernel alone (CUDA events around ops.rt_pghi, one frame of 513 bins per stream) ----
+from acids_transforms_b200 import ops
+rt = Tr.RealtimeDGT(n_fft=1024, hop_length=256)
+gm, eps = float(rt.gamma), float(rt.eps)
+for B in (1, 256):
+    hm, mg, hp = mag[:B, 100:102].contiguous(), mag[:B, 102:103].contiguous(), torch.zeros((B, 513), device="cuda")
+    for tol in (1e-2, 1e-6):
+        for _ in range(3):
+            ops.rt_pghi(mg, hm, hp, gm, 1024, 256, tol, eps)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(20):
+            ops.rt_pghi(mg, hm, hp, gm, 1024, 256, tol, eps)
+        e.record(); torch.cuda.synchronize()
+        print("rt_pghi kernel, %3d streams, tolerance %g: %.3f ms per frame" % (B, tol, s.elapsed_time(e) / 20))
