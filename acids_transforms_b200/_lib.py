@@ -8,7 +8,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ACIDS_B200_LIB") or os.path.join(_HERE, "libacids_b200.so")   # override: tuning builds only
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ACIDS_OK, ACIDS_EINVAL, ACIDS_ENOTSUP, ACIDS_ECUDA, ACIDS_EWORKSPACE = 0, -1, -2, -3, -4
 CONTRAST_IDS = {None: 0, "none": 0, "log1p": 1, "log": 2, "log10": 3}
@@ -60,6 +60,8 @@ _PROTOTYPES = {
     "acids_stream_synthesis": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_float, _P, _P, _P]),
     "acids_stream_roundtrip": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P]),
     "acids_pghi_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
+    "acids_mel_tc_workspace_bytes": (c_int64, [c_int]),
+    "acids_mel_tc": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int, _P, c_int64, _P, _P]),
     "acids_rt_pghi_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "acids_rt_pghi": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_int, c_int, c_float, c_float, _P, c_int64, _P, _P]),
     "acids_pghi": (c_int, [_P, c_int64, c_int64, c_int, c_float, c_int, c_int, ctypes.c_double, c_float, _P, c_int64, _P, _P]),

@@ -15,10 +15,10 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.environ.get("ACIDS_B200_OBJ") or os.path.join(PKG, "build")
 LIB = os.environ.get("ACIDS_B200_LIB") or os.path.join(PKG, "libacids_b200.so")
 SHIM = os.path.join(PKG, "libacids_b200_torch.so")       # TORCH_LIBRARY(acids_b200): csrc/torch_shim.cpp on top of the C ABI
-SOURCES = ["capi.cu", "stft_fwd.cu", "istft.cu", "spectral_repr.cu", "pointwise.cu", "mfcc_tc.cu", "stream.cu", "pghi.cu"]
+SOURCES = ["capi.cu", "stft_fwd.cu", "istft.cu", "spectral_repr.cu", "pointwise.cu", "mfcc_tc.cu", "mel_tc.cu", "stream.cu", "pghi.cu"]
 # the fused forward kernels: one translation unit per FFT plan (stft_fwd_plan.cu -DACIDS_FWD_PLAN_N=n), built in parallel
 FWD_PLANS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
-HEADERS = ["common.cuh", "fft_core.cuh", "plans.cuh", "stft_fwd_kernel.cuh", os.path.join(ROOT, "include", "acids_b200.h")]
+HEADERS = ["common.cuh", "tc_common.cuh", "fft_core.cuh", "plans.cuh", "stft_fwd_kernel.cuh", os.path.join(ROOT, "include", "acids_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

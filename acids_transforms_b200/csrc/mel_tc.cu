@@ -1,0 +1,231 @@
+// mel_tc.cu — the dense mel projection (|X|^p rows x filterbank, mel.py:38-44 / torchaudio MelScale) on the 5th-generation
+// tensor cores: SURVEY.md §7 hard part 2 / north_star "mel filterbank ... as tensor-core GEMMs", next to the banded FP32
+// epilogue the fused kernels use (DESIGN.md §6 has the measured comparison: the bank is 98 % zeros, so the banded form does
+// 1/60 of the multiplies and never materialises the spectrum; this kernel is the dense formulation, numerically faithful).
+//
+// Per tile of 128 frames:  D[128 frames x 128 mels] = S[128 x F] . BANK[F x 128], F = n_fft / 2 + 1 walked in chunks of 32.
+//   * both operands K-major in shared memory, no swizzle (8-row x 16-byte core matrices), UMMA descriptors, 3xTF32 operand
+//     split (hi + lo, three MMAs per K step of 8) for fp32 fidelity, accumulator in 128 TMEM columns;
+//   * the bank is split and laid out in the UMMA order ONCE per call by a small pack kernel; every chunk is then one
+//     contiguous 32 KB block that ONE thread moves with a bulk asynchronous copy (cp.async.bulk, the TMA engine) onto the
+//     stage's mbarrier — no warp touches the B operand;
+//   * the A chunk (128 frames x 32 bins) is loaded a chunk ahead, split and stored by the warps as conflict-free 16-byte
+//     rows while the tensor core multiplies the previous chunk (two stages, tcgen05.commit -> mbarrier frees a stage);
+//   * epilogue: tcgen05.ld 32x32b, stores coalesced along frames into [n_mels, T] (frequency-major like MelSpectrogram).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace acids {
+namespace tc {
+
+constexpr int MEL_TM = 128;       // frames per tile = MMA M
+constexpr int MEL_N = 128;        // mel bands = MMA N (banks with fewer bands are zero padded)
+constexpr int MEL_KC = 32;        // bins per pipeline stage
+constexpr int MEL_THREADS = 256;
+constexpr uint32_t MEL_A_BYTES = MEL_TM * MEL_KC * 4;      // one of hi / lo of an A chunk: 16 KB
+constexpr uint32_t MEL_B_BYTES = MEL_N * MEL_KC * 4;       // one of hi / lo of a B chunk: 16 KB
+
+struct MelParams {
+    const float* spec;        // [B, T, F] non-negative rows (|X| or |X|^2), unit stride along bins
+    int64_t B, T;
+    int F;
+    const float* bank_packed; // [n_chunks][hi, lo][MEL_N x MEL_KC] in UMMA order (mel_tc_pack_kernel)
+    int n_mels;
+    float* out;               // [B, n_mels, T]
+};
+
+// bank [F, n_mels] row-major -> per chunk of 32 bins: hi block then lo block, element (mel n, bin k) at the K-major
+// interleaved offset ((n >> 3) * 8 + (k >> 2)) * 128 + (n & 7) * 16 + (k & 3) * 4; zeros beyond F and n_mels
+__global__ void mel_tc_pack_kernel(const float* __restrict__ bank, int F, int n_mels, int n_chunks, float* __restrict__ packed) {
+    const int total = n_chunks * MEL_N * MEL_KC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i / (MEL_N * MEL_KC), r = i - c * (MEL_N * MEL_KC);
+        const int kk = r / MEL_N, n = r - kk * MEL_N;          // consecutive threads: consecutive mels of one bin (coalesced reads)
+        const int k = c * MEL_KC + kk;
+        float hi, lo;
+        split_tf32((k < F && n < n_mels) ? __ldg(bank + (size_t)k * n_mels + n) : 0.f, hi, lo);
+        const uint32_t off = (uint32_t)(((n >> 3) * (MEL_KC >> 2) + (kk >> 2)) * 128 + (n & 7) * 16 + (kk & 3) * 4) / 4;
+        float* dst = packed + (size_t)c * (2 * MEL_N * MEL_KC);
+        dst[off] = hi;
+        dst[MEL_N * MEL_KC + off] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(MEL_THREADS, 1) mel_tc_kernel(const MelParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // stage s: A hi | A lo | B hi | B lo  (4 x 16 KB)
+    constexpr uint32_t STAGE = 2 * MEL_A_BYTES + 2 * MEL_B_BYTES;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);   // [0], [1]: stage free (MMAs done); [2], [3]: B landed; [4]: accumulator done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 5);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = p.F;
+    const int n_chunks = (F + MEL_KC - 1) / MEL_KC;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(MEL_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + i)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t idesc = make_idesc_mn(MEL_TM, MEL_N);
+    constexpr uint32_t sbo = (uint32_t)(MEL_KC >> 2) * 128;      // 8-row groups are 8 core matrices (1 KB) apart, both operands
+    uint32_t ph_free[2] = {0, 0}, ph_b[2] = {0, 0}, ph_done = 0;
+    uint32_t used[2] = {0, 0};
+
+    const int64_t tiles_per_clip = (p.T + MEL_TM - 1) / MEL_TM;
+    const int64_t n_tiles = p.B * tiles_per_clip;
+    // A chunk = 128 frames x 8 blocks of 4 bins.  A warp-load covers 8 frames x 4 blocks (lane = frame % 8 + 8 * block): its
+    // 16-byte rows land as four contiguous 128-byte runs in shared memory (conflict free); 32 such pieces per chunk, 4 per warp.
+    constexpr int U = 4;
+    const int r8 = lane & 7, kbl = lane >> 3;
+    auto load_chunk = [&](int64_t tile, int kc, float (&v)[U][4]) {
+        const int64_t b = tile / tiles_per_clip;
+        const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int piece = warp * U + u;                     // 0..31: frame group (16) x block half (2)
+            const int g = piece >> 1, half = piece & 1;
+            const int64_t t = t0 + g * 8 + r8;
+            const int k = kc * MEL_KC + (half * 4 + kbl) * 4;
+            const float* src = p.spec + (b * p.T + t) * (int64_t)F + k;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[u][j] = (t < p.T && k + j < F) ? __ldg(src + j) : 0.f;
+        }
+    };
+    float v[U][4];
+    int stage = 0;
+    if ((int64_t)blockIdx.x < n_tiles) load_chunk(blockIdx.x, 0, v);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t b = tile / tiles_per_clip;
+        const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
+        for (int kc = 0; kc < n_chunks; ++kc, stage ^= 1) {
+            unsigned char* st = smem + stage * STAGE;
+            // the MMAs that read this stage two chunks ago have completed
+            if (used[stage]) {
+                mbar_wait_parity(mbar + stage, ph_free[stage]);
+                ph_free[stage] ^= 1;
+                used[stage] = 0;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // B chunk: one bulk copy of 32 KB (hi block, lo block), completing on the stage's "landed" mbarrier
+            if (tid == 0) {
+                const uint32_t bytes = 2 * MEL_B_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + 2 + stage)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(st + 2 * MEL_A_BYTES)),
+                             "l"(p.bank_packed + (size_t)kc * (2 * MEL_N * MEL_KC)), "r"(bytes), "r"(smem_u32(mbar + 2 + stage))
+                             : "memory");
+            }
+            // A chunk: split and store
+            unsigned char* ah = st;
+            unsigned char* al = st + MEL_A_BYTES;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int piece = warp * U + u;
+                const int g = piece >> 1, half = piece & 1;
+                float4 hi, lo;
+                split_tf32(v[u][0], hi.x, lo.x);
+                split_tf32(v[u][1], hi.y, lo.y);
+                split_tf32(v[u][2], hi.z, lo.z);
+                split_tf32(v[u][3], hi.w, lo.w);
+                const uint32_t off = (uint32_t)(g * (MEL_KC >> 2) + half * 4 + kbl) * 128 + (uint32_t)r8 * 16;   // row g * 8 + r8, block half * 4 + kbl
+                *reinterpret_cast<float4*>(ah + off) = hi;
+                *reinterpret_cast<float4*>(al + off) = lo;
+            }
+            if (kc + 1 < n_chunks) load_chunk(tile, kc + 1, v);
+            else if (tile + gridDim.x < n_tiles) load_chunk(tile + gridDim.x, 0, v);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    mbar_wait_parity(mbar + 2 + stage, ph_b[stage]);         // the bank chunk has landed
+                    const uint32_t sa_hi = smem_u32(ah), sa_lo = smem_u32(al);
+                    const uint32_t sb_hi = smem_u32(st + 2 * MEL_A_BYTES), sb_lo = sb_hi + MEL_B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < MEL_KC / 8; ++ks) {         // one MMA consumes K = 8 (two core matrices of 4 TF32)
+                        const uint32_t ko = (uint32_t)ks * 256;
+                        mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, (kc | ks) ? 1u : 0u);
+                        mma_tf32(tmem_d, make_desc(sa_lo + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, 1);
+                        mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_lo + ko, 128, sbo), idesc, 1);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + stage)) : "memory");
+                    if (kc == n_chunks - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 4)) : "memory");
+                }
+                __syncwarp();
+            }
+            ph_b[stage] ^= 1;
+            used[stage] = 1;
+        }
+        mbar_wait_parity(mbar + 4, ph_done);
+        ph_done ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: a warp reads its TMEM lane quadrant (32 frames); warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones
+        const int quad = warp & 3;
+        for (int chunk = warp >> 2; chunk * 16 < MEL_N; chunk += MEL_THREADS / 128) {
+            if (chunk * 16 >= p.n_mels) break;
+            uint32_t r[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chunk * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int64_t t = t0 + quad * 32 + lane;
+            if (t < p.T) {
+                float* o = p.out + (b * p.n_mels + chunk * 16) * p.T + t;
+#pragma unroll
+                for (int n = 0; n < 16; ++n)
+                    if (chunk * 16 + n < p.n_mels) stg_stream1(o + (int64_t)n * p.T, __uint_as_float(r[n]));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MEL_N) : "memory");
+}
+
+}  // namespace tc
+}  // namespace acids
+
+using namespace acids;
+
+extern "C" ACIDS_API int64_t acids_mel_tc_workspace_bytes(int n_bins) {
+    if (n_bins <= 0) return 0;
+    const int64_t n_chunks = (n_bins + tc::MEL_KC - 1) / tc::MEL_KC;
+    return n_chunks * 2 * tc::MEL_N * tc::MEL_KC * 4;
+}
+
+extern "C" ACIDS_API int acids_mel_tc(const float* spec, int64_t B, int64_t n_frames, int n_bins, const float* bank, int n_mels,
+                            void* workspace, int64_t workspace_bytes, float* out, void* stream) {
+    ACIDS_REQUIRE(spec && bank && out, ACIDS_EINVAL, "mel_tc: NULL pointer");
+    ACIDS_REQUIRE(B >= 0 && n_frames >= 0 && n_bins >= 1, ACIDS_EINVAL, "mel_tc: bad sizes");
+    ACIDS_REQUIRE(n_mels >= 1 && n_mels <= tc::MEL_N, ACIDS_EINVAL, "mel_tc: 1 <= n_mels <= %d (got %d)", tc::MEL_N, n_mels);
+    if (B == 0 || n_frames == 0) return ACIDS_OK;
+    ACIDS_REQUIRE(workspace && workspace_bytes >= acids_mel_tc_workspace_bytes(n_bins) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, ACIDS_EINVAL,
+                  "mel_tc: a 16-byte aligned workspace of %lld bytes is required", (long long)acids_mel_tc_workspace_bytes(n_bins));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n_chunks = (n_bins + tc::MEL_KC - 1) / tc::MEL_KC;
+    tc::mel_tc_pack_kernel<<<(n_chunks * 16 < 1024 ? n_chunks * 16 : 1024), 256, 0, st>>>(bank, n_bins, n_mels, n_chunks, static_cast<float*>(workspace));
+    ACIDS_CHECK_LAUNCH("mel_tc_pack");
+    tc::MelParams p{spec, B, n_frames, n_bins, static_cast<const float*>(workspace), n_mels, out};
+    const size_t smem = (size_t)2 * (2 * tc::MEL_A_BYTES + 2 * tc::MEL_B_BYTES) + 64;
+    ACIDS_REQUIRE(cudaFuncSetAttribute(tc::mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess, ACIDS_ECUDA,
+                  "mel_tc: cannot reserve %zu B of shared memory", smem);
+    int64_t grid = B * ((n_frames + tc::MEL_TM - 1) / tc::MEL_TM);
+    if (grid > (int64_t)num_sms()) grid = (int64_t)num_sms();
+    tc::mel_tc_kernel<<<(unsigned)grid, tc::MEL_THREADS, smem, st>>>(p);
+    ACIDS_CHECK_LAUNCH("mel_tc");
+    return ACIDS_OK;
+}

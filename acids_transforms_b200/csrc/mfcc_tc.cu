@@ -14,6 +14,7 @@
 // formulation north_star asks for, measured next to the FP32 register-tiled kernel (pointwise.cu).
 #include <float.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace acids {
 
@@ -24,41 +25,14 @@ constexpr int NP = 48;       // padded coefficient count = MMA N (multiple of 8 
 constexpr int KMAX = 128;    // n_mels <= 128, multiple of 8
 constexpr int TMEM_COLS = 64;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), K-major, SWIZZLE_NONE
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);                 // start address, bits [0, 14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;       // leading byte offset, bits [16, 30)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;       // stride byte offset, bits [32, 46)
-    d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
-    return d;                                               // base offset 0, lbo mode 0, layout type 0 (no swizzle)
-}
-
 // instruction descriptor (InstrDescriptor): D = F32, A = B = TF32, both K-major, dense, M = 128, N = NP
 __host__ __device__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // byte offset of element (row r, column k) in a K-major interleaved operand with K columns
 __device__ __forceinline__ uint32_t op_offset(int r, int k, int K) {
     return (uint32_t)((r >> 3) * (K >> 2) * 128 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);     // sign + exponent + 10 mantissa bits
-    lo = x - hi;                                                // exact; the tensor core reads its TF32 prefix
 }
 
 struct Params {

@@ -789,6 +789,27 @@ def rt_pghi(mag, hist_mag, hist_phase, gamma: float, n_fft: int, hop: int, tol: 
     return _ret(out.reshape(tuple(batch) + (n, F)), mag)
 
 
+def mel_tc(spec, bank) -> torch.Tensor:
+    """Dense mel projection on the tensor cores (3xTF32, csrc/mel_tc.cu): spec [..., T, F] (|X| or |X|^2) x bank [F, n_mels]
+    (n_mels <= 128) -> [..., n_mels, T], the layout of torchaudio's MelSpectrogram (mel.py:38-44)."""
+    lib = _lib.load()
+    sd = _dev(spec).to(torch.float32)
+    if sd.ndim < 2:
+        raise IndexError("Dimension out of range (expected a [..., frames, bins] spectrum)")
+    sf, batch = _flat_batch(sd, 2)
+    B, T, F = sf.shape
+    bk = bank.to(sf.device, torch.float32).contiguous()
+    if bk.ndim != 2 or bk.shape[0] != F:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %s)" % (B * T, F, "x".join(str(v) for v in bk.shape)))
+    n_mels = int(bk.shape[1])
+    out = torch.empty((B, n_mels, T), dtype=torch.float32, device=sf.device)
+    nbytes = int(lib.acids_mel_tc_workspace_bytes(F))
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=sf.device)
+    with torch.cuda.device(sf.device):
+        _run(out, lib.acids_mel_tc, _ptr(sf), B, T, F, _ptr(bk), n_mels, _ptr(ws), nbytes, _ptr(out), _stream(sf.device))
+    return _ret(out.reshape(tuple(batch) + (n_mels, T)), spec)
+
+
 # ------------------------------------------------------------------------------------------------
 # (5) mu-law / one-hot
 # ------------------------------------------------------------------------------------------------

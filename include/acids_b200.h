@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACIDS_ABI_VERSION 4
+#define ACIDS_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define ACIDS_API __attribute__((visibility("default")))
@@ -261,6 +261,16 @@ ACIDS_API int acids_stream_synthesis(const float* X, int64_t B, int64_t n, int n
 ACIDS_API int acids_stream_roundtrip(const float* x, int64_t B, int64_t n, int n_fft, int hop, const float* window,
                            const float* inv_window, float gain, float* tail, float* carry, float* X_out, float* out,
                            void* stream);
+
+/* Dense mel projection on the tensor cores (mel.py:38-44, torchaudio MelScale: spec @ fb): spec float32 [B, n_frames, n_bins]
+ * (|X| or |X|^2 rows, unit stride) x bank float32 [n_bins, n_mels] (n_mels <= 128) -> out float32 [B, n_mels, n_frames].
+ * tcgen05.mma kind::tf32 with 3xTF32 operand splitting (fp32 fidelity), accumulator in TMEM, the packed bank streamed by bulk
+ * asynchronous copies.  The fused kernels (acids_melspec_fwd, acids_stft_mag_fwd) use the banded FP32 form instead, which
+ * never materialises the spectrum; this is the dense formulation for callers that hold one.  workspace (16-byte aligned):
+ * acids_mel_tc_workspace_bytes(n_bins).                                                                                     */
+ACIDS_API int64_t acids_mel_tc_workspace_bytes(int n_bins);
+ACIDS_API int acids_mel_tc(const float* spec, int64_t B, int64_t n_frames, int n_bins, const float* bank, int n_mels, void* workspace,
+                 int64_t workspace_bytes, float* out, void* stream);
 
 /* ---- (4c) phase-gradient heap integration (PGHI): DGT.pghi, dgt.py:156-236 — the reference's default inversion of a magnitude ----
  * mag float32 [B, n_frames, n_bins] (clamped at eps inside) -> phase float32 of the same shape.  One CTA per clip: log-magnitude,

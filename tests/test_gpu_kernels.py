@@ -415,6 +415,44 @@ def test_mfcc_dct_tensor_cores(ops):
         assert_parity(host(got), host(ref32), REL, "tc dct vs fp32 kernel")
 
 
+def test_mel_projection_tensor_cores(ops):
+    """The dense mel projection on tcgen05 (3xTF32, bank chunks by bulk asynchronous copy) against a float64 matmul, against
+    the banded FP32 kernel on the same spectrum, and on the reference's own MelSpectrogram fixture; ragged frame counts,
+    bin counts that are not a multiple of the 32-bin chunk, banks narrower than the 128-column tile."""
+    from acids_transforms_b200.transforms.spectral_repr import melscale_fbanks
+    g = torch.Generator(device="cuda").manual_seed(17)
+    for B, T, n_fft, n_mels in [(3, 300, 2048, 128), (2, 129, 1024, 128), (1, 128, 512, 64), (2, 77, 256, 40), (1, 1, 64, 8)]:
+        F = n_fft // 2 + 1
+        spec = torch.rand((B, T, F), generator=g, device="cuda") ** 4 * 100.0
+        fb = melscale_fbanks(F, 0.0, 22050.0, n_mels, 44100).cuda()
+        got = ops.mel_tc(spec, fb)
+        assert tuple(got.shape) == (B, n_mels, T)
+        want = torch.einsum("btf,fm->bmt", spec.double(), fb.double())
+        assert_parity(host(got), host(want.float()), 1e-5, "tc mel vs float64 (n_fft %d, %d mels, %d frames)" % (n_fft, n_mels, T))
+        banded = ops.mag_epilogue(torch.complex(spec, torch.zeros_like(spec)), ops.BandedMatrix(fb.cpu()), None, 1e-7, None, None, False)
+        assert_parity(host(got), host(banded.transpose(-1, -2)), 1e-5, "tc mel vs the banded FP32 kernel")
+    # a dense random matrix (nothing banded about it) and the error message of a mismatched bank
+    spec = torch.rand((2, 200, 513), generator=g, device="cuda")
+    w = torch.randn((513, 96), generator=g, device="cuda")
+    want = torch.einsum("btf,fm->bmt", spec.double(), w.double())
+    # signed weights cancel: the 3xTF32 error is ~2^-22 of sum |a||b|, i.e. of the peak, not of each (small) element
+    assert_parity(host(ops.mel_tc(spec, w)), host(want.float()), REL, "tc projection, dense random matrix")
+    with pytest.raises(RuntimeError, match="cannot be multiplied"):
+        ops.mel_tc(spec, w[:512])
+    # the reference's MelSpectrogram (golden "mfcc": n_fft 2048-class fixture): power spectrum from the STFT kernel, then the GEMM
+    gm = load_golden("mfcc")
+    if "y" in gm and "x" in gm:
+        x = cu(gm["x"])
+        n_mels, Tm = gm["y"].shape[-2], gm["y"].shape[-1]
+        L = x.shape[-1]
+        hop = L // (Tm - 1)
+        for n_fft in (4 * hop,):
+            X = ops.stft_fwd(x.reshape(-1, L), torch.hann_window(n_fft).cuda(), n_fft, hop, True)
+            fb = melscale_fbanks(n_fft // 2 + 1, 0.0, 22050.0, n_mels, 44100).cuda()
+            got = ops.mel_tc(X.abs() ** 2, fb).reshape(gm["y"].shape)
+            assert_parity(host(got), gm["y"], REL, "tc mel vs the reference's MelSpectrogram")
+
+
 def test_griffinlim_update(ops):
     """The fused fast-Griffin-Lim update against the eager formula (torchaudio functional.py:336-350)."""
     g = torch.Generator(device="cuda").manual_seed(3)

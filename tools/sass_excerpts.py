@@ -13,6 +13,7 @@ WANT = [
     ("complex STFT, n_fft 1024", r"stft_fwd_kernelINS_4PlanILi1024ELi32ELi8ELi8ELi8ELi1EEELi0ELi1ELi0ELi0ELb0ELb0E"),
     ("ISTFT + overlap-add, n_fft 1024", r"istft_ola_kernelINS_4PlanILi1024ELi32ELi8ELi8ELi8ELi1EEEE"),
     ("MFCC DCT on tcgen05 (3xTF32)", r"mfcc_dct_tc"),
+    ("dense mel projection on tcgen05 (3xTF32, bank chunks by bulk asynchronous copy)", r"mel_tc_kernel"),
     ("streaming round trip, n_fft 1024", r"stream_step_kernelINS_4PlanILi1024ELi32ELi8ELi8ELi8ELi1EEES2_Lb1ELb1E"),
 ]
 CLASSES = [("packed FP32 (FADD2 / FMUL2 / FFMA2)", r"^(FADD2|FMUL2|FFMA2)"), ("scalar FP32 (FADD / FMUL / FFMA)", r"^(FADD|FMUL|FFMA)\b"),
@@ -27,9 +28,11 @@ def main():
     txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", txt)
     print("# SASS excerpts (round 2)\n\n`cuobjdump -sass acids_transforms_b200/libacids_b200.so` (sm_100a, nvcc 12.9), static instruction counts per kernel.\n"
-          "Whole library: %d `UTC*MMA`, %d `LDTM`, %d packed `F{ADD,MUL,FMA}2`, %d `LDGSTS`, 0 `UTMALDG` (no kernel here streams tiles large\n"
-          "enough to amortise a tensor map: frames are 4 KB and overlap by 75 %%, rows are gathered per thread).\n" % (
-              len(re.findall(r"\bUTC\w*MMA", txt)), len(re.findall(r"\bLDTM", txt)), len(re.findall(r"\bF(ADD|MUL|FMA)2\b", txt)), len(re.findall(r"\bLDGSTS", txt))))
+          "Whole library: %d `UTC*MMA`, %d `LDTM`, %d packed `F{ADD,MUL,FMA}2`, %d `LDGSTS`, %d `UBLKCP` (bulk asynchronous copies through the TMA\n"
+          "engine: the packed mel bank of mel_tc.cu), 0 `UTMALDG` (no kernel here streams tiles that a tensor map would describe: frames\n"
+          "are 4 KB and overlap by 75 %%, rows are gathered per thread).\n" % (
+              len(re.findall(r"\bUTC\w*MMA", txt)), len(re.findall(r"\bLDTM", txt)), len(re.findall(r"\bF(ADD|MUL|FMA)2\b", txt)), len(re.findall(r"\bLDGSTS", txt)),
+              len(re.findall(r"\bUBLKCP", txt))))
     for title, pat in WANT:
         hit = [f for f in funcs if re.search(pat, f.split("\n", 1)[0])]
         if not hit:
@@ -47,7 +50,7 @@ def main():
         top = ", ".join("%s %d" % kv for kv in c.most_common(12))
         print("\nMost frequent opcodes: %s.\n" % top)
         lines = [l.strip() for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4,}\*/", l)]
-        keep = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in lines if re.search(r"FFMA2|FADD2|FMUL2|UTC|LDTM|LDGSTS|LDS\.128|STS\.128", l)][:14]
+        keep = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in lines if re.search(r"FFMA2|FADD2|FMUL2|UTC|LDTM|LDGSTS|UBLKCP|LDS\.128|STS\.128", l)][:14]
         print("```\n%s\n```\n" % "\n".join(keep))
 
 
