@@ -20,7 +20,13 @@ namespace tc {
 
 constexpr int MEL_TM = 128;       // frames per tile = MMA M
 constexpr int MEL_N = 128;        // mel bands = MMA N (banks with fewer bands are zero padded)
-constexpr int MEL_KC = 32;        // bins per pipeline stage
+#ifndef ACIDS_MEL_TC_KC
+#define ACIDS_MEL_TC_KC 16
+#endif
+#ifndef ACIDS_MEL_TC_CTAS
+#define ACIDS_MEL_TC_CTAS 3
+#endif
+constexpr int MEL_KC = ACIDS_MEL_TC_KC;   // bins per pipeline stage (16: 64 KB of stages per CTA, three CTAs per SM; 32: one)
 constexpr int MEL_THREADS = 256;
 constexpr uint32_t MEL_A_BYTES = MEL_TM * MEL_KC * 4;      // one of hi / lo of an A chunk: 16 KB
 constexpr uint32_t MEL_B_BYTES = MEL_N * MEL_KC * 4;       // one of hi / lo of a B chunk: 16 KB
@@ -51,9 +57,9 @@ __global__ void mel_tc_pack_kernel(const float* __restrict__ bank, int F, int n_
     }
 }
 
-__global__ void __launch_bounds__(MEL_THREADS, 1) mel_tc_kernel(const MelParams p) {
+__global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(const MelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // stage s: A hi | A lo | B hi | B lo  (4 x 16 KB)
+    // stage s: A hi | A lo | B hi | B lo  (4 x 128 x MEL_KC floats)
     constexpr uint32_t STAGE = 2 * MEL_A_BYTES + 2 * MEL_B_BYTES;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);   // [0], [1]: stage free (MMAs done); [2], [3]: B landed; [4]: accumulator done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 5);
@@ -82,15 +88,17 @@ __global__ void __launch_bounds__(MEL_THREADS, 1) mel_tc_kernel(const MelParams 
     const int64_t n_tiles = p.B * tiles_per_clip;
     // A chunk = 128 frames x 8 blocks of 4 bins.  A warp-load covers 8 frames x 4 blocks (lane = frame % 8 + 8 * block): its
     // 16-byte rows land as four contiguous 128-byte runs in shared memory (conflict free); 32 such pieces per chunk, 4 per warp.
-    constexpr int U = 4;
+    constexpr int HALVES = MEL_KC / 16;                       // groups of four 4-bin blocks per chunk
+    constexpr int U = 16 * HALVES / (MEL_THREADS / 32);       // pieces per warp
+    static_assert(U >= 1 && U * (MEL_THREADS / 32) == 16 * HALVES, "a pass of the warps covers a chunk");
     const int r8 = lane & 7, kbl = lane >> 3;
     auto load_chunk = [&](int64_t tile, int kc, float (&v)[U][4]) {
         const int64_t b = tile / tiles_per_clip;
         const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int piece = warp * U + u;                     // 0..31: frame group (16) x block half (2)
-            const int g = piece >> 1, half = piece & 1;
+            const int piece = warp * U + u;                     // frame group (16) x group of four blocks (HALVES)
+            const int g = piece / HALVES, half = piece % HALVES;
             const int64_t t = t0 + g * 8 + r8;
             const int k = kc * MEL_KC + (half * 4 + kbl) * 4;
             const float* src = p.spec + (b * p.T + t) * (int64_t)F + k;
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(MEL_THREADS, 1) mel_tc_kernel(const MelParams 
                 used[stage] = 0;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // B chunk: one bulk copy of 32 KB (hi block, lo block), completing on the stage's "landed" mbarrier
+            // B chunk: one bulk copy (hi block, lo block: 2 x 128 x MEL_KC floats), completing on the stage's "landed" mbarrier
             if (tid == 0) {
                 const uint32_t bytes = 2 * MEL_B_BYTES;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + 2 + stage)), "r"(bytes) : "memory");
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(MEL_THREADS, 1) mel_tc_kernel(const MelParams 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int piece = warp * U + u;
-                const int g = piece >> 1, half = piece & 1;
+                const int g = piece / HALVES, half = piece % HALVES;
                 float4 hi, lo;
                 split_tf32(v[u][0], hi.x, lo.x);
                 split_tf32(v[u][1], hi.y, lo.y);
@@ -224,7 +232,7 @@ extern "C" ACIDS_API int acids_mel_tc(const float* spec, int64_t B, int64_t n_fr
     ACIDS_REQUIRE(cudaFuncSetAttribute(tc::mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess, ACIDS_ECUDA,
                   "mel_tc: cannot reserve %zu B of shared memory", smem);
     int64_t grid = B * ((n_frames + tc::MEL_TM - 1) / tc::MEL_TM);
-    if (grid > (int64_t)num_sms()) grid = (int64_t)num_sms();
+    if (grid > (int64_t)ACIDS_MEL_TC_CTAS * num_sms()) grid = (int64_t)ACIDS_MEL_TC_CTAS * num_sms();
     tc::mel_tc_kernel<<<(unsigned)grid, tc::MEL_THREADS, smem, st>>>(p);
     ACIDS_CHECK_LAUNCH("mel_tc");
     return ACIDS_OK;
