@@ -3,13 +3,13 @@
 // epilogue the fused kernels use (DESIGN.md §6 has the measured comparison: the bank is 98 % zeros, so the banded form does
 // 1/60 of the multiplies and never materialises the spectrum; this kernel is the dense formulation, numerically faithful).
 //
-// Per tile of 128 frames:  D[128 frames x 128 mels] = S[128 x F] . BANK[F x 128], F = n_fft / 2 + 1 walked in chunks of 32.
+// Per tile of 128 frames:  D[128 frames x 128 mels] = S[128 x F] . BANK[F x 128], F = n_fft / 2 + 1 walked in chunks of MEL_KC.
 //   * both operands K-major in shared memory, no swizzle (8-row x 16-byte core matrices), UMMA descriptors, 3xTF32 operand
 //     split (hi + lo, three MMAs per K step of 8) for fp32 fidelity, accumulator in 128 TMEM columns;
 //   * the bank is split and laid out in the UMMA order ONCE per call by a small pack kernel; every chunk is then one
-//     contiguous 32 KB block that ONE thread moves with a bulk asynchronous copy (cp.async.bulk, the TMA engine) onto the
-//     stage's mbarrier — no warp touches the B operand;
-//   * the A chunk (128 frames x 32 bins) is loaded a chunk ahead, split and stored by the warps as conflict-free 16-byte
+//     contiguous block that ONE thread moves with a bulk asynchronous copy (cp.async.bulk, the TMA engine) into a ring of
+//     four stages, two chunks ahead of its MMAs, completing on the stage's mbarrier — no warp touches the B operand;
+//   * the A chunk (128 frames x MEL_KC bins) is loaded a chunk ahead, split and stored by the warps as conflict-free 16-byte
 //     rows while the tensor core multiplies the previous chunk (two stages, tcgen05.commit -> mbarrier frees a stage);
 //   * epilogue: tcgen05.ld 32x32b, stores coalesced along frames into [n_mels, T] (frequency-major like MelSpectrogram).
 #include "common.cuh"
@@ -24,12 +24,13 @@ constexpr int MEL_N = 128;        // mel bands = MMA N (banks with fewer bands a
 #define ACIDS_MEL_TC_KC 16
 #endif
 #ifndef ACIDS_MEL_TC_CTAS
-#define ACIDS_MEL_TC_CTAS 3
+#define ACIDS_MEL_TC_CTAS 2
 #endif
-constexpr int MEL_KC = ACIDS_MEL_TC_KC;   // bins per pipeline stage (16: 64 KB of stages per CTA, three CTAs per SM; 32: one)
+constexpr int MEL_KC = ACIDS_MEL_TC_KC;   // bins per pipeline stage (16: 96 KB of rings per CTA, two CTAs per SM)
 constexpr int MEL_THREADS = 256;
 constexpr uint32_t MEL_A_BYTES = MEL_TM * MEL_KC * 4;      // one of hi / lo of an A chunk: 16 KB
-constexpr uint32_t MEL_B_BYTES = MEL_N * MEL_KC * 4;       // one of hi / lo of a B chunk: 16 KB
+constexpr uint32_t MEL_B_BYTES = MEL_N * MEL_KC * 4;       // one of hi / lo of a B chunk
+constexpr int MEL_BSTAGES = 4;                             // B ring: a chunk's copy is issued two chunks before its MMAs
 
 struct MelParams {
     const float* spec;        // [B, T, F] non-negative rows (|X| or |X|^2), unit stride along bins
@@ -59,10 +60,11 @@ __global__ void mel_tc_pack_kernel(const float* __restrict__ bank, int F, int n_
 
 __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(const MelParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // stage s: A hi | A lo | B hi | B lo  (4 x 128 x MEL_KC floats)
-    constexpr uint32_t STAGE = 2 * MEL_A_BYTES + 2 * MEL_B_BYTES;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);   // [0], [1]: stage free (MMAs done); [2], [3]: B landed; [4]: accumulator done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 5);
+    // A ring: 2 stages of (hi | lo); B ring: MEL_BSTAGES stages of (hi | lo), filled two chunks ahead of their use
+    constexpr uint32_t A_STAGE = 2 * MEL_A_BYTES, B_STAGE = 2 * MEL_B_BYTES;
+    unsigned char* b_ring = smem + 2 * A_STAGE;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(b_ring + MEL_BSTAGES * B_STAGE);   // [0], [1]: A stage free (its MMAs are done); [2]: accumulator done; [3 ...]: B stage landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3 + MEL_BSTAGES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F = p.F;
     const int n_chunks = (F + MEL_KC - 1) / MEL_KC;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + i)), "r"(1) : "memory");
+        for (int i = 0; i < 3 + MEL_BSTAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + i)), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -81,8 +83,28 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t idesc = make_idesc_mn(MEL_TM, MEL_N);
     constexpr uint32_t sbo = (uint32_t)(MEL_KC >> 2) * 128;      // 8-row groups are 8 core matrices (1 KB) apart, both operands
-    uint32_t ph_free[2] = {0, 0}, ph_b[2] = {0, 0}, ph_done = 0;
+    uint32_t ph_free[2] = {0, 0}, ph_done = 0;
     uint32_t used[2] = {0, 0};
+    uint32_t ph_b = 0;            // bit s: parity the B stage s completes with next
+    // this CTA's chunks, numbered across its tiles: chunk gc multiplies bank chunk gc % n_chunks from B stage gc % MEL_BSTAGES,
+    // and its copy is issued while chunk gc - 2 is being prepared (the stage's last reader, chunk gc - MEL_BSTAGES, is long done:
+    // the A-stage wait of chunk gc - 2 already covered chunk gc - 4)
+    const int64_t my_tiles = (int64_t)blockIdx.x < (p.B * ((p.T + MEL_TM - 1) / MEL_TM)) ? ((p.B * ((p.T + MEL_TM - 1) / MEL_TM)) - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t my_chunks = my_tiles * n_chunks;
+    int64_t gc = 0;
+    auto issue_b = [&](int64_t g) {          // thread 0 only
+        const int bs = (int)(g % MEL_BSTAGES);
+        const int bank_chunk = (int)(g % n_chunks);
+        const uint32_t bytes = B_STAGE;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + 3 + bs)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(b_ring + bs * B_STAGE)),
+                     "l"(p.bank_packed + (size_t)bank_chunk * (2 * MEL_N * MEL_KC)), "r"(bytes), "r"(smem_u32(mbar + 3 + bs))
+                     : "memory");
+    };
+    if (tid == 0) {
+        if (my_chunks > 0) issue_b(0);
+        if (my_chunks > 1) issue_b(1);
+    }
 
     const int64_t tiles_per_clip = (p.T + MEL_TM - 1) / MEL_TM;
     const int64_t n_tiles = p.B * tiles_per_clip;
@@ -112,8 +134,9 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t b = tile / tiles_per_clip;
         const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
-        for (int kc = 0; kc < n_chunks; ++kc, stage ^= 1) {
-            unsigned char* st = smem + stage * STAGE;
+        for (int kc = 0; kc < n_chunks; ++kc, stage ^= 1, ++gc) {
+            unsigned char* st = smem + stage * A_STAGE;
+            const int bs = (int)(gc % MEL_BSTAGES);
             // the MMAs that read this stage two chunks ago have completed
             if (used[stage]) {
                 mbar_wait_parity(mbar + stage, ph_free[stage]);
@@ -121,15 +144,8 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
                 used[stage] = 0;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // B chunk: one bulk copy (hi block, lo block: 2 x 128 x MEL_KC floats), completing on the stage's "landed" mbarrier
-            if (tid == 0) {
-                const uint32_t bytes = 2 * MEL_B_BYTES;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + 2 + stage)), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_u32(st + 2 * MEL_A_BYTES)),
-                             "l"(p.bank_packed + (size_t)kc * (2 * MEL_N * MEL_KC)), "r"(bytes), "r"(smem_u32(mbar + 2 + stage))
-                             : "memory");
-            }
+            // the bank chunk two ahead: its stage's last reader (chunk gc - 2, when MEL_BSTAGES = 4) completed with the wait above
+            if (tid == 0 && gc + 2 < my_chunks) issue_b(gc + 2);
             // A chunk: split and store
             unsigned char* ah = st;
             unsigned char* al = st + MEL_A_BYTES;
@@ -154,9 +170,9 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
             if (warp == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    mbar_wait_parity(mbar + 2 + stage, ph_b[stage]);         // the bank chunk has landed
+                    mbar_wait_parity(mbar + 3 + bs, (ph_b >> bs) & 1u);      // the bank chunk has landed
                     const uint32_t sa_hi = smem_u32(ah), sa_lo = smem_u32(al);
-                    const uint32_t sb_hi = smem_u32(st + 2 * MEL_A_BYTES), sb_lo = sb_hi + MEL_B_BYTES;
+                    const uint32_t sb_hi = smem_u32(b_ring + bs * B_STAGE), sb_lo = sb_hi + MEL_B_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < MEL_KC / 8; ++ks) {         // one MMA consumes K = 8 (two core matrices of 4 TF32)
                         const uint32_t ko = (uint32_t)ks * 256;
@@ -166,14 +182,14 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + stage)) : "memory");
                     if (kc == n_chunks - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 4)) : "memory");
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 2)) : "memory");
                 }
                 __syncwarp();
             }
-            ph_b[stage] ^= 1;
+            ph_b ^= 1u << bs;
             used[stage] = 1;
         }
-        mbar_wait_parity(mbar + 4, ph_done);
+        mbar_wait_parity(mbar + 2, ph_done);
         ph_done ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // epilogue: a warp reads its TMEM lane quadrant (32 frames); warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones
@@ -228,7 +244,7 @@ extern "C" ACIDS_API int acids_mel_tc(const float* spec, int64_t B, int64_t n_fr
     tc::mel_tc_pack_kernel<<<(n_chunks * 16 < 1024 ? n_chunks * 16 : 1024), 256, 0, st>>>(bank, n_bins, n_mels, n_chunks, static_cast<float*>(workspace));
     ACIDS_CHECK_LAUNCH("mel_tc_pack");
     tc::MelParams p{spec, B, n_frames, n_bins, static_cast<const float*>(workspace), n_mels, out};
-    const size_t smem = (size_t)2 * (2 * tc::MEL_A_BYTES + 2 * tc::MEL_B_BYTES) + 64;
+    const size_t smem = (size_t)2 * 2 * tc::MEL_A_BYTES + (size_t)tc::MEL_BSTAGES * 2 * tc::MEL_B_BYTES + 128;
     ACIDS_REQUIRE(cudaFuncSetAttribute(tc::mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess, ACIDS_ECUDA,
                   "mel_tc: cannot reserve %zu B of shared memory", smem);
     int64_t grid = B * ((n_frames + tc::MEL_TM - 1) / tc::MEL_TM);
