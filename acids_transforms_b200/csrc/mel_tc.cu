@@ -220,6 +220,183 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MEL_N) : "memory");
 }
 
+
+// ---- warp-specialised variant: no CTA barrier inside the tile ------------------------------------------------------------
+// Warps 4-7 are PRODUCERS (load, split, store A chunks into a ring of WS_ASTAGES stages, `a_full` arrive per warp), lane 0 of
+// warp 0 is the MMA ISSUER (waits `a_full` + the bank chunk's `b_full`, issues the MMAs, `tcgen05.commit` -> `a_free`; it also
+// keeps the bank ring two chunks ahead), warps 0-3 run the EPILOGUE of a tile (each its TMEM lane quadrant) and hand the
+// accumulator back through `acc_free`.  Stages change hands through mbarriers only, so the producers run ahead of the tensor
+// core by up to WS_ASTAGES chunks and across tile boundaries (the next tile's chunks are filled during the epilogue).
+constexpr int WS_ASTAGES = 3;
+
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(MEL_THREADS, 2) mel_tc_ws_kernel(const MelParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t A_STAGE = 2 * MEL_A_BYTES, B_STAGE = 2 * MEL_B_BYTES;
+    unsigned char* a_ring = smem;
+    unsigned char* b_ring = smem + WS_ASTAGES * A_STAGE;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + MEL_BSTAGES * B_STAGE);
+    uint64_t* a_free = a_full + WS_ASTAGES;
+    uint64_t* b_full = a_free + WS_ASTAGES;
+    uint64_t* acc_done = b_full + MEL_BSTAGES;
+    uint64_t* acc_free = acc_done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = p.F;
+    const int n_chunks = (F + MEL_KC - 1) / MEL_KC;
+    static_assert(MEL_KC == 16, "the producer mapping below covers a 128 x 16 chunk with four warps");
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(MEL_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        auto init = [](uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); };
+        for (int i = 0; i < WS_ASTAGES; ++i) { init(a_full + i, 4); init(a_free + i, 1); }
+        for (int i = 0; i < MEL_BSTAGES; ++i) init(b_full + i, 1);
+        init(acc_done, 1);
+        init(acc_free, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    const int64_t tiles_per_clip = (p.T + MEL_TM - 1) / MEL_TM;
+    const int64_t n_tiles = p.B * tiles_per_clip;
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t my_chunks = my_tiles * n_chunks;
+
+    if (warp >= 4) {
+        // ---------------- producers ----------------
+        const int pw = warp - 4;
+        const int r8 = lane & 7, kbl = lane >> 3;
+        constexpr int U = 4;                                   // 16 pieces (8 frames x 16 bins) per chunk, four per warp
+        float v[U][4];
+        auto load_chunk = [&](int64_t tile, int kc) {
+            const int64_t b = tile / tiles_per_clip;
+            const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t t = t0 + (pw * U + u) * 8 + r8;
+                const int k = kc * MEL_KC + kbl * 4;
+                const float* src = p.spec + (b * p.T + t) * (int64_t)F + k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[u][j] = (t < p.T && k + j < F) ? __ldg(src + j) : 0.f;
+            }
+        };
+        int64_t gc = 0;
+        if (my_tiles > 0) load_chunk(blockIdx.x, 0);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < n_chunks; ++kc, ++gc) {
+                const int as = (int)(gc % WS_ASTAGES);
+                if (gc >= WS_ASTAGES) mbar_wait_parity(a_free + as, (uint32_t)((gc / WS_ASTAGES - 1) & 1));
+                unsigned char* ah = a_ring + as * A_STAGE;
+                unsigned char* al = ah + MEL_A_BYTES;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float4 hi, lo;
+                    split_tf32(v[u][0], hi.x, lo.x);
+                    split_tf32(v[u][1], hi.y, lo.y);
+                    split_tf32(v[u][2], hi.z, lo.z);
+                    split_tf32(v[u][3], hi.w, lo.w);
+                    const uint32_t off = (uint32_t)((pw * U + u) * (MEL_KC >> 2) + kbl) * 128 + (uint32_t)r8 * 16;
+                    *reinterpret_cast<float4*>(ah + off) = hi;
+                    *reinterpret_cast<float4*>(al + off) = lo;
+                }
+                if (kc + 1 < n_chunks) load_chunk(tile, kc + 1);
+                else if (tile + gridDim.x < n_tiles) load_chunk(tile + gridDim.x, 0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_plain(a_full + as);
+            }
+        }
+    } else {
+        // ---------------- MMA issuer (warp 0, lane 0) and epilogue (warps 0-3) ----------------
+        const uint32_t idesc = make_idesc_mn(MEL_TM, MEL_N);
+        constexpr uint32_t sbo = (uint32_t)(MEL_KC >> 2) * 128;
+        auto issue_b = [&](int64_t g) {
+            const int bs = (int)(g % MEL_BSTAGES);
+            const int bank_chunk = (int)(g % n_chunks);
+            const uint32_t bytes = B_STAGE;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b_full + bs)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(b_ring + bs * B_STAGE)),
+                         "l"(p.bank_packed + (size_t)bank_chunk * (2 * MEL_N * MEL_KC)), "r"(bytes), "r"(smem_u32(b_full + bs))
+                         : "memory");
+        };
+        if (tid == 0) {
+            if (my_chunks > 0) issue_b(0);
+            if (my_chunks > 1) issue_b(1);
+        }
+        int64_t gc = 0, ti = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            if (warp == 0) {
+                if (lane == 0) {
+                    if (ti > 0) mbar_wait_parity(acc_free, (uint32_t)((ti - 1) & 1));       // the epilogue has read the accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kc = 0; kc < n_chunks; ++kc, ++gc) {
+                        const int as = (int)(gc % WS_ASTAGES), bs = (int)(gc % MEL_BSTAGES);
+                        // bank chunk gc + 2 goes into the stage chunk gc - 2 read: those MMAs have completed when its A stage is free
+                        if (gc + 2 < my_chunks) {
+                            if (gc >= 2) mbar_wait_parity(a_free + (int)((gc - 2) % WS_ASTAGES), (uint32_t)(((gc - 2) / WS_ASTAGES) & 1));
+                            issue_b(gc + 2);
+                        }
+                        mbar_wait_parity(a_full + as, (uint32_t)((gc / WS_ASTAGES) & 1));
+                        mbar_wait_parity(b_full + bs, (uint32_t)((gc / MEL_BSTAGES) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa_hi = smem_u32(a_ring + as * A_STAGE), sa_lo = sa_hi + MEL_A_BYTES;
+                        const uint32_t sb_hi = smem_u32(b_ring + bs * B_STAGE), sb_lo = sb_hi + MEL_B_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < MEL_KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * 256;
+                            mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, (kc | ks) ? 1u : 0u);
+                            mma_tf32(tmem_d, make_desc(sa_lo + ko, 128, sbo), make_desc(sb_hi + ko, 128, sbo), idesc, 1);
+                            mma_tf32(tmem_d, make_desc(sa_hi + ko, 128, sbo), make_desc(sb_lo + ko, 128, sbo), idesc, 1);
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(a_free + as)) : "memory");
+                        if (kc == n_chunks - 1)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(acc_done)) : "memory");
+                    }
+                }
+                __syncwarp();
+            }
+            // epilogue of this tile: warp w reads TMEM lanes 32 w ... 32 w + 31 (frames), all 128 columns in chunks of 16
+            mbar_wait_parity(acc_done, (uint32_t)(ti & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t b = tile / tiles_per_clip;
+            const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
+            for (int chunk = 0; chunk * 16 < p.n_mels; ++chunk) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(chunk * 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int64_t t = t0 + warp * 32 + lane;
+                if (t < p.T) {
+                    float* o = p.out + (b * p.n_mels + chunk * 16) * p.T + t;
+#pragma unroll
+                    for (int n = 0; n < 16; ++n)
+                        if (chunk * 16 + n < p.n_mels) stg_stream1(o + (int64_t)n * p.T, __uint_as_float(r[n]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_plain(acc_free);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MEL_N) : "memory");
+}
+
 }  // namespace tc
 }  // namespace acids
 
@@ -244,12 +421,20 @@ extern "C" ACIDS_API int acids_mel_tc(const float* spec, int64_t B, int64_t n_fr
     tc::mel_tc_pack_kernel<<<(n_chunks * 16 < 1024 ? n_chunks * 16 : 1024), 256, 0, st>>>(bank, n_bins, n_mels, n_chunks, static_cast<float*>(workspace));
     ACIDS_CHECK_LAUNCH("mel_tc_pack");
     tc::MelParams p{spec, B, n_frames, n_bins, static_cast<const float*>(workspace), n_mels, out};
-    const size_t smem = (size_t)2 * 2 * tc::MEL_A_BYTES + (size_t)tc::MEL_BSTAGES * 2 * tc::MEL_B_BYTES + 128;
-    ACIDS_REQUIRE(cudaFuncSetAttribute(tc::mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess, ACIDS_ECUDA,
-                  "mel_tc: cannot reserve %zu B of shared memory", smem);
+    // the warp-specialised kernel is correct and measured SLOWER (0.340 vs 0.305 ms at the cfg-3 shape): four producer warps
+    // per CTA do not keep up — the kernel is bound by the A operand's path (scalar loads of rows that are not 16-byte aligned,
+    // split, store), not by the CTA barrier.  Opt-in: -DACIDS_MEL_TC_WS=1 or ACIDS_MEL_TC_WS=1 in the environment.
+#ifndef ACIDS_MEL_TC_WS
+#define ACIDS_MEL_TC_WS 0
+#endif
+    static const bool ws = tc::MEL_KC == 16 && (ACIDS_MEL_TC_WS || getenv("ACIDS_MEL_TC_WS") != nullptr);
+    const size_t smem = (size_t)(ws ? tc::WS_ASTAGES : 2) * 2 * tc::MEL_A_BYTES + (size_t)tc::MEL_BSTAGES * 2 * tc::MEL_B_BYTES + 128;
+    ACIDS_REQUIRE(cudaFuncSetAttribute(ws ? tc::mel_tc_ws_kernel : tc::mel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                  ACIDS_ECUDA, "mel_tc: cannot reserve %zu B of shared memory", smem);
     int64_t grid = B * ((n_frames + tc::MEL_TM - 1) / tc::MEL_TM);
     if (grid > (int64_t)ACIDS_MEL_TC_CTAS * num_sms()) grid = (int64_t)ACIDS_MEL_TC_CTAS * num_sms();
-    tc::mel_tc_kernel<<<(unsigned)grid, tc::MEL_THREADS, smem, st>>>(p);
+    if (ws) tc::mel_tc_ws_kernel<<<(unsigned)grid, tc::MEL_THREADS, smem, st>>>(p);
+    else tc::mel_tc_kernel<<<(unsigned)grid, tc::MEL_THREADS, smem, st>>>(p);
     ACIDS_CHECK_LAUNCH("mel_tc");
     return ACIDS_OK;
 }
