@@ -30,6 +30,7 @@ constexpr int MEL_KC = ACIDS_MEL_TC_KC;   // bins per pipeline stage (16: 96 KB 
 constexpr int MEL_THREADS = 256;
 constexpr uint32_t MEL_A_BYTES = MEL_TM * MEL_KC * 4;      // one of hi / lo of an A chunk: 16 KB
 constexpr uint32_t MEL_B_BYTES = MEL_N * MEL_KC * 4;       // one of hi / lo of a B chunk
+constexpr int MEL_DEPTH = 3;                               // chunks of the spectrum a thread keeps in flight
 constexpr int MEL_BSTAGES = 4;                             // B ring: a chunk's copy is issued two chunks before its MMAs
 
 struct MelParams {
@@ -92,9 +93,7 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
     const int64_t my_tiles = (int64_t)blockIdx.x < (p.B * ((p.T + MEL_TM - 1) / MEL_TM)) ? ((p.B * ((p.T + MEL_TM - 1) / MEL_TM)) - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int64_t my_chunks = my_tiles * n_chunks;
     int64_t gc = 0;
-    auto issue_b = [&](int64_t g) {          // thread 0 only
-        const int bs = (int)(g % MEL_BSTAGES);
-        const int bank_chunk = (int)(g % n_chunks);
+    auto issue_b = [&](int bs, int bank_chunk) {          // thread 0 only: bank chunk -> B stage bs
         const uint32_t bytes = B_STAGE;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar + 3 + bs)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(b_ring + bs * B_STAGE)),
@@ -102,8 +101,8 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
                      : "memory");
     };
     if (tid == 0) {
-        if (my_chunks > 0) issue_b(0);
-        if (my_chunks > 1) issue_b(1);
+        if (my_chunks > 0) issue_b(0, 0);
+        if (my_chunks > 1) issue_b(1, 1 % n_chunks);
     }
 
     const int64_t tiles_per_clip = (p.T + MEL_TM - 1) / MEL_TM;
@@ -114,27 +113,50 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
     constexpr int U = 16 * HALVES / (MEL_THREADS / 32);       // pieces per warp
     static_assert(U >= 1 && U * (MEL_THREADS / 32) == 16 * HALVES, "a pass of the warps covers a chunk");
     const int r8 = lane & 7, kbl = lane >> 3;
-    auto load_chunk = [&](int64_t tile, int kc, float (&v)[U][4]) {
-        const int64_t b = tile / tiles_per_clip;
-        const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
+    // base = first frame of the tile, rows = frames of the clip from there on (both fixed per tile: no division per chunk)
+    auto load_chunk = [&](const float* __restrict__ base, int rows, int kc, float (&v)[U][4]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int piece = warp * U + u;                     // frame group (16) x group of four blocks (HALVES)
-            const int g = piece / HALVES, half = piece % HALVES;
-            const int64_t t = t0 + g * 8 + r8;
+            const int fg = piece / HALVES, half = piece % HALVES;
+            const int r = fg * 8 + r8;
             const int k = kc * MEL_KC + (half * 4 + kbl) * 4;
-            const float* src = p.spec + (b * p.T + t) * (int64_t)F + k;
+            const float* src = base + (int64_t)r * F + k;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[u][j] = (t < p.T && k + j < F) ? __ldg(src + j) : 0.f;
+            for (int j = 0; j < 4; ++j) v[u][j] = (r < rows && k + j < F) ? __ldg(src + j) : 0.f;
         }
     };
-    float v[U][4];
-    int stage = 0;
-    if ((int64_t)blockIdx.x < n_tiles) load_chunk(blockIdx.x, 0, v);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto tile_base = [&](int64_t tile, const float*& base, int& rows) {
         const int64_t b = tile / tiles_per_clip;
         const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
-        for (int kc = 0; kc < n_chunks; ++kc, stage ^= 1, ++gc) {
+        base = p.spec + (b * p.T + t0) * (int64_t)F;
+        rows = (int)((p.T - t0) < MEL_TM ? (p.T - t0) : MEL_TM);
+    };
+    // The kernel is bound by the bytes it keeps in flight (Little's law: with one chunk of prefetch a thread has 32 bytes out, an
+    // SM 16 KB, i.e. ~2.4 TB/s at a microsecond of latency): MEL_DEPTH register sets hold the chunks gc + 1 ... gc + MEL_DEPTH
+    // while chunk gc is split and stored.  The chunks of this CTA are numbered across its tiles, so the prefetch runs through
+    // tile boundaries; the loop is unrolled by MEL_DEPTH to keep the register sets statically indexed.
+    // two cursors over the CTA's chunk sequence, advanced without divisions: the next chunk to LOAD and the chunk being multiplied
+    int64_t l_tile = blockIdx.x, s_tile = blockIdx.x;
+    int l_kc = 0, s_kc = 0, l_rows = 0;
+    const float* l_base = p.spec;
+    int64_t loaded = 0;
+    if (my_chunks > 0) tile_base(l_tile, l_base, l_rows);
+    auto load_next = [&](float (&vv)[U][4]) {
+        if (loaded >= my_chunks) return;
+        load_chunk(l_base, l_rows, l_kc, vv);
+        ++loaded;
+        if (++l_kc == n_chunks) {
+            l_kc = 0;
+            l_tile += gridDim.x;
+            if (loaded < my_chunks) tile_base(l_tile, l_base, l_rows);
+        }
+    };
+    auto step = [&](float (&v)[U][4]) {
+        const int64_t tile = s_tile;
+        const int kc = s_kc;
+        const int stage = (int)(gc & 1);
+        {
             unsigned char* st = smem + stage * A_STAGE;
             const int bs = (int)(gc % MEL_BSTAGES);
             // the MMAs that read this stage two chunks ago have completed
@@ -145,25 +167,24 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // the bank chunk two ahead: its stage's last reader (chunk gc - 2, when MEL_BSTAGES = 4) completed with the wait above
-            if (tid == 0 && gc + 2 < my_chunks) issue_b(gc + 2);
+            if (tid == 0 && gc + 2 < my_chunks) issue_b((bs + 2) % MEL_BSTAGES, (kc + 2) % n_chunks);
             // A chunk: split and store
             unsigned char* ah = st;
             unsigned char* al = st + MEL_A_BYTES;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int piece = warp * U + u;
-                const int g = piece / HALVES, half = piece % HALVES;
+                const int fg = piece / HALVES, half = piece % HALVES;
                 float4 hi, lo;
                 split_tf32(v[u][0], hi.x, lo.x);
                 split_tf32(v[u][1], hi.y, lo.y);
                 split_tf32(v[u][2], hi.z, lo.z);
                 split_tf32(v[u][3], hi.w, lo.w);
-                const uint32_t off = (uint32_t)(g * (MEL_KC >> 2) + half * 4 + kbl) * 128 + (uint32_t)r8 * 16;   // row g * 8 + r8, block half * 4 + kbl
+                const uint32_t off = (uint32_t)(fg * (MEL_KC >> 2) + half * 4 + kbl) * 128 + (uint32_t)r8 * 16;   // row fg * 8 + r8, block half * 4 + kbl
                 *reinterpret_cast<float4*>(ah + off) = hi;
                 *reinterpret_cast<float4*>(al + off) = lo;
             }
-            if (kc + 1 < n_chunks) load_chunk(tile, kc + 1, v);
-            else if (tile + gridDim.x < n_tiles) load_chunk(tile + gridDim.x, 0, v);
+            load_next(v);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -189,6 +210,12 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
             ph_b ^= 1u << bs;
             used[stage] = 1;
         }
+        ++gc;
+        if (++s_kc < n_chunks) return;
+        s_kc = 0;
+        s_tile += gridDim.x;
+        const int64_t b = tile / tiles_per_clip;
+        const int64_t t0 = (tile - b * tiles_per_clip) * MEL_TM;
         mbar_wait_parity(mbar + 2, ph_done);
         ph_done ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -216,6 +243,16 @@ __global__ void __launch_bounds__(MEL_THREADS, ACIDS_MEL_TC_CTAS) mel_tc_kernel(
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    float va[U][4], vb[U][4], vc[U][4];
+    static_assert(MEL_DEPTH == 3, "three register sets below");
+    load_next(va);
+    load_next(vb);
+    load_next(vc);
+    while (gc < my_chunks) {
+        step(va);
+        if (gc < my_chunks) step(vb);
+        if (gc < my_chunks) step(vc);
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MEL_N) : "memory");
 }
